@@ -1,0 +1,156 @@
+/*
+ * minrms_b200.h -- C ABI of the B200-native MINRMS per-orientation search.
+ *
+ * Drop-in boundary: the reference has no FFI; its seam is the abstract C++ class
+ * minrms::SearchOr (bin/minrms/search_or.h:57-130: Search(og,start,stop), Refine(),
+ * WriteMSF(), WriteChimeraInfo()).  A `SearchOrCuda : SearchOr` (see INTEGRATION.md and
+ * minrms_b200/host/search_or_cuda.cc) implements Search/Refine by calling the entry
+ * points below; everything else of the reference (CLI, parser, PDB I/O, MSF writers)
+ * is unchanged host code.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; caller owns every host buffer; the context owns
+ *    device memory, streams and events.
+ *  - every function returns 0 on success, non-zero on error; mr_last_error() returns
+ *    the message (the reference prints to cerr and exit(-1), lib/global_utils/ERR.h:20-21;
+ *    the C++ wrapper turns a non-zero return into ERR(...)).
+ *  - coordinates are float[npoints][3] with npoints = residues * nb, exactly the arrays
+ *    the reference flattens at bin/minrms/search_or_dyn3d.cc:186-224; A = molecule 1
+ *    (fixed), B = molecule 2 (moved).
+ *  - a transform is 12 floats, row-major Matrix3x4 (lib/vect_3d/vect_3d.h:66-92,
+ *    lib/or_gen/or_gen.h:73-78): x' = M[r][0..2].x + M[r][3].
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MINRMS_B200_H
+#define MINRMS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_UPPER_BOUND 1.0e26f /* DistanceMetric::UPPER_BOUND, lib/dyn/distance_metric.cc:49 */
+
+/* The scalars SearchOrDyn3d::Settings carries to the hot path
+ * (bin/minrms/search_or_dyn3d.h:159-215, bin/minrms/search_or.h:149-308). */
+typedef struct mr_params {
+  int32_t nb;          /* atoms per residue, Biopolymer::Residue::NumBackboneAtoms() */
+  int32_t n_min;       /* settings.n_min  (-minN) */
+  int32_t n_max;       /* settings.n_max  (-maxN) */
+  float   max_dist;    /* settings.dyn3d_max_dist, < 0 = none (-max-dist) */
+  float   max_rmsd;    /* settings.dyn3d_max_rmsd, < 0 = none (-max-rmsd) */
+  int32_t use_filter;  /* settings.orientation_filter_nw (-of / -OF) */
+  float   of_dist;     /* settings.orientation_filter_nw_max_dist */
+  int32_t of_min;      /* settings.orientation_filter_nw_min_num_matches */
+  int32_t refine_while_searching; /* settings.refine_while_searching (-ir / -IR) */
+} mr_params;
+
+typedef struct mr_ctx mr_ctx;
+
+/* Replaces the SearchOrDyn3d constructor (bin/minrms/search_or_dyn3d.cc:109-234):
+ * uploads both coordinate arrays and sizes the device work space on CUDA device `device`. */
+int mr_create(mr_ctx **out, const float *A, int32_t m, const float *B, int32_t nB,
+              const mr_params *params, int32_t device);
+void mr_destroy(mr_ctx *ctx);
+/* message of the last failure on ctx (or of the last failed mr_create when ctx == NULL) */
+const char *mr_last_error(const mr_ctx *ctx);
+
+/* The per-size best table, exactly SearchOrDyn3d::aaSumSqdDists / aaTransforms /
+ * aaAlignments[0][n - n_min] (bin/minrms/search_or_dyn3d.h:293-310).  R = n_max-n_min+1,
+ * N = min(m, nB).  Slot r holds size n = n_min + r.
+ *   ssd[r]          selection score (MR_UPPER_BOUND = no solution)
+ *   T[12 r ..]      stored transform
+ *   pairs[2 N r ..] n pairs (i,j), 0-based indices into A/B residues, ascending
+ *   o_id[r]         id of the winning orientation (-1 none, -2 produced by mr_refine)
+ */
+typedef struct mr_best {
+  float   *ssd;
+  float   *T;
+  int16_t *pairs;
+  int64_t *o_id;
+} mr_best;
+
+/* Initialise a caller-allocated table (search_or_dyn3d.cc:165-184). */
+int mr_best_init(const mr_ctx *ctx, mr_best *best);
+
+/* Replaces SearchOrDyn3d::Search -> FirstPass over orientations
+ * (bin/minrms/search_or_dyn3d.cc:283-299, 1643-1946) for the `count` transforms in
+ * orient12 (host memory), whose ids are first_id, first_id+1, ...  The table is updated
+ * with the reference's rule "strictly lower score wins, lowest id wins ties"
+ * (search_or_dyn3d.cc:1825-1835), so calls over disjoint id ranges -- on one GPU or on
+ * several, in any order -- merge to the sequential result.  Host->device copy of the
+ * orientations and device->host copy of the table are inside the call. */
+int mr_search(mr_ctx *ctx, const float *orient12, int64_t count, int64_t first_id,
+              mr_best *best);
+
+/* Same search with the orientation list already resident in device memory
+ * (uploaded once with mr_upload_orientations); nothing is copied to the host until
+ * mr_fetch_best.  Used to time the kernels alone. */
+int mr_upload_orientations(mr_ctx *ctx, const float *orient12, int64_t count);
+int mr_search_resident(mr_ctx *ctx, int64_t first, int64_t count, int64_t first_id);
+int mr_reset_best(mr_ctx *ctx);
+int mr_fetch_best(mr_ctx *ctx, mr_best *best);
+
+/* Per-size sort keys of the device-side table: key[r] = (float_bits(ssd) << 32) | o_id.
+ * Non-negative IEEE floats order like unsigned integers, so an element-wise integer MIN
+ * over ranks (one small NCCL all-reduce) reproduces the reference's selection rule; the
+ * rank whose key equals the reduced key owns the payload for that size. */
+int mr_fetch_keys(mr_ctx *ctx, uint64_t *keys /* [R] */);
+
+/* One orientation, the body of the FirstPass / Refine n-loop, with every per-size
+ * result returned (used by Refine and by the parity tests).  Arrays are indexed n-1:
+ *   cost[N], valid[N] (1 = the reference would have compared this size), ssd[N],
+ *   T[12 N], pairs[2 N N]; any pointer may be NULL.  *n_last = last layer the reference
+ *   computes (0 = rejected by the -of filter), *nw_matches = NW filter count or -1. */
+int mr_eval_one(mr_ctx *ctx, const float *T12, int32_t apply_filter, int32_t *n_last,
+                int32_t *nw_matches, float *cost, uint8_t *valid, float *ssd, float *T,
+                int16_t *pairs);
+
+/* Replaces SearchOrDyn3d::Refine (bin/minrms/search_or_dyn3d.cc:2261-2658, REFINE_BEST,
+ * one solution per size).  max_iters < 0 = until convergence.  *n_evals = number of
+ * single-orientation evaluations performed. */
+int mr_refine(mr_ctx *ctx, mr_best *best, int32_t max_iters, int32_t *n_evals);
+
+/* Replaces OrientationGenerator::GenerateOrientationsUsingFragmentMatching + the
+ * std::random_shuffle that follows (lib/or_gen/or_gen.cc:237-587, 179).
+ * intervals: n_intervals x {startA, endA, startB, endB} inclusive 0-based residue
+ * indices (NULL/0 = whole-vs-whole, i.e. -HS).  cutoff_rmsd < 0 = none.
+ * Pass out12 = NULL to query the count.  Order = the reference's shuffled order when
+ * shuffle != 0, row-major (I,J) otherwise. */
+int mr_gen_orientations(mr_ctx *ctx, int32_t frag_len, float cutoff_rmsd,
+                        const int32_t *intervals, int32_t n_intervals, int32_t shuffle,
+                        float *out12, int64_t cap, int64_t *count);
+
+/* Least-squares superposition of np point pairs (Superimpose::FindTransformMinRMSD,
+ * lib/superimpose/superimpose.cc:17-287) for `batch` independent problems on the GPU.
+ * fixed/moveable: batch x np x 3 floats; T: batch x 12; rmsd: batch. */
+int mr_superimpose_batch(mr_ctx *ctx, int32_t batch, int32_t np, const float *fixed,
+                         const float *moveable, float *T, float *rmsd);
+
+/* Counters for the benchmark (reset by mr_reset_stats). */
+typedef struct mr_stats {
+  int64_t kernel_launches;   /* kernels of this library launched */
+  int64_t orientations;      /* orientations submitted */
+  int64_t orientations_dp;   /* orientations that reached the 3-D DP (passed -of) */
+  int64_t dp_cells;          /* Dyn3d cell updates executed on the GPU */
+  int64_t nw_cells;          /* NW filter cell updates executed on the GPU */
+  double  dp_kernel_ms;      /* device time inside the 3-D DP kernel (CUDA events) */
+  int64_t dp_kernel_launches;
+  double  nw_kernel_ms;
+  double  tb_kernel_ms;      /* traceback + Kabsch kernel */
+  int64_t h2d_bytes, d2h_bytes;
+} mr_stats;
+int mr_get_stats(mr_ctx *ctx, mr_stats *out);
+int mr_reset_stats(mr_ctx *ctx);
+
+/* Tuning knobs (by name), e.g. "dp_kernel" = 0 auto / 1 general / 2 tiled. */
+int mr_set_option(mr_ctx *ctx, const char *name, int64_t value);
+
+/* number of Dyn3d cells per orientation for all layers 1..n_max */
+int64_t mr_dp_cells_per_orientation(int32_t m, int32_t nB, int32_t n_min, int32_t n_max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

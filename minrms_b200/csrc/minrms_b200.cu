@@ -1,0 +1,825 @@
+// minrms_b200.cu -- C ABI (include/minrms_b200.h) over the sm_100a kernels.
+// Host side of the per-orientation search: chunking, streams, events, result tables.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//             -Xcompiler -fPIC -shared  (see __graft_entry__.build()).
+#include "../../include/minrms_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "mr_kernels.cuh"
+#include "mr_dp_tiled.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int kind;  // 0 dp, 1 nw, 2 tb
+};
+
+}  // namespace
+
+struct mr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop;
+  mr_params hp;
+  MrDevParams P;
+  int m = 0, nB = 0, N = 0, R = 0, NP = 0;
+  TbColumns Lc;
+  float *dA = nullptr, *dB = nullptr;
+  // resident orientation list
+  float* d_orient = nullptr;
+  int64_t orient_cap = 0, orient_count = 0;
+  // per-chunk work space
+  int chunk_cap = 0;
+  size_t tb_words = 0;  // per orientation (largest layout in use)
+  uint32_t* d_tb = nullptr;
+  float *d_cost = nullptr, *d_ssd = nullptr;
+  int *d_surv = nullptr, *d_surv_count = nullptr, *d_nw = nullptr, *d_nlast = nullptr;
+  unsigned char* d_valid = nullptr;
+  float* d_rowcost = nullptr;
+  unsigned short* d_rowcnt = nullptr;
+  int nw_threads_cap = 0;
+  short2* d_scratch = nullptr;
+  size_t scratch_threads = 0;
+  float* d_gcol = nullptr;
+  int dp_grid_cap = 0;
+  int use_gcol = 0;
+  size_t dp_smem = 0;
+  unsigned long long* d_keys = nullptr;
+  // winner / eval payload
+  float* d_orient_w = nullptr;  // [max(R,1)] transforms
+  int* d_widx = nullptr;
+  int2* d_items = nullptr;
+  float* d_Tout = nullptr;      // [max(R,NP)*12]
+  short* d_pairs_out = nullptr; // [max(R,NP)*2N]
+  short2* d_pairs_in = nullptr; // [N]
+  int* h_pinned = nullptr;      // surv counts per chunk
+  int h_pinned_cap = 0;
+  long long id_offset = 0;
+  bool id_offset_set = false;
+  int64_t opt_dp_kernel = 0;    // 0 auto, 1 general, 2 tiled
+  int64_t opt_budget_mb = 16384;
+  int64_t opt_chunk = 0;
+  mr_stats st;
+  std::vector<EventPair> events;
+  size_t events_used = 0;
+  std::vector<std::pair<int, int>> pending_counts;  // (pinned slot, chunk count)
+  std::string err;
+  MrTiledPlan tiled;
+};
+
+namespace {
+
+#define MR_FAIL(ctx, ...)                               \
+  do {                                                  \
+    char _b[512];                                       \
+    snprintf(_b, sizeof _b, __VA_ARGS__);               \
+    (ctx)->err = _b;                                    \
+    return 1;                                           \
+  } while (0)
+
+#define CU(ctx, expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      MR_FAIL(ctx, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,  \
+              cudaGetErrorString(_e));                                                      \
+    }                                                                                       \
+  } while (0)
+
+const unsigned long long KEY_NONE = ((unsigned long long)0x6aa56fa6u /* bits(1e26f) */ << 32) | 0xffffffffull;
+
+float metric_cutoff(float d, int nb) {  // lib/dyn/distance_metric.cc:76-87
+  if (d < 0.0f) return MR_UPPER_BOUND;
+  return (d * d) * (float)nb;
+}
+
+int64_t dp_cells(int m, int nB, int n_min, int n_max) {
+  int wA = m - n_min + 1, wB = nB - n_min + 1;
+  int64_t c = 0;
+  for (int n = 1; n <= n_max; n++)
+    c += (int64_t)(std::min(m, n + wA - 1) - n + 1) * (int64_t)(std::min(nB, n + wB - 1) - n + 1);
+  return c;
+}
+
+int64_t nw_cells(int m, int nB, int of_min) {
+  int w0 = m - of_min + 1, w1 = nB - of_min + 1;
+  int64_t c = 0;
+  for (int i = 1; i <= m; i++) {
+    int jlo = (i <= w0) ? 1 : i - w0 + 1;
+    int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
+    c += jhi - jlo + 1;
+  }
+  return c;
+}
+
+EventPair* next_events(mr_ctx* c, int kind) {
+  if (c->events_used == c->events.size()) {
+    EventPair e;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return nullptr;
+    c->events.push_back(e);
+  }
+  EventPair* e = &c->events[c->events_used++];
+  e->kind = kind;
+  return e;
+}
+
+// fold finished event pairs and pinned survivor counts into the stats (stream must be idle)
+void harvest(mr_ctx* c) {
+  for (size_t k = 0; k < c->events_used; k++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->events[k].a, c->events[k].b) == cudaSuccess) {
+      if (c->events[k].kind == 0) { c->st.dp_kernel_ms += ms; c->st.dp_kernel_launches++; }
+      else if (c->events[k].kind == 1) c->st.nw_kernel_ms += ms;
+      else c->st.tb_kernel_ms += ms;
+    }
+  }
+  c->events_used = 0;
+  const int64_t per = dp_cells(c->m, c->nB, c->hp.n_min, c->hp.n_max);
+  for (auto& pc : c->pending_counts) {
+    c->st.orientations_dp += c->h_pinned[pc.first];
+    c->st.dp_cells += per * (int64_t)c->h_pinned[pc.first];
+  }
+  c->pending_counts.clear();
+}
+
+int ensure_orient_cap(mr_ctx* c, int64_t count) {
+  if (count <= c->orient_cap) return 0;
+  if (c->d_orient) cudaFree(c->d_orient);
+  c->d_orient = nullptr;
+  c->orient_cap = 0;
+  CU(c, cudaMalloc(&c->d_orient, sizeof(float) * 12 * (size_t)count));
+  c->orient_cap = count;
+  return 0;
+}
+
+bool use_tiled(const mr_ctx* c) {
+  if (c->opt_dp_kernel == 1) return false;
+  return c->tiled.ok;
+}
+
+// (re)allocate the per-chunk work space for chunks of up to `want` orientations
+int ensure_chunk(mr_ctx* c, int64_t want) {
+  const size_t words_c = c->Lc.words(c->nB);
+  const size_t words_t = c->tiled.ok ? c->tiled.tb_words : 0;
+  const size_t words = std::max(words_c, words_t);
+  const size_t per_thread_scr = (size_t)c->N * sizeof(short2);
+  const int per = std::max(1, c->hp.n_max - std::max(2, c->hp.n_min) + 1);
+  // bytes per orientation in a chunk
+  const size_t per_o = words * 4 + (size_t)c->NP * 4 * 2 + (size_t)per * per_thread_scr + 64;
+  int64_t cap = (int64_t)((size_t)c->opt_budget_mb * 1024 * 1024 / per_o);
+  cap = std::max<int64_t>(1, std::min<int64_t>(cap, 1 << 18));
+  if (c->opt_chunk > 0) cap = std::min<int64_t>(cap, c->opt_chunk);
+  int64_t need = std::min<int64_t>(want, cap);
+  need = std::max<int64_t>(need, (int64_t)std::max(c->R, 1));  // winners pass needs R slots
+  if (need <= c->chunk_cap && words == c->tb_words) return 0;
+  cudaStreamSynchronize(c->stream);
+  harvest(c);
+  cudaFree(c->d_tb); cudaFree(c->d_cost); cudaFree(c->d_ssd); cudaFree(c->d_surv);
+  cudaFree(c->d_nw); cudaFree(c->d_nlast); cudaFree(c->d_valid); cudaFree(c->d_scratch);
+  cudaFree(c->d_rowcost); cudaFree(c->d_rowcnt);
+  c->d_tb = nullptr; c->d_cost = c->d_ssd = nullptr; c->d_surv = c->d_nw = c->d_nlast = nullptr;
+  c->d_valid = nullptr; c->d_scratch = nullptr; c->d_rowcost = nullptr; c->d_rowcnt = nullptr;
+  c->chunk_cap = 0;
+  c->tb_words = words;
+  CU(c, cudaMalloc(&c->d_tb, words * 4 * (size_t)need));
+  CU(c, cudaMalloc(&c->d_cost, (size_t)need * c->NP * 4));
+  CU(c, cudaMalloc(&c->d_ssd, (size_t)need * c->NP * 4));
+  CU(c, cudaMalloc(&c->d_valid, (size_t)need * c->NP));
+  CU(c, cudaMalloc(&c->d_surv, (size_t)need * 4));
+  CU(c, cudaMalloc(&c->d_nw, (size_t)need * 4));
+  CU(c, cudaMalloc(&c->d_nlast, (size_t)need * 4));
+  // traceback scratch: one slice of N pairs per (orientation,size) thread, warp-interleaved
+  c->scratch_threads = (((size_t)need * per + 127) / 128) * 128;
+  CU(c, cudaMalloc(&c->d_scratch, c->scratch_threads * per_thread_scr));
+  if (c->hp.use_filter) {
+    c->nw_threads_cap = (int)(((need + 127) / 128) * 128);
+    CU(c, cudaMalloc(&c->d_rowcost, (size_t)(c->nB + 1) * c->nw_threads_cap * 4));
+    CU(c, cudaMalloc(&c->d_rowcnt, (size_t)(c->nB + 1) * c->nw_threads_cap * 2));
+  }
+  c->chunk_cap = (int)need;
+  return 0;
+}
+
+// launch the 3-D DP for the survivors of the current chunk
+int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count) {
+  EventPair* ev = next_events(c, 0);
+  if (!ev) MR_FAIL(c, "cudaEventCreate failed");
+  CU(c, cudaEventRecord(ev->a, c->stream));
+  if (use_tiled(c)) {
+    if (mr_launch_dp_tiled(c->tiled, c->P, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count,
+                           c->d_tb, c->d_cost, count, c->stream) != 0)
+      MR_FAIL(c, "tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  } else {
+    int grid = std::min(count, c->dp_grid_cap);
+    k_dp_columns<<<grid, c->NP, c->dp_smem, c->stream>>>(c->P, c->Lc, c->dA, c->dB, d_orient_chunk,
+                                                        c->d_surv, c->d_surv_count, c->d_tb,
+                                                        c->d_cost, c->d_gcol, c->use_gcol);
+  }
+  CU(c, cudaGetLastError());
+  CU(c, cudaEventRecord(ev->b, c->stream));
+  c->st.kernel_launches++;
+  return 0;
+}
+
+template <bool EMIT>
+int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* items, int n_items) {
+  const int n_lo = std::max(2, c->hp.n_min);
+  const int per = c->hp.n_max - n_lo + 1;
+  const int64_t threads = items ? n_items : (int64_t)count * std::max(per, 0);
+  if (threads <= 0) return 0;
+  EventPair* ev = next_events(c, 2);
+  if (!ev) MR_FAIL(c, "cudaEventCreate failed");
+  CU(c, cudaEventRecord(ev->a, c->stream));
+  const int grid = (int)((threads + 127) / 128);
+  if (use_tiled(c))
+    k_traceback_kabsch<TbTiled, EMIT><<<grid, 128, 0, c->stream>>>(
+        c->P, c->tiled.layout, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb,
+        c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, c->d_Tout, c->d_pairs_out);
+  else
+    k_traceback_kabsch<TbColumns, EMIT><<<grid, 128, 0, c->stream>>>(
+        c->P, c->Lc, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb, c->d_cost,
+        items, n_items, n_lo, c->d_scratch, c->d_ssd, c->d_Tout, c->d_pairs_out);
+  CU(c, cudaGetLastError());
+  CU(c, cudaEventRecord(ev->b, c->stream));
+  c->st.kernel_launches++;
+  return 0;
+}
+
+// filter (or identity) -> survivors of the chunk
+int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_filter) {
+  if (apply_filter && c->hp.use_filter) {
+    CU(c, cudaMemsetAsync(c->d_surv_count, 0, 4, c->stream));
+    EventPair* ev = next_events(c, 1);
+    if (!ev) MR_FAIL(c, "cudaEventCreate failed");
+    CU(c, cudaEventRecord(ev->a, c->stream));
+    const int grid = (count + 127) / 128;
+    k_nw_filter<<<grid, 128, 0, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, c->d_rowcost,
+                                            c->d_rowcnt, c->d_nw, c->d_surv, c->d_surv_count);
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(ev->b, c->stream));
+    c->st.nw_cells += nw_cells(c->m, c->nB, c->hp.of_min) * (int64_t)count;
+  } else {
+    k_iota<<<(count + 255) / 256, 256, 0, c->stream>>>(c->d_surv, c->d_surv_count, count);
+    CU(c, cudaGetLastError());
+  }
+  c->st.kernel_launches++;
+  return 0;
+}
+
+// FirstPass over a device-resident list
+int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first_id) {
+  if (count <= 0) return 0;
+  if (ensure_chunk(c, count)) return 1;
+  for (int64_t start = 0; start < count; start += c->chunk_cap) {
+    const int cnt = (int)std::min<int64_t>(c->chunk_cap, count - start);
+    const float* oc = d_orient + 12 * (size_t)start;
+    if (launch_filter(c, oc, cnt, true)) return 1;
+    // survivor count -> pinned host (for the stats only; nothing waits on it)
+    if ((int)c->pending_counts.size() >= c->h_pinned_cap) {
+      CU(c, cudaStreamSynchronize(c->stream));
+      harvest(c);
+    }
+    const int slot = (int)c->pending_counts.size();
+    CU(c, cudaMemcpyAsync(&c->h_pinned[slot], c->d_surv_count, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->pending_counts.push_back({slot, cnt});
+    if (launch_dp(c, oc, cnt)) return 1;
+    if (launch_tb<false>(c, oc, cnt, nullptr, 0)) return 1;
+    k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->d_surv, c->d_surv_count,
+                                                      c->d_cost, c->d_ssd, (long long)(first_id + start),
+                                                      c->d_keys, nullptr, nullptr);
+    CU(c, cudaGetLastError());
+    c->st.kernel_launches++;
+    c->st.orientations += cnt;
+  }
+  return 0;
+}
+
+int reset_keys(mr_ctx* c) {
+  std::vector<unsigned long long> k((size_t)std::max(c->R, 1), KEY_NONE);
+  CU(c, cudaMemcpyAsync(c->d_keys, k.data(), sizeof(unsigned long long) * k.size(),
+                        cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->id_offset_set = false;
+  return 0;
+}
+
+void best_init_host(const mr_ctx* c, mr_best* b) {  // search_or_dyn3d.cc:165-184
+  for (int r = 0; r < c->R; r++) {
+    b->ssd[r] = MR_UPPER_BOUND;
+    for (int k = 0; k < 12; k++) b->T[12 * r + k] = (k % 5 == 0) ? 1.0f : 0.0f;
+    if (b->o_id) b->o_id[r] = -1;
+  }
+}
+
+// Turn the device key table into a full best table: re-run the DP for the (few) winning
+// orientations and emit transform + alignment for exactly the winning (orientation,size)
+// pairs.  d_orient / id_offset locate a winner's transform: index = o_id - id_offset.
+int fetch_payload(mr_ctx* c, const float* d_orient, long long id_offset, mr_best* out) {
+  std::vector<unsigned long long> keys((size_t)c->R);
+  CU(c, cudaMemcpyAsync(keys.data(), c->d_keys, 8 * (size_t)c->R, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->st.d2h_bytes += 8 * (int64_t)c->R;
+  best_init_host(c, out);
+  std::map<long long, int> widx;  // o_id -> winner slot
+  std::vector<int> idx;
+  std::vector<int2> items;
+  std::vector<int> item_r;
+  for (int r = 0; r < c->R; r++) {
+    if (keys[r] == KEY_NONE) continue;
+    const long long oid = (long long)(keys[r] & 0xffffffffull);
+    auto it = widx.find(oid);
+    int w;
+    if (it == widx.end()) {
+      w = (int)idx.size();
+      widx[oid] = w;
+      idx.push_back((int)(oid - id_offset));
+    } else {
+      w = it->second;
+    }
+    items.push_back(make_int2(w, c->hp.n_min + r));
+    item_r.push_back(r);
+  }
+  if (items.empty()) return 0;
+  const int nw = (int)idx.size(), ni = (int)items.size();
+  if (ensure_chunk(c, nw)) return 1;
+  CU(c, cudaMemcpyAsync(c->d_widx, idx.data(), 4 * (size_t)nw, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_items, items.data(), sizeof(int2) * (size_t)ni, cudaMemcpyHostToDevice, c->stream));
+  k_gather_orient<<<(nw * 12 + 127) / 128, 128, 0, c->stream>>>(d_orient, c->d_widx, nw, c->d_orient_w);
+  CU(c, cudaGetLastError());
+  c->st.kernel_launches++;
+  if (launch_filter(c, c->d_orient_w, nw, false)) return 1;
+  if (launch_dp(c, c->d_orient_w, nw)) return 1;
+  if (launch_tb<true>(c, c->d_orient_w, nw, c->d_items, ni)) return 1;
+  std::vector<float> T((size_t)ni * 12);
+  std::vector<short> pairs((size_t)ni * 2 * c->N);
+  CU(c, cudaMemcpyAsync(T.data(), c->d_Tout, 4 * T.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(pairs.data(), c->d_pairs_out, 2 * pairs.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->st.d2h_bytes += (int64_t)(4 * T.size() + 2 * pairs.size());
+  for (int k = 0; k < ni; k++) {
+    const int r = item_r[k], n = c->hp.n_min + r;
+    unsigned int bits = (unsigned int)(keys[r] >> 32);
+    memcpy(&out->ssd[r], &bits, 4);
+    memcpy(out->T + 12 * r, &T[12 * (size_t)k], 48);
+    memcpy(out->pairs + (size_t)r * 2 * c->N, &pairs[(size_t)k * 2 * c->N], sizeof(short) * 2 * (size_t)n);
+    if (out->o_id) out->o_id[r] = (long long)(keys[r] & 0xffffffffull);
+  }
+  return 0;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------- C ABI
+extern "C" {
+
+const char* mr_last_error(const mr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int64_t mr_dp_cells_per_orientation(int32_t m, int32_t nB, int32_t n_min, int32_t n_max) {
+  return dp_cells(m, nB, n_min, n_max);
+}
+
+int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t nB,
+              const mr_params* p, int32_t device) {
+  *out = nullptr;
+  auto fail = [&](const std::string& s) { g_create_error = s; return 1; };
+  if (!A || !B || !p) return fail("mr_create: null argument");
+  const int N = std::min(m, nB);
+  if (m < 1 || nB < 1 || p->nb < 1) return fail("mr_create: empty molecule");
+  if (p->n_min < 1 || p->n_min > N || p->n_max < 1 || p->n_max > N || p->n_max < p->n_min)
+    return fail("Minimum and/or maximum number of matches allowed does not make sense "
+                "(lib/dyn/dyn3d.cc:459-467)");
+  if ((long long)N * p->nb > 32767) return fail("n*nb exceeds the reference's short limit (32767)");
+  if (p->use_filter && (p->of_min < 1 || p->of_min > N)) return fail("mr_create: of_min out of range");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(std::string("mr_create: no CUDA device (this library has no CPU fallback): ") +
+                cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail("mr_create: bad device index");
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(cudaGetErrorString(e));
+  mr_ctx* c = new mr_ctx();
+  c->device = device;
+  cudaGetDeviceProperties(&c->prop, device);
+  c->hp = *p;
+  c->m = m; c->nB = nB; c->N = N; c->R = p->n_max - p->n_min + 1;
+  c->NP = ((p->n_max + 31) / 32) * 32;
+  memset(&c->st, 0, sizeof c->st);
+  MrDevParams& P = c->P;
+  P.m = m; P.nB = nB; P.nb = p->nb; P.N = N;
+  P.n_min = p->n_min; P.n_max = p->n_max;
+  P.wA = m - p->n_min + 1; P.wB = nB - p->n_min + 1;
+  P.dp_cutoff = metric_cutoff(p->max_dist, p->nb);
+  P.max_rmsd = p->max_rmsd;
+  P.use_filter = p->use_filter;
+  P.nw_cutoff = metric_cutoff(p->of_dist, p->nb);
+  // orientation_filter.cc:77-79 (double expression rounded to float)
+  P.nw_gap = (float)(0.5 * (double)(p->of_dist * p->of_dist) * (double)N * (double)p->nb);
+  P.of_min = p->of_min;
+  P.w0 = m - p->of_min + 1; P.w1 = nB - p->of_min + 1;
+  P.refine_while_searching = p->refine_while_searching;
+  c->Lc.IW = (m + 15) / 16;
+  c->Lc.NP = c->NP;
+  auto bail = [&](const char* what) {
+    g_create_error = std::string("mr_create: ") + what + ": " + cudaGetErrorString(cudaGetLastError());
+    mr_destroy(c);
+    return 1;
+  };
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+  const size_t na = (size_t)m * p->nb * 3, nbb = (size_t)nB * p->nb * 3;
+  if (cudaMalloc(&c->dA, na * 4) != cudaSuccess || cudaMalloc(&c->dB, nbb * 4) != cudaSuccess) return bail("malloc");
+  if (cudaMemcpy(c->dA, A, na * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail("memcpy");
+  if (cudaMemcpy(c->dB, B, nbb * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail("memcpy");
+  // general DP kernel: column buffers in shared memory when they fit
+  if (c->NP > 1024) { g_create_error = "mr_create: n_max > 1024 is not supported yet"; mr_destroy(c); return 1; }
+  const size_t colbytes = 2 * (size_t)(m + 1) * c->NP * 4;
+  const size_t coordbytes = (na + nbb) * 4;
+  const size_t smem_max = c->prop.sharedMemPerBlockOptin;
+  if (coordbytes > smem_max) { g_create_error = "mr_create: molecules too large for shared memory"; mr_destroy(c); return 1; }
+  if (coordbytes + colbytes <= smem_max) {
+    c->use_gcol = 0;
+    c->dp_smem = coordbytes + colbytes;
+    c->dp_grid_cap = c->prop.multiProcessorCount * 4;
+  } else {
+    c->use_gcol = 1;
+    c->dp_smem = coordbytes;
+    c->dp_grid_cap = c->prop.multiProcessorCount * 2;
+    if (cudaMalloc(&c->d_gcol, colbytes * c->dp_grid_cap) != cudaSuccess) return bail("malloc gcol");
+  }
+  if (cudaFuncSetAttribute(k_dp_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dp_smem) != cudaSuccess)
+    return bail("smem attribute");
+  mr_plan_dp_tiled(&c->tiled, P, c->prop);
+  const int RR = std::max(c->R, 1), slots = std::max(RR, c->NP);
+  if (cudaMalloc(&c->d_keys, 8 * (size_t)RR) != cudaSuccess) return bail("malloc");
+  if (cudaMalloc(&c->d_surv_count, 4) != cudaSuccess) return bail("malloc");
+  if (cudaMalloc(&c->d_orient_w, 48 * (size_t)RR) != cudaSuccess) return bail("malloc");
+  if (cudaMalloc(&c->d_widx, 4 * (size_t)RR) != cudaSuccess) return bail("malloc");
+  if (cudaMalloc(&c->d_items, sizeof(int2) * (size_t)RR) != cudaSuccess) return bail("malloc");
+  if (cudaMalloc(&c->d_Tout, 48 * (size_t)slots) != cudaSuccess) return bail("malloc");
+  if (cudaMalloc(&c->d_pairs_out, sizeof(short) * 2 * (size_t)N * slots) != cudaSuccess) return bail("malloc");
+  if (cudaMalloc(&c->d_pairs_in, sizeof(short2) * (size_t)N) != cudaSuccess) return bail("malloc");
+  c->h_pinned_cap = 4096;
+  if (cudaMallocHost(&c->h_pinned, 4 * (size_t)c->h_pinned_cap) != cudaSuccess) return bail("pinned");
+  if (reset_keys(c)) { g_create_error = c->err; mr_destroy(c); return 1; }
+  *out = c;
+  return 0;
+}
+
+void mr_destroy(mr_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  cudaFree(c->dA); cudaFree(c->dB); cudaFree(c->d_orient); cudaFree(c->d_tb); cudaFree(c->d_cost);
+  cudaFree(c->d_ssd); cudaFree(c->d_surv); cudaFree(c->d_surv_count); cudaFree(c->d_nw);
+  cudaFree(c->d_nlast); cudaFree(c->d_valid); cudaFree(c->d_rowcost); cudaFree(c->d_rowcnt);
+  cudaFree(c->d_scratch); cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w);
+  cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
+  cudaFree(c->d_pairs_in);
+  mr_free_dp_tiled(&c->tiled);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int mr_best_init(const mr_ctx* c, mr_best* best) {
+  if (!c || !best || !best->ssd || !best->T || !best->pairs) return 1;
+  best_init_host(c, best);
+  return 0;
+}
+
+int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
+  if (!c || !name) return 1;
+  if (!strcmp(name, "dp_kernel")) c->opt_dp_kernel = value;
+  else if (!strcmp(name, "budget_mb")) c->opt_budget_mb = std::max<int64_t>(64, value);
+  else if (!strcmp(name, "chunk")) c->opt_chunk = value;
+  else MR_FAIL(c, "mr_set_option: unknown option %s", name);
+  if (c->opt_dp_kernel == 2 && !c->tiled.ok) MR_FAIL(c, "tiled DP kernel not available for this problem: %s", c->tiled.why);
+  return 0;
+}
+
+int mr_upload_orientations(mr_ctx* c, const float* orient12, int64_t count) {
+  if (!c) return 1;
+  CU(c, cudaSetDevice(c->device));
+  if (count < 0 || (count > 0 && !orient12)) MR_FAIL(c, "mr_upload_orientations: bad arguments");
+  if (ensure_orient_cap(c, std::max<int64_t>(count, 1))) return 1;
+  CU(c, cudaMemcpyAsync(c->d_orient, orient12, 48 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->orient_count = count;
+  c->st.h2d_bytes += 48 * count;
+  return 0;
+}
+
+int mr_reset_best(mr_ctx* c) {
+  if (!c) return 1;
+  CU(c, cudaSetDevice(c->device));
+  return reset_keys(c);
+}
+
+int mr_search_resident(mr_ctx* c, int64_t first, int64_t count, int64_t first_id) {
+  if (!c) return 1;
+  CU(c, cudaSetDevice(c->device));
+  if (first < 0 || count < 0 || first + count > c->orient_count) MR_FAIL(c, "mr_search_resident: range outside the uploaded list");
+  if (first_id < 0 || first_id + count > 0xfffffffell) MR_FAIL(c, "orientation ids must fit 32 bits");
+  const long long off = first_id - first;
+  if (c->id_offset_set && off != c->id_offset) MR_FAIL(c, "mr_search_resident: id mapping changed since mr_reset_best");
+  c->id_offset = off;
+  c->id_offset_set = true;
+  if (search_device(c, c->d_orient + 12 * (size_t)first, count, first_id)) return 1;
+  CU(c, cudaStreamSynchronize(c->stream));
+  harvest(c);
+  return 0;
+}
+
+int mr_fetch_keys(mr_ctx* c, uint64_t* keys) {
+  if (!c || !keys) return 1;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(keys, c->d_keys, 8 * (size_t)c->R, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->st.d2h_bytes += 8 * (int64_t)c->R;
+  return 0;
+}
+
+int mr_fetch_best(mr_ctx* c, mr_best* best) {
+  if (!c || !best) return 1;
+  CU(c, cudaSetDevice(c->device));
+  if (fetch_payload(c, c->d_orient, c->id_offset, best)) return 1;
+  harvest(c);
+  return 0;
+}
+
+int mr_search(mr_ctx* c, const float* orient12, int64_t count, int64_t first_id, mr_best* best) {
+  if (!c || !best) return 1;
+  CU(c, cudaSetDevice(c->device));
+  if (count < 0 || (count > 0 && !orient12)) MR_FAIL(c, "mr_search: bad arguments");
+  if (first_id < 0 || first_id + count > 0xfffffffell) MR_FAIL(c, "orientation ids must fit 32 bits");
+  if (count == 0) return 0;
+  if (mr_upload_orientations(c, orient12, count)) return 1;
+  if (reset_keys(c)) return 1;
+  c->id_offset = first_id;
+  c->id_offset_set = true;
+  if (search_device(c, c->d_orient, count, first_id)) return 1;
+  std::vector<float> ssd((size_t)c->R), T((size_t)c->R * 12);
+  std::vector<int16_t> pairs((size_t)c->R * 2 * c->N);
+  std::vector<int64_t> oid((size_t)c->R);
+  mr_best mine = {ssd.data(), T.data(), pairs.data(), oid.data()};
+  if (fetch_payload(c, c->d_orient, first_id, &mine)) return 1;
+  harvest(c);
+  // merge into the caller's table: strictly lower score wins; on equal score the lower
+  // orientation id wins (what sequential evaluation in id order gives, :1825-1835)
+  for (int r = 0; r < c->R; r++) {
+    if (!(mine.ssd[r] < MR_UPPER_BOUND)) continue;
+    bool take = mine.ssd[r] < best->ssd[r];
+    if (!take && best->o_id && mine.ssd[r] == best->ssd[r] && best->o_id[r] >= 0 && mine.o_id[r] < best->o_id[r])
+      take = true;
+    if (!take) continue;
+    const int n = c->hp.n_min + r;
+    best->ssd[r] = mine.ssd[r];
+    memcpy(best->T + 12 * r, mine.T + 12 * r, 48);
+    memcpy(best->pairs + (size_t)r * 2 * c->N, mine.pairs + (size_t)r * 2 * c->N, sizeof(int16_t) * 2 * (size_t)n);
+    if (best->o_id) best->o_id[r] = mine.o_id[r];
+  }
+  return 0;
+}
+
+// evaluate the transform sitting in d_orient_w[0]; copy every per-size result back
+static int eval_w0(mr_ctx* c, bool apply_filter, int32_t* n_last, int32_t* nw_matches, float* cost,
+                   uint8_t* valid, float* ssd, float* T, int16_t* pairs) {
+  const int N = c->N, NP = c->NP;
+  if (ensure_chunk(c, 1)) return 1;
+  if (launch_filter(c, c->d_orient_w, 1, apply_filter)) return 1;
+  int h[2] = {0, -1};
+  CU(c, cudaMemcpyAsync(&c->h_pinned[c->h_pinned_cap - 1], c->d_surv_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  if (apply_filter && c->hp.use_filter) {
+    CU(c, cudaMemcpyAsync(&h[1], c->d_nw, 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(c, cudaMemsetAsync(c->d_valid, 0, (size_t)NP, c->stream));
+  CU(c, cudaMemsetAsync(c->d_cost, 0, (size_t)NP * 4, c->stream));
+  CU(c, cudaMemsetAsync(c->d_ssd, 0, (size_t)NP * 4, c->stream));
+  CU(c, cudaMemsetAsync(c->d_nlast, 0, 4, c->stream));
+  if (launch_dp(c, c->d_orient_w, 1)) return 1;
+  if (launch_tb<true>(c, c->d_orient_w, 1, nullptr, 0)) return 1;
+  k_select<<<1, 32, 0, c->stream>>>(c->P, NP, c->d_surv, c->d_surv_count, c->d_cost, c->d_ssd, 0ll,
+                                   nullptr, c->d_valid, c->d_nlast);
+  CU(c, cudaGetLastError());
+  c->st.kernel_launches++;
+  std::vector<float> hc((size_t)NP), hs((size_t)NP), hT((size_t)NP * 12);
+  std::vector<uint8_t> hv((size_t)NP);
+  std::vector<int16_t> hp((size_t)NP * 2 * N);
+  CU(c, cudaMemcpyAsync(&h[0], c->d_nlast, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(hc.data(), c->d_cost, 4 * (size_t)NP, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(hs.data(), c->d_ssd, 4 * (size_t)NP, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(hv.data(), c->d_valid, (size_t)NP, cudaMemcpyDeviceToHost, c->stream));
+  if (T) CU(c, cudaMemcpyAsync(hT.data(), c->d_Tout, 48 * (size_t)NP, cudaMemcpyDeviceToHost, c->stream));
+  if (pairs) CU(c, cudaMemcpyAsync(hp.data(), c->d_pairs_out, 2 * hp.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->st.d2h_bytes += (int64_t)NP * (9 + (T ? 48 : 0) + (pairs ? 4 * N : 0));
+  const bool passed = c->h_pinned[c->h_pinned_cap - 1] > 0;
+  c->events_used = 0;  // single evaluations are not part of the throughput stats
+  if (n_last) *n_last = passed ? h[0] : 0;
+  if (nw_matches) *nw_matches = h[1];
+  const int nl = passed ? h[0] : 0;
+  for (int n = 1; n <= N; n++) {
+    const bool v = passed && n <= c->hp.n_max && hv[n - 1];
+    if (cost) cost[n - 1] = (n <= nl) ? hc[n - 1] : 0.0f;
+    if (valid) valid[n - 1] = v;
+    if (ssd) ssd[n - 1] = v ? hs[n - 1] : 0.0f;
+    if (T) for (int k = 0; k < 12; k++) T[12 * (n - 1) + k] = v ? hT[12 * (size_t)(n - 1) + k] : 0.0f;
+    if (pairs)
+      for (int k = 0; k < 2 * N; k++)
+        pairs[(size_t)(n - 1) * 2 * N + k] = (v && k < 2 * n) ? hp[(size_t)(n - 1) * 2 * N + k] : 0;
+  }
+  return 0;
+}
+
+int mr_eval_one(mr_ctx* c, const float* T12, int32_t apply_filter, int32_t* n_last,
+                int32_t* nw_matches, float* cost, uint8_t* valid, float* ssd, float* T, int16_t* pairs) {
+  if (!c || !T12) return 1;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(c->d_orient_w, T12, 48, cudaMemcpyHostToDevice, c->stream));
+  c->st.h2d_bytes += 48;
+  return eval_w0(c, apply_filter != 0, n_last, nw_matches, cost, valid, ssd, T, pairs);
+}
+
+// lib/global_utils/simple_numeric_utils.h:350-376
+static int find_median(const std::vector<char>& in_set, int n_min, int n_max) {
+  int num = 0;
+  for (int n = n_min; n <= n_max; n++) num += in_set[n - n_min] ? 1 : 0;
+  if (num == 0) return n_min - 1;
+  const int half = (num + 1) / 2;
+  int n = n_min - 1, count = 0;
+  do {
+    ++n;
+    if (in_set[n - n_min]) ++count;
+  } while (count < half);
+  return n;
+}
+
+int mr_refine(mr_ctx* c, mr_best* best, int32_t max_iters, int32_t* n_evals) {
+  if (!c || !best) return 1;
+  CU(c, cudaSetDevice(c->device));
+  const int N = c->N, n_min = c->hp.n_min, n_max = c->hp.n_max, R = c->R;
+  std::vector<char> need((size_t)R);
+  for (int r = 0; r < R; r++) need[r] = best->ssd[r] < MR_UPPER_BOUND;  // :2348-2358
+  std::vector<float> ssd((size_t)N), T((size_t)N * 12);
+  std::vector<uint8_t> valid((size_t)N);
+  std::vector<int16_t> pairs((size_t)N * 2 * N), old((size_t)2 * N);
+  int evals = 0;
+  for (int it = 1; it <= max_iters || max_iters < 0; it++) {
+    const int n = find_median(need, n_min, n_max);
+    if (n == n_min - 1) break;
+    int16_t* cur = best->pairs + (size_t)(n - n_min) * 2 * N;
+    // orientation that optimally superimposes the current size-n alignment (:2401-2407)
+    CU(c, cudaMemcpyAsync(c->d_pairs_in, cur, sizeof(short2) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->st.h2d_bytes += 4 * n;
+    k_superimpose_pairs<<<1, 32, 0, c->stream>>>(c->P, c->dA, c->dB, c->d_pairs_in, n, c->d_orient_w);
+    CU(c, cudaGetLastError());
+    c->st.kernel_launches++;
+    memcpy(old.data(), cur, sizeof(int16_t) * 2 * (size_t)n);
+    int32_t nl = 0;
+    if (eval_w0(c, false, &nl, nullptr, nullptr, valid.data(), ssd.data(), T.data(), pairs.data())) return 1;
+    evals++;
+    for (int m2 = std::max(2, n_min); m2 <= nl; m2++) {
+      if (!valid[m2 - 1] || !(ssd[m2 - 1] < best->ssd[m2 - n_min])) continue;  // strict <, :2515
+      const int r = m2 - n_min;
+      best->ssd[r] = ssd[m2 - 1];
+      memcpy(best->T + 12 * r, &T[12 * (size_t)(m2 - 1)], 48);
+      memcpy(best->pairs + (size_t)r * 2 * N, &pairs[(size_t)(m2 - 1) * 2 * N], sizeof(int16_t) * 2 * (size_t)m2);
+      if (best->o_id) best->o_id[r] = -2;
+      if (m2 != n) need[r] = 1;  // :2546
+    }
+    need[n - n_min] = memcmp(old.data(), cur, sizeof(int16_t) * 2 * (size_t)n) != 0;  // :2619-2629
+  }
+  if (n_evals) *n_evals = evals;
+  return 0;
+}
+
+int mr_superimpose_batch(mr_ctx* c, int32_t batch, int32_t np, const float* fixed,
+                         const float* moveable, float* T, float* rmsd) {
+  if (!c) return 1;
+  CU(c, cudaSetDevice(c->device));
+  if (batch <= 0 || np <= 0) return 0;
+  float *df = nullptr, *dm = nullptr, *dT = nullptr, *dr = nullptr;
+  const size_t pts = (size_t)batch * np * 3 * 4;
+  CU(c, cudaMalloc(&df, pts)); CU(c, cudaMalloc(&dm, pts));
+  CU(c, cudaMalloc(&dT, (size_t)batch * 48)); CU(c, cudaMalloc(&dr, (size_t)batch * 4));
+  CU(c, cudaMemcpyAsync(df, fixed, pts, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(dm, moveable, pts, cudaMemcpyHostToDevice, c->stream));
+  k_superimpose_batch<<<(batch + 63) / 64, 64, 0, c->stream>>>(batch, np, df, dm, dT, dr);
+  CU(c, cudaGetLastError());
+  c->st.kernel_launches++;
+  CU(c, cudaMemcpyAsync(T, dT, (size_t)batch * 48, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(rmsd, dr, (size_t)batch * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(df); cudaFree(dm); cudaFree(dT); cudaFree(dr);
+  return 0;
+}
+
+// glibc rand() in its never-seeded state (TYPE_3 additive feedback generator, seed 1):
+// std::random_shuffle in lib/or_gen/or_gen.cc:179 is driven by it.
+namespace {
+struct GlibcRand {
+  int32_t r[34];
+  int f = 3, b = 0;
+  GlibcRand() {
+    int32_t word = 1;
+    r[0] = word;
+    for (int i = 1; i < 31; i++) {
+      long hi = word / 127773, lo = word % 127773;
+      long w = 16807 * lo - 2836 * hi;
+      if (w < 0) w += 2147483647;
+      word = (int32_t)w;
+      r[i] = word;
+    }
+    for (int i = 0; i < 310; i++) next();
+  }
+  int next() {
+    uint32_t v = (uint32_t)r[f] + (uint32_t)r[b];
+    r[f] = (int32_t)v;
+    f = (f + 1) % 31;
+    b = (b + 1) % 31;
+    return (int)(v >> 1);
+  }
+};
+}  // namespace
+
+int mr_gen_orientations(mr_ctx* c, int32_t L, float cutoff_rmsd, const int32_t* intervals,
+                        int32_t n_intervals, int32_t shuffle, float* out12, int64_t cap, int64_t* count) {
+  if (!c || !count) return 1;
+  CU(c, cudaSetDevice(c->device));
+  const int m = c->m, nB = c->nB, nb = c->hp.nb;
+  if (L < 1 || L > c->N) MR_FAIL(c, "fragment size must be in [1, min(m,n)]");
+  const int w1 = m - c->hp.n_min + 1, w2 = nB - c->hp.n_min + 1;  // or_gen.cc:253-254
+  std::vector<char> mask((size_t)m * nB, 0);
+  int32_t whole[4] = {0, m - 1, 0, nB - 1};
+  if (!intervals || n_intervals == 0) { intervals = whole; n_intervals = 1; }
+  for (int p = 0; p < n_intervals; p++) {  // or_gen.cc:345-493
+    const int s1 = intervals[4 * p], e1 = intervals[4 * p + 1], s2 = intervals[4 * p + 2], e2 = intervals[4 * p + 3];
+    if (s1 < 0 || s2 < 0 || e1 >= m || e2 >= nB || e1 < s1 || e2 < s2) MR_FAIL(c, "bad fragment-matching interval");
+    if (s1 > e1 - L + 1 || s2 > e2 - L + 1) continue;
+    for (int I = s1; I <= e1 - L + 1; I++) {
+      const int jlo = std::max(s2, I - (w1 - 1)), jhi = std::min(I + (w2 - 1), e2 - L + 1);
+      for (int J = jlo; J <= jhi; J++) mask[(size_t)I * nB + J] = 1;
+    }
+  }
+  std::vector<int2> ij;
+  for (int I = 0; I < m; I++)
+    for (int J = 0; J < nB; J++)
+      if (mask[(size_t)I * nB + J]) ij.push_back(make_int2(I, J));
+  const int64_t cand = (int64_t)ij.size();
+  std::vector<float> T((size_t)cand * 12), rm((size_t)cand);
+  if (cand > 0) {
+    int2* dij = nullptr;
+    float *dT = nullptr, *dr = nullptr;
+    CU(c, cudaMalloc(&dij, sizeof(int2) * (size_t)cand));
+    CU(c, cudaMalloc(&dT, 48 * (size_t)cand));
+    CU(c, cudaMalloc(&dr, 4 * (size_t)cand));
+    CU(c, cudaMemcpyAsync(dij, ij.data(), sizeof(int2) * (size_t)cand, cudaMemcpyHostToDevice, c->stream));
+    k_fragment_fit<<<(unsigned)((cand + 63) / 64), 64, 0, c->stream>>>(c->dA, c->dB, nb, L, dij, cand, dT, dr);
+    CU(c, cudaGetLastError());
+    c->st.kernel_launches++;
+    CU(c, cudaMemcpyAsync(T.data(), dT, 48 * (size_t)cand, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(rm.data(), dr, 4 * (size_t)cand, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dij); cudaFree(dT); cudaFree(dr);
+  }
+  std::vector<int64_t> keep;
+  for (int64_t k = 0; k < cand; k++)
+    if (cutoff_rmsd < 0.0f || rm[k] <= cutoff_rmsd) keep.push_back(k);  // or_gen.cc:537-541
+  const int64_t n = (int64_t)keep.size();
+  *count = n;
+  if (!out12) return 0;
+  if (cap < n) MR_FAIL(c, "mr_gen_orientations: output capacity %lld < %lld", (long long)cap, (long long)n);
+  if (shuffle) {  // libstdc++ std::random_shuffle(first,last): j = rand() % (i+1); swap
+    GlibcRand g;
+    for (int64_t i = 1; i < n; i++) {
+      const int64_t j = (int64_t)g.next() % (i + 1);
+      if (i != j) std::swap(keep[i], keep[j]);
+    }
+  }
+  for (int64_t k = 0; k < n; k++) memcpy(out12 + 12 * k, &T[12 * (size_t)keep[k]], 48);
+  return 0;
+}
+
+int mr_get_stats(mr_ctx* c, mr_stats* out) {
+  if (!c || !out) return 1;
+  *out = c->st;
+  return 0;
+}
+
+int mr_reset_stats(mr_ctx* c) {
+  if (!c) return 1;
+  memset(&c->st, 0, sizeof c->st);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// mr_kernels.cuh -- the sm_100a kernels of the per-orientation search.
+//
+//   k_fragment_fit     K0  orientation generation (lib/or_gen/or_gen.cc:507-544)
+//   k_nw_filter        K1+K2 rotate + banded NW filter (apply_trans.cc:72-108,
+//                      orientation_filter.cc:88-130, dynNW.cc:243-531)
+//   k_dp_columns       K1+K3+K4 general 3-D DP: rotate, distance build, all layers,
+//                      2-bit traceback (dyn3d.cc:135-387, 664-701)
+//   k_traceback_kabsch K5+K6 per-(orientation,size) traceback + superposition
+//                      (dyn3d.cc:391-431, pair_alignment.cc:714-820, superimpose.cc:17-287)
+//   k_select           K7 early-exit prefix + per-size arg-min (search_or_dyn3d.cc:1714-1835)
+#pragma once
+#include "mr_device.cuh"
+
+// ---------------------------------------------------------------------------
+// Traceback storage of the general kernel: 2 bits per cell {0 match, 1 skip-i, 2 skip-j}
+// (codes of lib/dyn/dyn3d.cc:53-58), 16 consecutive rows i per 32-bit word,
+// word index = ((j-1) * IW + ((i-1) >> 4)) * NP + (n-1): consecutive layers n are
+// consecutive words, so the layer-per-thread kernel writes coalesced.
+// ---------------------------------------------------------------------------
+struct TbColumns {
+  int IW, NP;
+  __host__ __device__ size_t words(int nB) const { return (size_t)nB * IW * NP; }
+  __device__ __forceinline__ size_t word(int n, int i, int j) const {
+    return ((size_t)(j - 1) * IW + ((i - 1) >> 4)) * NP + (n - 1);
+  }
+  __device__ __forceinline__ int shift(int i) const { return 2 * ((i - 1) & 15); }
+};
+
+// ---------------------------------------------------------------------------
+// K0: one thread per fragment pair (I,J): least-squares fit of L*nb points of B onto A.
+// ---------------------------------------------------------------------------
+__global__ void k_fragment_fit(const float* __restrict__ A, const float* __restrict__ B, int nb,
+                               int L, const int2* __restrict__ ij, int64_t count,
+                               float* __restrict__ out12, float* __restrict__ out_rmsd) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const float* f = A + 3 * (size_t)ij[t].x * nb;
+  const float* mv = B + 3 * (size_t)ij[t].y * nb;
+  float T[12];
+  float r = mr_superimpose(L * nb, [&](int a, float* pf, float* pm) {
+    pf[0] = f[3 * a]; pf[1] = f[3 * a + 1]; pf[2] = f[3 * a + 2];
+    pm[0] = mv[3 * a]; pm[1] = mv[3 * a + 1]; pm[2] = mv[3 * a + 2];
+  }, T);
+#pragma unroll
+  for (int k = 0; k < 12; k++) out12[12 * t + k] = T[k];
+  out_rmsd[t] = r;
+}
+
+// generic batched superposition (mr_superimpose_batch)
+__global__ void k_superimpose_batch(int batch, int np, const float* __restrict__ fixed,
+                                    const float* __restrict__ moveable, float* __restrict__ Tout,
+                                    float* __restrict__ rmsd) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch) return;
+  const float* f = fixed + (size_t)t * np * 3;
+  const float* mv = moveable + (size_t)t * np * 3;
+  float T[12];
+  float r = mr_superimpose(np, [&](int a, float* pf, float* pm) {
+    pf[0] = f[3 * a]; pf[1] = f[3 * a + 1]; pf[2] = f[3 * a + 2];
+    pm[0] = mv[3 * a]; pm[1] = mv[3 * a + 1]; pm[2] = mv[3 * a + 2];
+  }, T);
+#pragma unroll
+  for (int k = 0; k < 12; k++) Tout[12 * (size_t)t + k] = T[k];
+  rmsd[t] = r;
+}
+
+// ---------------------------------------------------------------------------
+// K1+K2: NW orientation filter, one thread per orientation.  All threads of a warp walk
+// the same (i,j) sequence, so A_i / B_j loads are warp-uniform broadcasts; the one-row
+// table lives in a [j][thread] scratch array (coalesced).  The number of matches on the
+// traceback is carried forward as a counter (border cells reset it: dynNW.h GetPrevCell
+// PREV_PTR_UNINITIALIZED jumps to (0,0)), so no traceback table is stored.
+// Writes nw_matches[o] and appends survivors (matches >= of_min) to surv[] (unordered).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_nw_filter(MrDevParams P, const float* __restrict__ A, const float* __restrict__ B,
+            const float* __restrict__ orient, int count, float* __restrict__ row_cost,
+            unsigned short* __restrict__ row_cnt, int* __restrict__ nw_matches,
+            int* __restrict__ surv, int* __restrict__ surv_count) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthreads = gridDim.x * blockDim.x;
+  if (tid >= count) return;
+  float T[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) T[k] = orient[12 * (size_t)tid + k];
+  const int m = P.m, nB = P.nB, nb = P.nb, w0 = P.w0, w1 = P.w1;
+  const float G = P.nw_gap, cutoff = P.nw_cutoff;
+  float left = 0.f;
+  int leftc = 0;
+  for (int i = 1; i <= m; i++) {
+    const int jlo = (i <= w0) ? 1 : i - w0 + 1;
+    const int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
+    // band of the previous row (row 0 has none)
+    const int pjlo = (i - 1 <= w0) ? 1 : i - 1 - w0 + 1;
+    const int pjhi = (i - 1 + w1 <= nB) ? i - 1 + w1 - 1 : nB;
+    const bool prow = (i - 1) >= 1;
+    left = (float)(i + jlo - 1) * G;  // border cell (i, jlo-1), dynNW.cc:200-216
+    leftc = 0;
+    float diag;
+    int diagc;
+    {
+      const int j = jlo - 1;
+      if (prow && j >= pjlo && j <= pjhi) {
+        diag = row_cost[(size_t)j * nthreads + tid];
+        diagc = row_cnt[(size_t)j * nthreads + tid];
+      } else {
+        diag = (float)(i - 1 + j) * G;
+        diagc = 0;
+      }
+    }
+    for (int j = jlo; j <= jhi; j++) {
+      float up;
+      int upc;
+      if (prow && j >= pjlo && j <= pjhi) {
+        up = row_cost[(size_t)j * nthreads + tid];
+        upc = row_cnt[(size_t)j * nthreads + tid];
+      } else {
+        up = (float)(i - 1 + j) * G;  // border cell, dynNW.cc:218-234
+        upc = 0;
+      }
+      float c = 0.0f;
+      for (int q = 0; q < nb; q++) {
+        const float* a = A + 3 * ((size_t)(i - 1) * nb + q);
+        const float* b = B + 3 * ((size_t)(j - 1) * nb + q);
+        float bx, by, bz;
+        mr_xform(T, b[0], b[1], b[2], bx, by, bz);
+        c += mr_d2(a[0], a[1], a[2], bx, by, bz);
+      }
+      if (c > cutoff) c = MR_UB;
+      const float c_match = diag + c, c_i = up + G, c_j = left + G;
+      float best = c_i;  // tie order of dynNW.cc:350-363: skip-i, then skip-j (<), then match (<)
+      int bc = upc;
+      if (c_j < best) { best = c_j; bc = leftc; }
+      if (c_match < best) { best = c_match; bc = diagc + 1; }
+      row_cost[(size_t)j * nthreads + tid] = best;
+      row_cnt[(size_t)j * nthreads + tid] = (unsigned short)bc;
+      diag = up; diagc = upc;
+      left = best; leftc = bc;
+    }
+  }
+  nw_matches[tid] = leftc;
+  if (leftc >= P.of_min) {
+    int slot = atomicAdd(surv_count, 1);
+    surv[slot] = tid;
+  }
+}
+
+// identity survivor list when the filter is off
+__global__ void k_iota(int* __restrict__ surv, int* __restrict__ surv_count, int count) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) surv[t] = t;
+  if (t == 0) *surv_count = count;
+}
+
+// ---------------------------------------------------------------------------
+// K1+K3+K4, general kernel: one CTA per orientation, one thread per layer n, sweeping
+// the columns j of molecule 2.  Within a column a thread walks its rows i = n..i_max(n)
+// keeping A(n,i-1,j) in a register; A(n-1,i-1,j-1) and A(n,i,j-1) come from the previous
+// column's buffer colA[i][n-1] (shared memory when it fits, else a per-CTA global work
+// space), the results go to colB; one __syncthreads per column.
+// Recurrence and tie order of lib/dyn/dyn3d.cc:283-382: start with match, "<=" skip-i,
+// "<=" skip-j.  C(i,j) is rebuilt on the fly from A_i (shared) and the rotated B'_j.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_dp_columns(MrDevParams P, TbColumns L, const float* __restrict__ A, const float* __restrict__ B,
+             const float* __restrict__ orient, const int* __restrict__ surv,
+             const int* __restrict__ surv_count, uint32_t* __restrict__ tb,
+             float* __restrict__ cost_out, float* __restrict__ gcol, int use_gcol) {
+  extern __shared__ float smem[];
+  const int m = P.m, nB = P.nB, nb = P.nb, NP = L.NP;
+  const int n = threadIdx.x + 1;
+  float* sA = smem;                       // m*nb*3
+  float* sB = sA + (size_t)m * nb * 3;     // nB*nb*3 rotated
+  float* col0;
+  float* col1;
+  const size_t colsz = (size_t)(m + 1) * NP;
+  if (use_gcol) {
+    col0 = gcol + (size_t)blockIdx.x * 2 * colsz;
+    col1 = col0 + colsz;
+  } else {
+    col0 = sB + (size_t)nB * nb * 3;
+    col1 = col0 + colsz;
+  }
+  for (int k = threadIdx.x; k < m * nb * 3; k += blockDim.x) sA[k] = A[k];
+  const int nsurv = *surv_count;
+  const float INF = __int_as_float(0x7f800000);
+  for (int s = blockIdx.x; s < nsurv; s += gridDim.x) {
+    const int o = surv[s];
+    const float* T = orient + 12 * (size_t)o;
+    __syncthreads();
+    for (int k = threadIdx.x; k < nB * nb; k += blockDim.x) {
+      float x, y, z;
+      mr_xform(T, B[3 * k], B[3 * k + 1], B[3 * k + 2], x, y, z);
+      sB[3 * k] = x; sB[3 * k + 1] = y; sB[3 * k + 2] = z;
+    }
+    __syncthreads();
+    uint32_t* tbo = tb + (size_t)s * L.words(nB);
+    const bool live_n = n <= P.n_max;
+    const int imax = min(m, n + P.wA - 1), jmax = min(nB, n + P.wB - 1);
+    float* colA = col0;
+    float* colB = col1;
+    for (int j = 1; j <= nB; j++) {
+      if (live_n && j >= n && j <= jmax) {
+        float up = INF;
+        uint32_t acc = 0;
+        float res = 0.f;
+        for (int i = n; i <= imax; i++) {
+          float c = 0.0f;
+          for (int q = 0; q < nb; q++) {
+            const float* a = sA + 3 * ((i - 1) * nb + q);
+            const float* b = sB + 3 * ((j - 1) * nb + q);
+            c += mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
+          }
+          if (c > P.dp_cutoff) c = MR_UB;
+          const float prev = (n > 1) ? colA[(size_t)(i - 1) * NP + (n - 2)] : 0.0f;
+          const float d = (n > 1) ? prev + c : c;
+          const float left = (j > n) ? colA[(size_t)i * NP + (n - 1)] : INF;
+          float best = d;
+          uint32_t code = 0;
+          if (up <= best) { best = up; code = 1; }
+          if (left <= best) { best = left; code = 2; }
+          colB[(size_t)i * NP + (n - 1)] = best;
+          up = best;
+          res = best;
+          acc |= code << L.shift(i);
+          if (((i - 1) & 15) == 15 || i == imax) {
+            tbo[L.word(n, i, j)] = acc;
+            acc = 0;
+          }
+        }
+        if (j == jmax) cost_out[(size_t)s * NP + (n - 1)] = res;
+      }
+      __syncthreads();
+      float* t = colA; colA = colB; colB = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5+K6: one thread per (survivor s, size n): walk the traceback from (n, m, nB)
+// (Dyn3d::ExportSolution, dyn3d.cc:391-431), then superimpose the n matched residue pairs
+// taken from the ORIGINAL coordinates (pair_alignment.cc:754-804) and form
+// ssd = SQR(rmsd)*n*nb (search_or_dyn3d.cc:587-588).  The pair list is staged in a
+// per-thread scratch slice so the sums run in ascending pair order like the reference.
+//   items == NULL: dense grid over (s, n in [n_lo, n_max]);  else explicit (s,n) list.
+//   EMIT: also write the transform and the pair list.
+// ---------------------------------------------------------------------------
+template <class Layout, bool EMIT>
+__global__ void __launch_bounds__(128)
+k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const float* __restrict__ B,
+                   const float* __restrict__ orient, const int* __restrict__ surv,
+                   const int* __restrict__ surv_count, const uint32_t* __restrict__ tb,
+                   const float* __restrict__ cost, const int2* __restrict__ items, int n_items,
+                   int n_lo, short2* __restrict__ scratch, float* __restrict__ ssd_out,
+                   float* __restrict__ T_out, short* __restrict__ pairs_out) {
+  const int NP = L.NP;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  int s, n;
+  if (items) {
+    if (tid >= n_items) return;
+    s = items[tid].x;
+    n = items[tid].y;
+  } else {
+    const int per = P.n_max - n_lo + 1;
+    if (per <= 0) return;
+    s = tid / per;
+    n = n_lo + tid % per;
+    if (s >= *surv_count) return;
+  }
+  const size_t slot = (size_t)s * NP + (n - 1);
+  // warp-interleaved slice: entry k of lane l sits at [warp][k][l] (coalesced per warp)
+  short2* my = scratch + (size_t)(tid >> 5) * 32 * P.N + (tid & 31);
+#define MY(k) my[(size_t)(k) * 32]
+  const uint32_t* tbo = tb + (size_t)s * L.words(P.nB);
+  int cn = n, ci = P.m, cj = P.nB;
+  while (cn > 0) {
+    const uint32_t code = (tbo[L.word(cn, ci, cj)] >> L.shift(ci)) & 3u;
+    if (code == 0) {
+      MY(cn - 1) = make_short2((short)(ci - 1), (short)(cj - 1));
+      cn--; ci--; cj--;
+    } else if (code == 1) {
+      ci--;
+    } else {
+      cj--;
+    }
+  }
+  float T[12];
+  float ssd;
+  if (P.refine_while_searching) {
+    const int nb = P.nb;
+    float rmsd = mr_superimpose(n * nb, [&](int a, float* pf, float* pm) {
+      const int k = a / nb, q = a - k * nb;
+      const short2 pr = MY(k);
+      const float* f = A + 3 * ((size_t)pr.x * nb + q);
+      const float* mv = B + 3 * ((size_t)pr.y * nb + q);
+      pf[0] = f[0]; pf[1] = f[1]; pf[2] = f[2];
+      pm[0] = mv[0]; pm[1] = mv[1]; pm[2] = mv[2];
+    }, T);
+    ssd = ((rmsd * rmsd) * (float)n) * (float)nb;
+  } else {
+    ssd = cost[slot];
+    if (EMIT) {
+      const float* To = orient + 12 * (size_t)surv[s];
+#pragma unroll
+      for (int k = 0; k < 12; k++) T[k] = To[k];
+    }
+  }
+  ssd_out[slot] = ssd;
+  if (EMIT) {
+    const size_t e = items ? (size_t)tid : slot;
+#pragma unroll
+    for (int k = 0; k < 12; k++) T_out[12 * e + k] = T[k];
+    short* po = pairs_out + e * 2 * P.N;
+    for (int k = 0; k < n; k++) {
+      po[2 * k] = MY(k).x;
+      po[2 * k + 1] = MY(k).y;
+    }
+  }
+}
+
+#undef MY
+
+// transforms of the winning orientations: out[k] = orient[idx[k]]
+__global__ void k_gather_orient(const float* __restrict__ orient, const int* __restrict__ idx, int n,
+                                float* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * 12) out[t] = orient[12 * (size_t)idx[t / 12] + t % 12];
+}
+
+// Refine: orientation that optimally superimposes one alignment
+// (PairwiseAlignment::CalcMinRMSD, pair_alignment.cc:714-820); single thread.
+__global__ void k_superimpose_pairs(MrDevParams P, const float* __restrict__ A,
+                                    const float* __restrict__ B, const short2* __restrict__ pairs,
+                                    int n, float* __restrict__ T_out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int nb = P.nb;
+  float T[12];
+  mr_superimpose(n * nb, [&](int a, float* pf, float* pm) {
+    const int k = a / nb, q = a - k * nb;
+    const short2 pr = pairs[k];
+    const float* f = A + 3 * ((size_t)pr.x * nb + q);
+    const float* mv = B + 3 * ((size_t)pr.y * nb + q);
+    pf[0] = f[0]; pf[1] = f[1]; pf[2] = f[2];
+    pm[0] = mv[0]; pm[1] = mv[1]; pm[2] = mv[2];
+  }, T);
+  for (int k = 0; k < 12; k++) T_out[k] = T[k];
+}
+
+// ---------------------------------------------------------------------------
+// K7: one thread per survivor: replay the reference's sequential n-loop early exits
+// (search_or_dyn3d.cc:1714-1721 max-dist, 1810-1811 max-rmsd) as a prefix over n, then
+// atomicMin the 64-bit key (float_bits(ssd) << 32 | o_id) per size: strict "<" with the
+// lowest orientation id winning ties is exactly search_or_dyn3d.cc:1825-1835 evaluated
+// in id order.  Optionally writes valid[] / n_last for mr_eval_one.
+// ---------------------------------------------------------------------------
+__global__ void k_select(MrDevParams P, int NP, const int* __restrict__ surv,
+                         const int* __restrict__ surv_count, const float* __restrict__ cost,
+                         const float* __restrict__ ssd, long long id_base,
+                         unsigned long long* __restrict__ keys, unsigned char* __restrict__ valid,
+                         int* __restrict__ n_last_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= *surv_count) return;
+  const unsigned long long oid = (unsigned long long)(id_base + surv[s]);
+  int n_last = min(1, P.n_max);
+  for (int n = 2; n <= P.n_max; n++) {
+    const size_t slot = (size_t)s * NP + (n - 1);
+    n_last = n;
+    if (cost[slot] >= MR_UB) break;
+    if (n >= P.n_min) {
+      const float v = ssd[slot];
+      if (P.max_rmsd >= 0.0f && v > (float)(n * P.nb) * (P.max_rmsd * P.max_rmsd)) break;
+      if (valid) valid[slot] = 1;
+      if (keys && v < MR_UB) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | oid;
+        atomicMin(&keys[n - P.n_min], key);
+      }
+    }
+  }
+  if (n_last_out) n_last_out[s] = n_last;
+}

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _load(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def golden_c1():
+    return _load("ref_c1.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_c2():
+    return _load("ref_c2.npz")

@@ -1,0 +1,79 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/*.h declares,
+fails loudly without a GPU, and the host-side logic (shuffle, parameter mapping)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_ctypes as oc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for f in os.listdir(inc):
+        src = open(os.path.join(inc, f)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(mr_[a-z_0-9]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    from minrms_b200 import _lib, build
+    build.build()
+    L = C.CDLL(_lib.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(L, s), "missing export " + s
+    assert set(_lib.EXPORTS) == set(syms)
+
+
+def test_sass_is_sm100a():
+    from minrms_b200 import _lib, build
+    build.build()
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only check")
+def test_create_fails_loudly_without_gpu():
+    from minrms_b200 import SearchOrCuda, Settings, MinrmsError
+    A = np.zeros((5, 3), np.float32)
+    with pytest.raises(MinrmsError, match="no CPU fallback"):
+        SearchOrCuda(A, A, Settings())
+
+
+def test_interpret_num_matches():
+    from minrms_b200 import interpret_num_matches
+    assert interpret_num_matches(0.33, 141, 151) == 47      # config 1: -minN 0.33
+    assert interpret_num_matches(47, 141, 151) == 47
+    assert interpret_num_matches(0.33, 1500, 2000) == 495   # config 4 filter minimum
+
+
+def test_shuffle_matches_libc_rand():
+    """the restated glibc rand()/std::random_shuffle against the real libc in a fresh
+    process (never-seeded rand(), as in lib/or_gen/or_gen.cc:179)"""
+    code = ("import ctypes,sys; L=ctypes.CDLL('libc.so.6'); n=int(sys.argv[1]); p=list(range(n))\n"
+            "for i in range(1,n):\n j=L.rand()%(i+1)\n p[i],p[j]=p[j],p[i]\n"
+            "print(' '.join(map(str,p)))")
+    out = subprocess.run([sys.executable, "-c", code, "5000"], capture_output=True, text=True, check=True)
+    expect = np.array(out.stdout.split(), np.int64)
+    assert np.array_equal(oc.shuffle_perm(5000), expect)
+
+
+def test_partition_covers_everything():
+    from minrms_b200.dist import partition
+    for count in (0, 1, 7, 20424):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                a, b = partition(count, r, world)
+                seen.extend(range(a, b))
+            assert seen == list(range(count))
