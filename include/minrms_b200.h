@@ -144,6 +144,11 @@ typedef struct mr_stats {
 int mr_get_stats(mr_ctx *ctx, mr_stats *out);
 int mr_reset_stats(mr_ctx *ctx);
 
+/* CUDA events on the context's own stream (slots 0..15), so a caller can time a region
+ * on the device: torch.cuda.Event only sees torch's stream, not this library's. */
+int mr_event_record(mr_ctx *ctx, int32_t slot);
+int mr_event_elapsed_ms(mr_ctx *ctx, int32_t slot_a, int32_t slot_b, float *ms);
+
 /* Tuning knobs (by name), e.g. "dp_kernel" = 0 auto / 1 general / 2 tiled. */
 int mr_set_option(mr_ctx *ctx, const char *name, int64_t value);
 

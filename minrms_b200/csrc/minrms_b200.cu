@@ -75,6 +75,7 @@ struct mr_ctx {
   std::vector<std::pair<int, int>> pending_counts;  // (pinned slot, chunk count)
   std::string err;
   MrTiledPlan tiled;
+  cudaEvent_t user_ev[16] = {};
 };
 
 namespace {
@@ -479,6 +480,7 @@ void mr_destroy(mr_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
   cudaFree(c->dA); cudaFree(c->dB); cudaFree(c->d_orient); cudaFree(c->d_tb); cudaFree(c->d_cost);
   cudaFree(c->d_ssd); cudaFree(c->d_surv); cudaFree(c->d_surv_count); cudaFree(c->d_nw);
   cudaFree(c->d_nlast); cudaFree(c->d_valid); cudaFree(c->d_rowcost); cudaFree(c->d_rowcnt);
@@ -807,6 +809,22 @@ int mr_gen_orientations(mr_ctx* c, int32_t L, float cutoff_rmsd, const int32_t* 
     }
   }
   for (int64_t k = 0; k < n; k++) memcpy(out12 + 12 * k, &T[12 * (size_t)keep[k]], 48);
+  return 0;
+}
+
+int mr_event_record(mr_ctx* c, int32_t slot) {
+  if (!c || slot < 0 || slot >= 16) return 1;
+  CU(c, cudaSetDevice(c->device));
+  if (!c->user_ev[slot]) CU(c, cudaEventCreate(&c->user_ev[slot]));
+  CU(c, cudaEventRecord(c->user_ev[slot], c->stream));
+  return 0;
+}
+
+int mr_event_elapsed_ms(mr_ctx* c, int32_t a, int32_t b, float* ms) {
+  if (!c || !ms || a < 0 || a >= 16 || b < 0 || b >= 16 || !c->user_ev[a] || !c->user_ev[b]) return 1;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventSynchronize(c->user_ev[b]));
+  CU(c, cudaEventElapsedTime(ms, c->user_ev[a], c->user_ev[b]));
   return 0;
 }
 

@@ -193,6 +193,14 @@ class SearchOrCuda:
         res["n_last"], res["nw_matches"] = nl.value, nw.value
         return res
 
+    def event_record(self, slot):
+        self._check(self.lib.mr_event_record(self.ctx, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float(0)
+        self._check(self.lib.mr_event_elapsed_ms(self.ctx, a, b, C.byref(ms)))
+        return ms.value
+
     def stats(self, reset=False):
         st = _lib.MrStats()
         self._check(self.lib.mr_get_stats(self.ctx, C.byref(st)))

@@ -8,8 +8,8 @@
 #   flavour "fast"   = the flags the reference ships (setup_gcc.sh:9)   -> Oracle-F
 #   flavour "strict" = no fast-math, no FMA contraction                 -> Oracle-S
 #
-# Outputs per flavour: libminrms_ref.a (all lib/* objects), minrms (the CLI),
-# and ref_dump (oracle/ref_dump.cc linked against the reference objects).
+# Outputs per flavour: libminrms_ref.a (all lib/* objects), minrms (the CLI), and the
+# drivers ref_dump / ref_bench (oracle/*.cc linked against the reference objects).
 set -e
 REF=${REF:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -60,9 +60,11 @@ build_flavour() {
   rm -f $O/libminrms_bin.a
   ar rcs $O/libminrms_bin.a $binobjs
   g++ -o $O/minrms $O/obj/bin_main.o $O/libminrms_bin.a $O/libminrms_ref.a
-  if [ -f $HERE/ref_dump.cc ]; then
-    g++ -std=c++11 $FLAGS -w $INC $HERE/ref_dump.cc $O/libminrms_bin.a $O/libminrms_ref.a -o $O/ref_dump
-  fi
+  for drv in ref_dump ref_bench; do
+    if [ -f $HERE/$drv.cc ]; then
+      g++ -std=c++11 $FLAGS -w $INC $HERE/$drv.cc $O/libminrms_bin.a $O/libminrms_ref.a -o $O/$drv
+    fi
+  done
   echo "built $O"
 }
 
