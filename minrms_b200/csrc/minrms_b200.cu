@@ -458,7 +458,7 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   }
   if (cudaFuncSetAttribute(k_dp_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dp_smem) != cudaSuccess)
     return bail("smem attribute");
-  mr_plan_dp_tiled(&c->tiled, P, c->prop);
+  mr_plan_dp_tiled(&c->tiled, P, c->prop, c->NP);
   const int RR = std::max(c->R, 1), slots = std::max(RR, c->NP);
   if (cudaMalloc(&c->d_keys, 8 * (size_t)RR) != cudaSuccess) return bail("malloc");
   if (cudaMalloc(&c->d_surv_count, 4) != cudaSuccess) return bail("malloc");

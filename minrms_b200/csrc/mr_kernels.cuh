@@ -24,6 +24,9 @@ struct TbColumns {
     return ((size_t)(j - 1) * IW + ((i - 1) >> 4)) * NP + (n - 1);
   }
   __device__ __forceinline__ int shift(int i) const { return 2 * ((i - 1) & 15); }
+  __device__ __forceinline__ uint32_t code(const uint32_t* __restrict__ tbo, int n, int i, int j) const {
+    return (tbo[word(n, i, j)] >> shift(i)) & 3u;
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -274,7 +277,7 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
   const uint32_t* tbo = tb + (size_t)s * L.words(P.nB);
   int cn = n, ci = P.m, cj = P.nB;
   while (cn > 0) {
-    const uint32_t code = (tbo[L.word(cn, ci, cj)] >> L.shift(ci)) & 3u;
+    const uint32_t code = L.code(tbo, cn, ci, cj);
     if (code == 0) {
       MY(cn - 1) = make_short2((short)(ci - 1), (short)(cj - 1));
       cn--; ci--; cj--;
