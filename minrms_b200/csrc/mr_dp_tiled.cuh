@@ -7,27 +7,31 @@
 // bits per cell.  Written over the whole (n,i,j) box with the boundary values
 //     A(0,.,.) = 0,   A(n>=1, 0, j) = A(n>=1, i, 0) = +inf
 // it reproduces the reference's special-cased first row / first column of every layer
-// exactly: cells with i < n or j < n stay +inf and never win a min, live cells only ever
-// read live cells or those boundaries.
+// exactly: cells with i < n or j < n stay +inf and never win a min, and live cells only ever
+// read live cells or those boundaries (layer 0 is carried as a real, constant-0 layer).
 //
-// Mapping (one CTA = one orientation):
-//   * the sweep axis is j (columns of molecule 2), one column per step;
-//   * a thread owns a K x R register tile: K consecutive layers x R consecutive rows;
-//     lane = layer chunk (32 lanes x K layers >= n_max + 1; layer 0 is the constant-0 base
-//     layer so the lowest real layer needs no special case), warp = row strip;
-//   * A(n-1,i-1,j-1) for the lowest layer of a lane comes from the neighbouring lane's
-//     previous-column registers by warp shuffle (the previous column is complete, so no
-//     skew is needed between lanes); inside the tile it is a register of the same thread;
-//   * A(n,i-1,j) across strips goes through a double-buffered shared-memory row of
-//     boundary values; strip w runs one column behind strip w-1 (wavefront over warps),
-//     one __syncthreads per step;
-//   * C(i,j) is built once per orientation into shared memory, transposed ([j][i]) and
-//     padded with +inf rows/columns so pipeline fill/drain steps leave the state untouched;
-//   * the two tie-break predicates are taken from the sign bits of (d - up) and
-//     (best - left) (exact for IEEE floats) and funnel-shifted into a per-layer bit
-//     accumulator: 3 FADD (FMA pipe) + 1 FMNMX3 + 2 SHF (ALU pipe) per cell.
+// Mapping (one CTA = one orientation, a small dataflow machine):
+//   * the sweep axis is j (columns of molecule 2), one column per step; the (layer,row)
+//     cross-section is cut into K x R tiles (K consecutive layers x R consecutive rows) and
+//     every LIVE tile is owned by one thread, which keeps it in registers for the whole
+//     sweep; the tiles of row strip w run w columns behind strip 0 (wavefront);
+//   * per step a thread reads, from shared memory, the K boundary values A(n, i_lo-1, j) its
+//     upper neighbour published one step earlier and the R values A(n_lo-1, i-1, j-1) its
+//     lower-layer neighbour published one step earlier, updates its K*R cells in registers
+//     and publishes its own bottom row / top layer (double-buffered by step parity, one
+//     __syncthreads per step).  No warp shuffles: neighbours may sit anywhere, so
+//   * tiles are packed into warps sorted by the step at which they become live (cells with
+//     j < n are dead): a warp skips the steps outside the window of its lanes, which removes
+//     most of the triangular waste of the (n <= i, n <= j) pyramid;
+//   * C(i,j) = |A_i - B'_j|^2 is produced one column ahead by the first threads of the CTA
+//     into a 32-column shared-memory ring (+inf outside the matrix, so pipeline fill and
+//     drain steps leave the state untouched);
+//   * the two tie-break predicates are the sign bits of (d - up) and (best - left) (exact
+//     for IEEE floats), funnel-shifted into a per-layer accumulator:
+//     3 FADD (FMA pipes) + FMNMX3 + 2 SHF (ALU pipe) per cell.
 #pragma once
 #include <algorithm>
+#include <vector>
 #include "mr_device.cuh"
 
 // Traceback storage of the tiled kernel.  One 32-bit word per (strip, column pair, layer):
@@ -35,90 +39,105 @@
 // bit pair of cell (row r of the strip, column half h): s1 at bit 31-(16h+2r), s2 one below.
 //   s1 = 1  <=>  NOT (up <= d)        s2 = 1  <=>  NOT (left <= min(d,up))
 struct TbTiled {
-  int K, R, W, JP, pad, NP;  // layers/lane, rows/strip, strips, column pairs, top padding rows
-  __host__ __device__ size_t words(int /*nB*/) const { return (size_t)W * JP * 32 * K; }
+  int K, R, W, JP, pad, NP, CN;  // layers/tile, rows/tile, strips, column pairs, top pad rows, cost pitch, chunks
+  __host__ __device__ size_t words(int /*nB*/) const { return (size_t)W * JP * CN * K; }
   __device__ __forceinline__ uint32_t code(const uint32_t* __restrict__ tbo, int n, int i, int j) const {
     const int rho = i - 1 + pad;
     const int w = rho / R, r = rho - w * R;
     const int c = n / K, k = n - c * K;
     const int jp = (j - 1) >> 1, h = (j - 1) & 1;
-    const uint32_t word = tbo[((size_t)w * JP + jp) * (32 * K) + k * 32 + c];
+    const uint32_t word = tbo[((size_t)w * JP + jp) * (CN * K) + k * CN + c];
     const int a = h * 2 * R + 2 * r;
     const uint32_t s1 = (word >> (31 - a)) & 1u, s2 = (word >> (30 - a)) & 1u;
     return s2 ? (s1 ? 0u : 1u) : 2u;
   }
 };
 
+// one entry per thread of the CTA (built on the host by mr_plan_dp_tiled)
+struct MrTile {
+  int w, c;              // row strip, layer chunk (-1: idle thread)
+  int s_lo, s_hi;        // first / last step at which this tile has live cells
+  int up_slot, dg_slot;  // exchange slots of the tiles (w-1,c) and (w,c-1) (or an INIT slot)
+  int warp_lo, warp_hi;  // step window of the whole warp
+};
+
 struct MrTiledPlan {
   bool ok = false;
   const char* why = "not planned";
-  int K = 0, R = 8, W = 0;
-  int nBe = 0;            // columns rounded up to even
-  int threads = 0;
+  int K = 0, R = 8, W = 0, CN = 0;
+  int nBe = 0;  // columns rounded up to even
+  int threads = 0, nslots = 0, steps = 0;
   size_t smem = 0;
   int ctas_per_sm = 1;
   int grid_cap = 0;
   size_t tb_words = 0;
+  double lane_efficiency = 0.0;
   TbTiled layout;
+  MrTile* d_tiles = nullptr;
 };
 
-template <int K, int R, int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, 1)
-k_dp_tiled(MrDevParams P, TbTiled L, int nBe, const float* __restrict__ A, const float* __restrict__ B,
-           const float* __restrict__ orient, const int* __restrict__ surv,
-           const int* __restrict__ surv_count, uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
-  extern __shared__ float smem[];
+#define MR_CRING 32  // columns in the C ring (>= strips + 2)
+
+template <int K, int R, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_dp_tiles(MrDevParams P, TbTiled L, int nBe, int nslots, int nsteps, const MrTile* __restrict__ tiles,
+           const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
+           const int* __restrict__ surv, const int* __restrict__ surv_count,
+           uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
+  static_assert(R == 8, "traceback word packing assumes 8 rows per tile");
+  extern __shared__ float4 smem4[];
   const int m = P.m, nB = P.nB, nb = P.nb;
-  const int W = L.W, WR = W * R, pad = L.pad, JP = L.JP;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;  // warp = strip, lane = layer chunk
-  const int LT = 32 * K;
-  float* sB = smem;                                   // rotated molecule 2: nB*nb*3
-  float* Ct = sB + ((nB * nb * 3 + 3) & ~3);          // (nBe+2) x WR, column jc in 0..nBe+1
-  float* ring = Ct + (size_t)(nBe + 2) * WR;          // 2 x W x LT boundary rows
+  const int W = L.W, WR = W * R, pad = L.pad, JP = L.JP, CN = L.CN;
+  const int tid = threadIdx.x;
+  // shared memory carve-up (all 16-byte aligned)
+  float4* dgA = smem4;             // [2][nslots] published top layer: {upper boundary, rows 0..2}
+  float4* dgB = dgA + 2 * nslots;  // [2][nslots] rows 3..6
+  float* bnd = reinterpret_cast<float*>(dgB + 2 * nslots);  // [2][nslots][K] published bottom rows
+  float* Cr = bnd + ((2 * nslots * K + 3) & ~3);            // [MR_CRING][WR] distance columns
+  float* sB = Cr + MR_CRING * WR;                           // rotated molecule 2: nB*nb*3
+  float* sA = sB + ((nB * nb * 3 + 3) & ~3);                // molecule 1: m*nb*3
   const float INF = __int_as_float(0x7f800000);
   const int nsurv = *surv_count;
 
-  // per-layer constants of this lane
-  float initk[K];
+  const MrTile me = tiles[tid];
+  const bool has_tile = me.w >= 0;
+  const int w = has_tile ? me.w : 0, c = has_tile ? me.c : 0;
+  const int slot = tid;  // own exchange slot
+  // live column window of each of my layers (for the traceback stores)
   int jlo[K], jhi[K];
+  float initk[K];
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    const int n = lane * K + k;
+    const int n = c * K + k;
     initk[k] = (n == 0) ? 0.0f : INF;
-    // columns where layer n has live cells in this strip (rows i_lo..i_hi of the strip)
     const int i_lo = w * R + 1 - pad, i_hi = w * R + R - pad;
     const int imax = min(m, n + P.wA - 1);
-    const bool live = n >= 1 && n <= P.n_max && n <= i_hi && i_lo <= imax;
+    const bool live = has_tile && n >= 1 && n <= P.n_max && n <= i_hi && i_lo <= imax;
     jlo[k] = live ? n : 0x3fffffff;
     jhi[k] = live ? min(nB, n + P.wB - 1) : -1;
   }
+  for (int k = tid; k < m * nb * 3; k += blockDim.x) sA[k] = A[k];
 
   for (int sv = blockIdx.x; sv < nsurv; sv += gridDim.x) {
     const float* T = orient + 12 * (size_t)surv[sv];
     __syncthreads();
-    for (int k = threadIdx.x; k < nB * nb; k += blockDim.x) {
+    for (int k = tid; k < nB * nb; k += blockDim.x) {
       float x, y, z;
       mr_xform(T, B[3 * k], B[3 * k + 1], B[3 * k + 2], x, y, z);
       sB[3 * k] = x; sB[3 * k + 1] = y; sB[3 * k + 2] = z;
     }
-    for (int k = threadIdx.x; k < 2 * W * LT; k += blockDim.x) ring[k] = (k % LT == 0) ? 0.0f : INF;  // layer 0 (lane 0, k 0) is the constant-0 base layer
-    __syncthreads();
-    // distance matrix, transposed and padded (Dyn3d::FillLookupTable, dyn3d.cc:664-701)
-    for (int idx = threadIdx.x; idx < (nBe + 2) * WR; idx += blockDim.x) {
-      const int jc = idx / WR, rho = idx - jc * WR;
-      const int i = rho - pad + 1;
-      float c = INF;
-      if (jc >= 1 && jc <= nB && i >= 1) {
-        c = 0.0f;
-        for (int q = 0; q < nb; q++) {
-          const float* a = A + 3 * ((i - 1) * nb + q);
-          const float* b = sB + 3 * ((jc - 1) * nb + q);
-          c += mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
-        }
-        if (c > P.dp_cutoff) c = MR_UB;
-      }
-      Ct[idx] = c;
+    // exchange slots start at the boundary values
+    // (slot nslots-2: {0, inf, ..} above strip 0 for chunk 0; slot nslots-1: all +inf)
+    for (int k = tid; k < 2 * nslots; k += blockDim.x) {
+      dgA[k] = make_float4(INF, INF, INF, INF);
+      dgB[k] = make_float4(INF, INF, INF, INF);
     }
+    for (int k = tid; k < 2 * nslots * K; k += blockDim.x) {
+      const int sl = (k / K) % nslots, kk = k % K;
+      const bool zero = kk == 0 && (sl == nslots - 2 || (sl < nslots - 2 && tiles[sl].c == 0));
+      bnd[k] = zero ? 0.0f : INF;
+    }
+    for (int k = tid; k < MR_CRING * WR; k += blockDim.x) Cr[k] = INF;
     __syncthreads();
 
     float st[K][R], bprev[K];
@@ -131,93 +150,141 @@ k_dp_tiled(MrDevParams P, TbTiled L, int nBe, const float* __restrict__ A, const
       for (int r = 0; r < R; r++) st[k][r] = initk[k];
     }
     uint32_t* tbo = tb + (size_t)sv * L.words(nB);
-    const int S = nBe + W - 1;
-    for (int s = 1; s <= S; s++) {
-      const int j = s - w;
-      const int jc = min(max(j, 0), nBe + 1);
-      // C(i, j) for the R rows of this strip
-      float c[R];
-      {
-        const float4* cp = reinterpret_cast<const float4*>(Ct + (size_t)jc * WR + w * R);
-#pragma unroll
-        for (int q = 0; q < R / 4; q++) {
-          const float4 v = cp[q];
-          c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
-        }
-      }
-      // A(n, i_lo - 1, j) for my layers: boundary row written by the strip above last step
-      float bin[K];
-      if (w == 0) {
-#pragma unroll
-        for (int k = 0; k < K; k++) bin[k] = initk[k];
-      } else {
-        const float* rp = ring + ((size_t)((s - 1) & 1) * W + (w - 1)) * LT;
-#pragma unroll
-        for (int k = 0; k < K; k++) bin[k] = rp[k * 32 + lane];
-      }
-      // A(n0-1, i-1, j-1) for my lowest layer: neighbour lane's highest layer, previous column
-      float dsh[R];
-      dsh[0] = __shfl_up_sync(0xffffffffu, bprev[K - 1], 1);
-#pragma unroll
-      for (int r = 1; r < R; r++) dsh[r] = __shfl_up_sync(0xffffffffu, st[K - 1][r - 1], 1);
 
-#pragma unroll
-      for (int k = K - 1; k >= 0; k--) {
-        float up = bin[k];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
-          const float d = dg + c[r];
-          const float left = st[k][r];
-          const float best = fminf(fminf(d, up), left);
-          const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
-          const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
-          acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
-          acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
-          st[k][r] = best;
-          up = best;
+    // column 1 of C before the first step
+    for (int rho = tid; rho < WR; rho += blockDim.x) {
+      const int i = rho - pad + 1;
+      float cc = INF;
+      if (i >= 1) {
+        cc = 0.0f;
+        for (int q = 0; q < nb; q++) {
+          const float* a = sA + 3 * ((i - 1) * nb + q);
+          const float* b = sB + 3 * q;
+          cc += mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
         }
+        if (cc > P.dp_cutoff) cc = MR_UB;
       }
-      // hand the bottom row of this strip to the strip below; remember this column's top boundary
-      {
-        float* wp = ring + ((size_t)(s & 1) * W + w) * LT;
+      Cr[1 * WR + rho] = cc;
+    }
+    __syncthreads();
+
+    for (int s = 1; s <= nsteps; s++) {
+      const int par = s & 1;
+      if (s >= me.warp_lo && s <= me.warp_hi) {
+        const int j = s - w;
+        // C(i, j) for my R rows: ring column j & 31 (columns <= 0 and > nB hold +inf)
+        float cv[R];
+        {
+          const float4* cp = reinterpret_cast<const float4*>(Cr + (size_t)(j & (MR_CRING - 1)) * WR + w * R);
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-          wp[k * 32 + lane] = st[k][R - 1];
-          bprev[k] = bin[k];
-        }
-      }
-      // traceback words: one per layer every second column
-      if (j >= 1 && j <= nBe && (j & 1) == 0) {
-        uint32_t* tw = tbo + ((size_t)w * JP + ((j - 1) >> 1)) * LT + lane;
-#pragma unroll
-        for (int k = 0; k < K; k++)
-          if (j >= jlo[k] && j - 1 <= jhi[k]) tw[k * 32] = acc[k];
-      }
-      // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
-      if (j == nB && w == W - 1) {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          const int n = lane * K + k;
-          if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
-        }
-      }
-      // n < n_min: the reference reports the corner of the layer's window,
-      // A(n, n+wA-1, n+wB-1) (dyn3d.cc:385, dyn3d.h:407-408): one layer per column
-      if (P.n_min > 1) {
-        const int nq = j - P.wB + 1;
-        if (nq >= 1 && nq < P.n_min && nq <= P.n_max && nq / K == lane) {
-          const int rho = nq + P.wA - 2 + pad;
-          if (rho / R == w) {
-            const int kq = nq - lane * K, rq = rho - w * R;
-            float v = 0.0f;
-#pragma unroll
-            for (int k = 0; k < K; k++)
-#pragma unroll
-              for (int r = 0; r < R; r++)
-                if (k == kq && r == rq) v = st[k][r];
-            cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+          for (int q = 0; q < R / 4; q++) {
+            const float4 v = cp[q];
+            cv[4 * q] = v.x; cv[4 * q + 1] = v.y; cv[4 * q + 2] = v.z; cv[4 * q + 3] = v.w;
           }
+        }
+        // A(n, i_lo-1, j): the bottom row the tile above published last step
+        float bin[K];
+        {
+          const float* bp = bnd + ((size_t)(par ^ 1) * nslots + me.up_slot) * K;
+          if (K == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(bp);
+            bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) bin[k] = bp[k];
+          }
+        }
+        // A(n_lo-1, i-1, j-1) for my lowest layer: what the lower-layer tile published last
+        // step = {its upper boundary, rows 0..6} of its top layer after column j-1
+        float dsh[R];
+        {
+          const float4 a4 = dgA[(par ^ 1) * nslots + me.dg_slot];
+          const float4 b4 = dgB[(par ^ 1) * nslots + me.dg_slot];
+          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
+        }
+#pragma unroll
+        for (int k = K - 1; k >= 0; k--) {
+          float up = bin[k];
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
+            const float d = dg + cv[r];
+            const float left = st[k][r];
+            const float best = fminf(fminf(d, up), left);
+            const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
+            const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
+            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+            st[k][r] = best;
+            up = best;
+          }
+        }
+        // publish: bottom row (for the tile below, same column, next step) and top layer
+        // shifted down one row (for the tile one chunk up, next column, next step)
+        {
+          float* bo = bnd + ((size_t)par * nslots + slot) * K;
+          if (K == 4) {
+            *reinterpret_cast<float4*>(bo) = make_float4(st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) bo[k] = st[k][R - 1];
+          }
+          dgA[par * nslots + slot] = make_float4(bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
+          dgB[par * nslots + slot] = make_float4(st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
+#pragma unroll
+          for (int k = 0; k < K; k++) bprev[k] = bin[k];
+        }
+        // traceback words: one per layer every second column
+        if (j >= 1 && j <= nBe && (j & 1) == 0) {
+          uint32_t* tw = tbo + ((size_t)w * JP + ((j - 1) >> 1)) * (CN * K) + c;
+#pragma unroll
+          for (int k = 0; k < K; k++)
+            if (j >= jlo[k] && j - 1 <= jhi[k]) tw[k * CN] = acc[k];
+        }
+        // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
+        if (j == nB && w == W - 1 && has_tile) {
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const int n = c * K + k;
+            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
+          }
+        }
+        // n < n_min: the reference reports the corner of the layer's window,
+        // A(n, n+wA-1, n+wB-1) (dyn3d.cc:385, dyn3d.h:407-408): one layer per column
+        if (P.n_min > 1 && has_tile) {
+          const int nq = j - P.wB + 1;
+          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && nq / K == c) {
+            const int rho = nq + P.wA - 2 + pad;
+            if (rho / R == w) {
+              const int kq = nq - c * K, rq = rho - w * R;
+              float v = 0.0f;
+#pragma unroll
+              for (int k = 0; k < K; k++)
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                  if (k == kq && r == rq) v = st[k][r];
+              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+            }
+          }
+        }
+      }
+      // produce column s+1 of C (needed by strip 0 at the next step)
+      {
+        const int jn = s + 1;
+        for (int rho = tid; rho < WR; rho += blockDim.x) {
+          const int i = rho - pad + 1;
+          float cc = INF;
+          if (i >= 1 && jn <= nB) {
+            cc = 0.0f;
+            for (int q = 0; q < nb; q++) {
+              const float* a = sA + 3 * ((i - 1) * nb + q);
+              const float* b = sB + 3 * ((jn - 1) * nb + q);
+              cc += mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
+            }
+            if (cc > P.dp_cutoff) cc = MR_UB;
+          }
+          Cr[(size_t)(jn & (MR_CRING - 1)) * WR + rho] = cc;
         }
       }
       __syncthreads();
@@ -225,68 +292,127 @@ k_dp_tiled(MrDevParams P, TbTiled L, int nBe, const float* __restrict__ A, const
   }
 }
 
+// ---------------------------------------------------------------------------------- host
+static inline void mr_free_dp_tiled(MrTiledPlan* p) {
+  if (p->d_tiles) cudaFree(p->d_tiles);
+  p->d_tiles = nullptr;
+}
+
 static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const cudaDeviceProp& prop, int NP) {
   p->ok = false;
-  const int R = 8;
-  const int K = (P.n_max + 1 + 31) / 32;
-  if (K > 6) { p->why = "n_max + 1 > 192 layers"; return; }
-  const int W = (P.m + R - 1) / R;
-  if (W > 32) { p->why = "more than 256 rows"; return; }
-  const int nBe = (P.nB + 1) & ~1;
-  const size_t smem = 4 * (size_t)(((P.nB * P.nb * 3 + 3) & ~3) + (size_t)(nBe + 2) * W * R + 2 * (size_t)W * 32 * K);
-  if (smem > prop.sharedMemPerBlockOptin) { p->why = "distance matrix does not fit shared memory"; return; }
-  p->K = K; p->R = R; p->W = W; p->nBe = nBe;
-  p->threads = 32 * W;
+  const int R = 8, K = 4;
+  const int m = P.m, nB = P.nB;
+  const int W = (m + R - 1) / R, pad = W * R - m;
+  const int CN = (P.n_max + 1 + K - 1) / K;  // chunks incl. the constant layer 0
+  const int nBe = (nB + 1) & ~1;
+  if (W + 2 > MR_CRING) { p->why = "more than 240 rows"; return; }
+  // live tiles and their step windows
+  struct T { int w, c, lo, hi; };
+  std::vector<T> ts;
+  std::vector<int> index((size_t)W * CN, -1);
+  long long live_cells = 0;
+  for (int n = 1; n <= P.n_max; n++)
+    live_cells += (long long)(std::min(m, n + P.wA - 1) - n + 1) * (std::min(nB, n + P.wB - 1) - n + 1);
+  for (int w = 0; w < W; w++) {
+    const int i_lo = w * R + 1 - pad, i_hi = w * R + R - pad;
+    for (int c = 0; c < CN; c++) {
+      int jlo = 1 << 30, jhi = -1;
+      for (int n = std::max(1, c * K); n <= std::min(P.n_max, c * K + K - 1); n++) {
+        const int imax = std::min(m, n + P.wA - 1);
+        if (std::max(n, i_lo) > std::min(imax, i_hi)) continue;
+        jlo = std::min(jlo, n);
+        jhi = std::max(jhi, std::min(nB, n + P.wB - 1));
+      }
+      if (c == 0) { jlo = std::min(jlo, 1); jhi = std::max(jhi, 1); }  // the base-layer chain always exists
+      if (jhi < 0) continue;
+      jhi = (jhi + 1) & ~1;  // finish the traceback word of the last column pair
+      ts.push_back({w, c, jlo + w, jhi + w});
+    }
+  }
+  // closure: the lowest layer of tile (w,c) reads A(n_lo-1, i_lo-1, j-1) from what tile
+  // (w,c-1) relays of ITS upper boundary, so (w,c-1) must run even where all of its own
+  // cells are outside the band (-minN > 1): add it with the window of (w,c), one step early
+  {
+    std::vector<int> have((size_t)W * CN, -1);
+    for (size_t t = 0; t < ts.size(); t++) have[(size_t)ts[t].w * CN + ts[t].c] = (int)t;
+    const size_t n0 = ts.size();
+    for (size_t t = 0; t < n0; t++) {
+      const T x = ts[t];
+      if (x.c >= 1 && have[(size_t)x.w * CN + x.c - 1] < 0) {
+        have[(size_t)x.w * CN + x.c - 1] = (int)ts.size();
+        ts.push_back({x.w, x.c - 1, std::max(1, x.lo - 1), x.hi});
+      }
+    }
+  }
+  std::stable_sort(ts.begin(), ts.end(), [](const T& a, const T& b) { return a.lo != b.lo ? a.lo < b.lo : a.hi < b.hi; });
+  const int ntiles = (int)ts.size();
+  const int threads = ((ntiles + 31) / 32) * 32;
+  if (threads > 1024) { p->why = "more than 1024 live tiles"; return; }
+  for (int t = 0; t < ntiles; t++) index[(size_t)ts[t].w * CN + ts[t].c] = t;
+  const int nslots = threads + 2;
+  std::vector<MrTile> tab((size_t)threads);
+  int steps = 0;
+  long long warp_steps = 0;
+  for (int wp = 0; wp < threads / 32; wp++) {
+    int lo = 1 << 30, hi = -1;
+    for (int t = wp * 32; t < std::min(ntiles, wp * 32 + 32); t++) { lo = std::min(lo, ts[t].lo); hi = std::max(hi, ts[t].hi); }
+    warp_steps += hi - lo + 1;
+    steps = std::max(steps, hi);
+    for (int t = wp * 32; t < wp * 32 + 32; t++) {
+      MrTile& e = tab[t];
+      e.warp_lo = lo; e.warp_hi = hi;
+      if (t >= ntiles) { e.w = -1; e.c = -1; e.s_lo = 1 << 30; e.s_hi = -1; e.up_slot = nslots - 1; e.dg_slot = nslots - 1; continue; }
+      e.w = ts[t].w; e.c = ts[t].c; e.s_lo = ts[t].lo; e.s_hi = ts[t].hi;
+      const int up = (e.w > 0) ? index[(size_t)(e.w - 1) * CN + e.c] : -1;
+      const int dg = (e.c > 0) ? index[(size_t)e.w * CN + e.c - 1] : -1;
+      e.up_slot = up >= 0 ? up : ((e.c == 0) ? nslots - 2 : nslots - 1);
+      e.dg_slot = dg >= 0 ? dg : nslots - 1;
+    }
+  }
+  const size_t smem = 16 * (size_t)(4 * nslots) + 4 * (size_t)(((2 * nslots * K + 3) & ~3) + MR_CRING * W * R +
+                                                              ((nB * P.nb * 3 + 3) & ~3) + m * P.nb * 3);
+  if (smem > prop.sharedMemPerBlockOptin) { p->why = "work space does not fit shared memory"; return; }
+  mr_free_dp_tiled(p);
+  if (cudaMalloc(&p->d_tiles, sizeof(MrTile) * tab.size()) != cudaSuccess) { p->why = "cudaMalloc"; return; }
+  if (cudaMemcpy(p->d_tiles, tab.data(), sizeof(MrTile) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) { p->why = "cudaMemcpy"; return; }
+  p->K = K; p->R = R; p->W = W; p->CN = CN; p->nBe = nBe;
+  p->threads = threads; p->nslots = nslots; p->steps = steps;
   p->smem = smem;
-  p->ctas_per_sm = 1;
+  const int by_smem = (int)(prop.sharedMemPerMultiprocessor / (smem + 1024));
+  int want = threads <= 256 ? 3 : (threads <= 384 ? 2 : 1);
+  p->ctas_per_sm = std::max(1, std::min(by_smem, want));
   p->grid_cap = prop.multiProcessorCount * p->ctas_per_sm;
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
-  p->layout.pad = W * R - P.m; p->layout.NP = NP;
-  p->tb_words = p->layout.words(P.nB);
+  p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN;
+  p->tb_words = p->layout.words(nB);
+  p->lane_efficiency = (double)live_cells / ((double)warp_steps * 32 * K * R);
   p->ok = true;
   p->why = "";
 }
 
-static inline void mr_free_dp_tiled(MrTiledPlan*) {}
-
-template <int K, int MAXW>
-static inline int mr_launch_dp_tiled_kw(const MrTiledPlan& p, const MrDevParams& P, const float* A,
+template <int MAXT, int MINB>
+static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& P, const float* A,
                                        const float* B, const float* orient, const int* surv,
                                        const int* surv_count, uint32_t* tb, float* cost, int count,
                                        cudaStream_t stream) {
-  auto kern = k_dp_tiled<K, 8, MAXW>;
+  auto kern = k_dp_tiles<4, 8, MAXT, MINB>;
   static size_t attr_set = 0;
   if (attr_set < p.smem) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
     attr_set = p.smem;
   }
   const int grid = std::min(count, p.grid_cap);
-  kern<<<grid, p.threads, p.smem, stream>>>(P, p.layout, p.nBe, A, B, orient, surv, surv_count, tb, cost);
+  kern<<<grid, p.threads, p.smem, stream>>>(P, p.layout, p.nBe, p.nslots, p.steps, p.d_tiles, A, B, orient,
+                                           surv, surv_count, tb, cost);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
-}
-
-template <int K>
-static inline int mr_launch_dp_tiled_k(const MrTiledPlan& p, const MrDevParams& P, const float* A,
-                                       const float* B, const float* orient, const int* surv,
-                                       const int* surv_count, uint32_t* tb, float* cost, int count,
-                                       cudaStream_t stream) {
-  if (p.W <= 12) return mr_launch_dp_tiled_kw<K, 12>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-  if (p.W <= 18) return mr_launch_dp_tiled_kw<K, 18>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-  if (p.W <= 24) return mr_launch_dp_tiled_kw<K, 24>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-  return mr_launch_dp_tiled_kw<K, 32>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
 }
 
 static inline int mr_launch_dp_tiled(const MrTiledPlan& p, const MrDevParams& P, const float* A,
                                      const float* B, const float* orient, const int* surv,
                                      const int* surv_count, uint32_t* tb, float* cost, int count,
                                      cudaStream_t stream) {
-  switch (p.K) {
-    case 1: return mr_launch_dp_tiled_k<1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-    case 2: return mr_launch_dp_tiled_k<2>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-    case 3: return mr_launch_dp_tiled_k<3>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-    case 4: return mr_launch_dp_tiled_k<4>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-    case 5: return mr_launch_dp_tiled_k<5>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-    case 6: return mr_launch_dp_tiled_k<6>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-  }
-  return 1;
+  if (p.threads <= 256) return mr_launch_dp_tiles_t<256, 3>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+  if (p.threads <= 384) return mr_launch_dp_tiles_t<384, 2>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+  if (p.threads <= 640) return mr_launch_dp_tiles_t<640, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+  return mr_launch_dp_tiles_t<1024, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
 }
