@@ -34,19 +34,24 @@
 #include <vector>
 #include "mr_device.cuh"
 
-// Traceback storage of the tiled kernel.  One 32-bit word per (strip, column pair, layer):
-// 2 columns x R=8 rows x 2 bits, appended MSB-first in processing order.
+// Traceback storage of the tiled kernel.  Each tile (thread t of the CTA) writes, every
+// second column, one 32-bit word per layer of the tile: 2 columns x R=8 rows x 2 bits,
+// appended MSB-first in processing order; the K words of a tile are one 16-byte store and
+// the stores of a warp are contiguous: word index = ((jp * T) + t) * K + k.
 // bit pair of cell (row r of the strip, column half h): s1 at bit 31-(16h+2r), s2 one below.
 //   s1 = 1  <=>  NOT (up <= d)        s2 = 1  <=>  NOT (left <= min(d,up))
+// tile_of[w * CN + c] maps (strip, chunk) to the owning thread.
 struct TbTiled {
-  int K, R, W, JP, pad, NP, CN;  // layers/tile, rows/tile, strips, column pairs, top pad rows, cost pitch, chunks
-  __host__ __device__ size_t words(int /*nB*/) const { return (size_t)W * JP * CN * K; }
+  int K, R, W, JP, pad, NP, CN, T;  // layers/tile, rows/tile, strips, column pairs, top pad rows, cost pitch, chunks, threads
+  const int* tile_of;
+  __host__ __device__ size_t words(int /*nB*/) const { return (size_t)JP * T * K; }
   __device__ __forceinline__ uint32_t code(const uint32_t* __restrict__ tbo, int n, int i, int j) const {
     const int rho = i - 1 + pad;
     const int w = rho / R, r = rho - w * R;
     const int c = n / K, k = n - c * K;
     const int jp = (j - 1) >> 1, h = (j - 1) & 1;
-    const uint32_t word = tbo[((size_t)w * JP + jp) * (CN * K) + k * CN + c];
+    const int t = tile_of[w * CN + c];
+    const uint32_t word = tbo[((size_t)jp * T + t) * K + k];
     const int a = h * 2 * R + 2 * r;
     const uint32_t s1 = (word >> (31 - a)) & 1u, s2 = (word >> (30 - a)) & 1u;
     return s2 ? (s1 ? 0u : 1u) : 2u;
@@ -74,26 +79,57 @@ struct MrTiledPlan {
   double lane_efficiency = 0.0;
   TbTiled layout;
   MrTile* d_tiles = nullptr;
+  int* d_tile_of = nullptr;
 };
 
-#define MR_CRING 32  // columns in the C ring (>= strips + 2)
+#define MR_CRING 32  // columns in the C ring (>= strips + MR_CBATCH)
+#define MR_CBATCH 8  // columns of C produced at a time
 
-template <int K, int R, int MAXT, int MINB>
+// distance columns [j0, j0+MR_CBATCH) into the ring, all threads of the CTA
+template <bool NB1>
+__device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float* __restrict__ sA,
+                                             const float* __restrict__ sB, int j0, int WR, int pad,
+                                             int nB, int nb, float cutoff, int tid, int nthreads) {
+  const float INF = __int_as_float(0x7f800000);
+  for (int e = tid; e < MR_CBATCH * WR; e += nthreads) {
+    const int dj = e / WR, rho = e - dj * WR;
+    const int jn = j0 + dj, i = rho - pad + 1;
+    float cc = INF;
+    if (i >= 1 && jn <= nB) {
+      if (NB1) {
+        const float* a = sA + 3 * (i - 1);
+        const float* b = sB + 3 * (jn - 1);
+        cc = mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
+      } else {
+        cc = 0.0f;
+        for (int q = 0; q < nb; q++) {
+          const float* a = sA + 3 * ((i - 1) * nb + q);
+          const float* b = sB + 3 * ((jn - 1) * nb + q);
+          cc += mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
+        }
+      }
+      if (cc > cutoff) cc = MR_UB;
+    }
+    Cr[(jn & (MR_CRING - 1)) * WR + rho] = cc;
+  }
+}
+
+template <int K, int R, int MAXT, int MINB, bool NB1>
 __global__ void __launch_bounds__(MAXT, MINB)
-k_dp_tiles(MrDevParams P, TbTiled L, int nBe, int nslots, int nsteps, const MrTile* __restrict__ tiles,
+k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
            const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
            const int* __restrict__ surv, const int* __restrict__ surv_count,
            uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
-  static_assert(R == 8, "traceback word packing assumes 8 rows per tile");
+  static_assert(R == 8 && K == 4, "traceback word packing assumes 4 x 8 tiles");
   extern __shared__ float4 smem4[];
   const int m = P.m, nB = P.nB, nb = P.nb;
-  const int W = L.W, WR = W * R, pad = L.pad, JP = L.JP, CN = L.CN;
-  const int tid = threadIdx.x;
+  const int W = L.W, WR = W * R, pad = L.pad;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
   // shared memory carve-up (all 16-byte aligned)
-  float4* dgA = smem4;             // [2][nslots] published top layer: {upper boundary, rows 0..2}
-  float4* dgB = dgA + 2 * nslots;  // [2][nslots] rows 3..6
-  float* bnd = reinterpret_cast<float*>(dgB + 2 * nslots);  // [2][nslots][K] published bottom rows
-  float* Cr = bnd + ((2 * nslots * K + 3) & ~3);            // [MR_CRING][WR] distance columns
+  float4* dgA = smem4;                 // [2][nslots] published top layer: {upper boundary, rows 0..2}
+  float4* dgB = dgA + 2 * nslots;      // [2][nslots] rows 3..6
+  float4* bnd = dgB + 2 * nslots;      // [2][nslots] published bottom rows (K = 4 layers)
+  float* Cr = reinterpret_cast<float*>(bnd + 2 * nslots);  // [MR_CRING][WR] distance columns
   float* sB = Cr + MR_CRING * WR;                           // rotated molecule 2: nB*nb*3
   float* sA = sB + ((nB * nb * 3 + 3) & ~3);                // molecule 1: m*nb*3
   const float INF = __int_as_float(0x7f800000);
@@ -102,104 +138,74 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nBe, int nslots, int nsteps, const MrTi
   const MrTile me = tiles[tid];
   const bool has_tile = me.w >= 0;
   const int w = has_tile ? me.w : 0, c = has_tile ? me.c : 0;
-  const int slot = tid;  // own exchange slot
-  // live column window of each of my layers (for the traceback stores)
-  int jlo[K], jhi[K];
-  float initk[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    const int n = c * K + k;
-    initk[k] = (n == 0) ? 0.0f : INF;
-    const int i_lo = w * R + 1 - pad, i_hi = w * R + R - pad;
-    const int imax = min(m, n + P.wA - 1);
-    const bool live = has_tile && n >= 1 && n <= P.n_max && n <= i_hi && i_lo <= imax;
-    jlo[k] = live ? n : 0x3fffffff;
-    jhi[k] = live ? min(nB, n + P.wB - 1) : -1;
-  }
-  for (int k = tid; k < m * nb * 3; k += blockDim.x) sA[k] = A[k];
+  const int warp_lo = me.warp_lo, warp_hi = me.warp_hi;
+  // steps at which this tile stores traceback words / reports costs
+  const int tb_lo = has_tile ? me.s_lo : 0x3fffffff, tb_hi = has_tile ? me.s_hi : -1;
+  const int cost_step = (has_tile && w == W - 1) ? nB + w : -1;
+  const float4* const cbase = reinterpret_cast<const float4*>(Cr + w * R);
+  const int cstride4 = WR / 4;
+  for (int k = tid; k < m * nb * 3; k += nthreads) sA[k] = A[k];
 
   for (int sv = blockIdx.x; sv < nsurv; sv += gridDim.x) {
     const float* T = orient + 12 * (size_t)surv[sv];
     __syncthreads();
-    for (int k = tid; k < nB * nb; k += blockDim.x) {
+    for (int k = tid; k < nB * nb; k += nthreads) {
       float x, y, z;
       mr_xform(T, B[3 * k], B[3 * k + 1], B[3 * k + 2], x, y, z);
       sB[3 * k] = x; sB[3 * k + 1] = y; sB[3 * k + 2] = z;
     }
     // exchange slots start at the boundary values
     // (slot nslots-2: {0, inf, ..} above strip 0 for chunk 0; slot nslots-1: all +inf)
-    for (int k = tid; k < 2 * nslots; k += blockDim.x) {
+    for (int k = tid; k < 2 * nslots; k += nthreads) {
+      const int sl = k % nslots;
+      const bool zero = sl == nslots - 2 || (sl < nslots - 2 && tiles[sl].c == 0);
       dgA[k] = make_float4(INF, INF, INF, INF);
       dgB[k] = make_float4(INF, INF, INF, INF);
+      bnd[k] = make_float4(zero ? 0.0f : INF, INF, INF, INF);
     }
-    for (int k = tid; k < 2 * nslots * K; k += blockDim.x) {
-      const int sl = (k / K) % nslots, kk = k % K;
-      const bool zero = kk == 0 && (sl == nslots - 2 || (sl < nslots - 2 && tiles[sl].c == 0));
-      bnd[k] = zero ? 0.0f : INF;
-    }
-    for (int k = tid; k < MR_CRING * WR; k += blockDim.x) Cr[k] = INF;
+    for (int k = tid; k < MR_CRING * WR; k += nthreads) Cr[k] = INF;
     __syncthreads();
+    mr_produce_c<NB1>(Cr, sA, sB, 1, WR, pad, nB, nb, P.dp_cutoff, tid, nthreads);
 
     float st[K][R], bprev[K];
     uint32_t acc[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      bprev[k] = initk[k];
+      const float v = (c * K + k == 0) ? 0.0f : INF;
+      bprev[k] = v;
       acc[k] = 0;
 #pragma unroll
-      for (int r = 0; r < R; r++) st[k][r] = initk[k];
+      for (int r = 0; r < R; r++) st[k][r] = v;
     }
-    uint32_t* tbo = tb + (size_t)sv * L.words(nB);
-
-    // column 1 of C before the first step
-    for (int rho = tid; rho < WR; rho += blockDim.x) {
-      const int i = rho - pad + 1;
-      float cc = INF;
-      if (i >= 1) {
-        cc = 0.0f;
-        for (int q = 0; q < nb; q++) {
-          const float* a = sA + 3 * ((i - 1) * nb + q);
-          const float* b = sB + 3 * q;
-          cc += mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
-        }
-        if (cc > P.dp_cutoff) cc = MR_UB;
-      }
-      Cr[1 * WR + rho] = cc;
-    }
+    uint4* tbo = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid;
     __syncthreads();
 
+    // read / write offsets of the parity-double-buffered exchange slots
+    int rd = nslots, wr = 0;  // step 1: read parity 0 ... wait: write parity (s&1), read the other
+    rd = 0; wr = nslots;      // s = 1: write slot set 1, read slot set 0
+    int col = (1 - w) & (MR_CRING - 1);
     for (int s = 1; s <= nsteps; s++) {
-      const int par = s & 1;
-      if (s >= me.warp_lo && s <= me.warp_hi) {
-        const int j = s - w;
+      if (s >= warp_lo && s <= warp_hi) {
         // C(i, j) for my R rows: ring column j & 31 (columns <= 0 and > nB hold +inf)
         float cv[R];
         {
-          const float4* cp = reinterpret_cast<const float4*>(Cr + (size_t)(j & (MR_CRING - 1)) * WR + w * R);
-#pragma unroll
-          for (int q = 0; q < R / 4; q++) {
-            const float4 v = cp[q];
-            cv[4 * q] = v.x; cv[4 * q + 1] = v.y; cv[4 * q + 2] = v.z; cv[4 * q + 3] = v.w;
-          }
+          const float4* cp = cbase + col * cstride4;
+          const float4 v0 = cp[0], v1 = cp[1];
+          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
+          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
         }
         // A(n, i_lo-1, j): the bottom row the tile above published last step
         float bin[K];
         {
-          const float* bp = bnd + ((size_t)(par ^ 1) * nslots + me.up_slot) * K;
-          if (K == 4) {
-            const float4 v = *reinterpret_cast<const float4*>(bp);
-            bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
-          } else {
-#pragma unroll
-            for (int k = 0; k < K; k++) bin[k] = bp[k];
-          }
+          const float4 v = bnd[rd + me.up_slot];
+          bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
         }
         // A(n_lo-1, i-1, j-1) for my lowest layer: what the lower-layer tile published last
         // step = {its upper boundary, rows 0..6} of its top layer after column j-1
         float dsh[R];
         {
-          const float4 a4 = dgA[(par ^ 1) * nslots + me.dg_slot];
-          const float4 b4 = dgB[(par ^ 1) * nslots + me.dg_slot];
+          const float4 a4 = dgA[rd + me.dg_slot];
+          const float4 b4 = dgB[rd + me.dg_slot];
           dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
           dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
         }
@@ -222,28 +228,16 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nBe, int nslots, int nsteps, const MrTi
         }
         // publish: bottom row (for the tile below, same column, next step) and top layer
         // shifted down one row (for the tile one chunk up, next column, next step)
-        {
-          float* bo = bnd + ((size_t)par * nslots + slot) * K;
-          if (K == 4) {
-            *reinterpret_cast<float4*>(bo) = make_float4(st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
-          } else {
+        bnd[wr + tid] = make_float4(st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
+        dgA[wr + tid] = make_float4(bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
+        dgB[wr + tid] = make_float4(st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
 #pragma unroll
-            for (int k = 0; k < K; k++) bo[k] = st[k][R - 1];
-          }
-          dgA[par * nslots + slot] = make_float4(bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
-          dgB[par * nslots + slot] = make_float4(st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
-#pragma unroll
-          for (int k = 0; k < K; k++) bprev[k] = bin[k];
-        }
-        // traceback words: one per layer every second column
-        if (j >= 1 && j <= nBe && (j & 1) == 0) {
-          uint32_t* tw = tbo + ((size_t)w * JP + ((j - 1) >> 1)) * (CN * K) + c;
-#pragma unroll
-          for (int k = 0; k < K; k++)
-            if (j >= jlo[k] && j - 1 <= jhi[k]) tw[k * CN] = acc[k];
-        }
+        for (int k = 0; k < K; k++) bprev[k] = bin[k];
+        // traceback: the K words of this tile every second column (j = s - w even)
+        if (((s - w) & 1) == 0 && s >= tb_lo && s <= tb_hi)
+          tbo[(size_t)((s - w - 1) >> 1) * nthreads] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
         // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
-        if (j == nB && w == W - 1 && has_tile) {
+        if (s == cost_step) {
 #pragma unroll
           for (int k = 0; k < K; k++) {
             const int n = c * K + k;
@@ -253,7 +247,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nBe, int nslots, int nsteps, const MrTi
         // n < n_min: the reference reports the corner of the layer's window,
         // A(n, n+wA-1, n+wB-1) (dyn3d.cc:385, dyn3d.h:407-408): one layer per column
         if (P.n_min > 1 && has_tile) {
-          const int nq = j - P.wB + 1;
+          const int nq = s - w - P.wB + 1;
           if (nq >= 1 && nq < P.n_min && nq <= P.n_max && nq / K == c) {
             const int rho = nq + P.wA - 2 + pad;
             if (rho / R == w) {
@@ -269,24 +263,11 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nBe, int nslots, int nsteps, const MrTi
           }
         }
       }
-      // produce column s+1 of C (needed by strip 0 at the next step)
-      {
-        const int jn = s + 1;
-        for (int rho = tid; rho < WR; rho += blockDim.x) {
-          const int i = rho - pad + 1;
-          float cc = INF;
-          if (i >= 1 && jn <= nB) {
-            cc = 0.0f;
-            for (int q = 0; q < nb; q++) {
-              const float* a = sA + 3 * ((i - 1) * nb + q);
-              const float* b = sB + 3 * ((jn - 1) * nb + q);
-              cc += mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
-            }
-            if (cc > P.dp_cutoff) cc = MR_UB;
-          }
-          Cr[(size_t)(jn & (MR_CRING - 1)) * WR + rho] = cc;
-        }
-      }
+      // every MR_CBATCH steps all threads produce the next MR_CBATCH columns of C
+      if ((s & (MR_CBATCH - 1)) == 0)
+        mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, pad, nB, nb, P.dp_cutoff, tid, nthreads);
+      col = (col + 1) & (MR_CRING - 1);
+      rd ^= wr; wr ^= rd; rd ^= wr;  // swap the parity sets
       __syncthreads();
     }
   }
@@ -295,7 +276,9 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nBe, int nslots, int nsteps, const MrTi
 // ---------------------------------------------------------------------------------- host
 static inline void mr_free_dp_tiled(MrTiledPlan* p) {
   if (p->d_tiles) cudaFree(p->d_tiles);
+  if (p->d_tile_of) cudaFree(p->d_tile_of);
   p->d_tiles = nullptr;
+  p->d_tile_of = nullptr;
 }
 
 static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const cudaDeviceProp& prop, int NP) {
@@ -305,7 +288,7 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   const int W = (m + R - 1) / R, pad = W * R - m;
   const int CN = (P.n_max + 1 + K - 1) / K;  // chunks incl. the constant layer 0
   const int nBe = (nB + 1) & ~1;
-  if (W + 2 > MR_CRING) { p->why = "more than 240 rows"; return; }
+  if (W + MR_CBATCH > MR_CRING) { p->why = "more than 192 rows"; return; }
   // live tiles and their step windows
   struct T { int w, c, lo, hi; };
   std::vector<T> ts;
@@ -369,12 +352,14 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
       e.dg_slot = dg >= 0 ? dg : nslots - 1;
     }
   }
-  const size_t smem = 16 * (size_t)(4 * nslots) + 4 * (size_t)(((2 * nslots * K + 3) & ~3) + MR_CRING * W * R +
-                                                              ((nB * P.nb * 3 + 3) & ~3) + m * P.nb * 3);
+  const size_t smem = 16 * (size_t)(6 * nslots) + 4 * (size_t)(MR_CRING * W * R + ((nB * P.nb * 3 + 3) & ~3) + m * P.nb * 3);
   if (smem > prop.sharedMemPerBlockOptin) { p->why = "work space does not fit shared memory"; return; }
   mr_free_dp_tiled(p);
   if (cudaMalloc(&p->d_tiles, sizeof(MrTile) * tab.size()) != cudaSuccess) { p->why = "cudaMalloc"; return; }
   if (cudaMemcpy(p->d_tiles, tab.data(), sizeof(MrTile) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) { p->why = "cudaMemcpy"; return; }
+  for (auto& v : index) if (v < 0) v = 0;
+  if (cudaMalloc(&p->d_tile_of, sizeof(int) * index.size()) != cudaSuccess) { p->why = "cudaMalloc"; return; }
+  if (cudaMemcpy(p->d_tile_of, index.data(), sizeof(int) * index.size(), cudaMemcpyHostToDevice) != cudaSuccess) { p->why = "cudaMemcpy"; return; }
   p->K = K; p->R = R; p->W = W; p->CN = CN; p->nBe = nBe;
   p->threads = threads; p->nslots = nslots; p->steps = steps;
   p->smem = smem;
@@ -383,7 +368,8 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   p->ctas_per_sm = std::max(1, std::min(by_smem, want));
   p->grid_cap = prop.multiProcessorCount * p->ctas_per_sm;
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
-  p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN;
+  p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = threads;
+  p->layout.tile_of = p->d_tile_of;
   p->tb_words = p->layout.words(nB);
   p->lane_efficiency = (double)live_cells / ((double)warp_steps * 32 * K * R);
   p->ok = true;
@@ -395,14 +381,15 @@ static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& 
                                        const float* B, const float* orient, const int* surv,
                                        const int* surv_count, uint32_t* tb, float* cost, int count,
                                        cudaStream_t stream) {
-  auto kern = k_dp_tiles<4, 8, MAXT, MINB>;
+  auto kern = (P.nb == 1) ? k_dp_tiles<4, 8, MAXT, MINB, true> : k_dp_tiles<4, 8, MAXT, MINB, false>;
   static size_t attr_set = 0;
   if (attr_set < p.smem) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_dp_tiles<4, 8, MAXT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_dp_tiles<4, 8, MAXT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
     attr_set = p.smem;
   }
   const int grid = std::min(count, p.grid_cap);
-  kern<<<grid, p.threads, p.smem, stream>>>(P, p.layout, p.nBe, p.nslots, p.steps, p.d_tiles, A, B, orient,
+  kern<<<grid, p.threads, p.smem, stream>>>(P, p.layout, p.nslots, p.steps, p.d_tiles, A, B, orient,
                                            surv, surv_count, tb, cost);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
