@@ -27,7 +27,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    extra = os.environ.get("MR_NVCC_EXTRA", "").split()   # experiments only, e.g. -DMR_DP_MIN3
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     subprocess.check_call(cmd)
     return OUT
 

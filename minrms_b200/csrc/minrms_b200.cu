@@ -242,12 +242,13 @@ int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* ite
   if (!ev) MR_FAIL(c, "cudaEventCreate failed");
   CU(c, cudaEventRecord(ev->a, c->stream));
   const int grid = (int)((threads + 127) / 128);
+  const size_t coords = 4 * 3 * (size_t)(c->m + c->nB) * c->hp.nb;
   if (use_tiled(c))
-    k_traceback_kabsch<TbTiled, EMIT><<<grid, 128, 0, c->stream>>>(
+    k_traceback_kabsch<TbTiled, EMIT><<<grid, 128, 4 * c->tiled.layout.table_ints() + coords, c->stream>>>(
         c->P, c->tiled.layout, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb,
         c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, c->d_Tout, c->d_pairs_out);
   else
-    k_traceback_kabsch<TbColumns, EMIT><<<grid, 128, 0, c->stream>>>(
+    k_traceback_kabsch<TbColumns, EMIT><<<grid, 128, coords, c->stream>>>(
         c->P, c->Lc, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb, c->d_cost,
         items, n_items, n_lo, c->d_scratch, c->d_ssd, c->d_Tout, c->d_pairs_out);
   CU(c, cudaGetLastError());

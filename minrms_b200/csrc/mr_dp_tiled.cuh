@@ -45,16 +45,19 @@ struct TbTiled {
   int K, R, W, JP, pad, NP, CN, T;  // layers/tile, rows/tile, strips, column pairs, top pad rows, cost pitch, chunks, threads
   const int* tile_of;
   __host__ __device__ size_t words(int /*nB*/) const { return (size_t)JP * T * K; }
-  __device__ __forceinline__ uint32_t code(const uint32_t* __restrict__ tbo, int n, int i, int j) const {
+  __host__ __device__ int table_ints() const { return (W * CN + 3) & ~3; }
+  __device__ __forceinline__ void load_table(int* tab, int tid, int nthreads) const {
+    for (int k = tid; k < W * CN; k += nthreads) tab[k] = tile_of[k];
+  }
+  // K = 4 layers x R = 8 rows per tile (the only shape built): shifts instead of divisions
+  __device__ __forceinline__ uint32_t code(const uint32_t* __restrict__ tbo, const int* __restrict__ tab,
+                                           int n, int i, int j) const {
     const int rho = i - 1 + pad;
-    const int w = rho / R, r = rho - w * R;
-    const int c = n / K, k = n - c * K;
-    const int jp = (j - 1) >> 1, h = (j - 1) & 1;
-    const int t = tile_of[w * CN + c];
-    const uint32_t word = tbo[((size_t)jp * T + t) * K + k];
-    const int a = h * 2 * R + 2 * r;
-    const uint32_t s1 = (word >> (31 - a)) & 1u, s2 = (word >> (30 - a)) & 1u;
-    return s2 ? (s1 ? 0u : 1u) : 2u;
+    const int t = tab[(rho >> 3) * CN + (n >> 2)];
+    const uint32_t word = tbo[((size_t)((j - 1) >> 1) * T + t) * 4 + (n & 3)];
+    const int a = ((j - 1) & 1) * 16 + 2 * (rho & 7);
+    const uint32_t bits = (word >> (30 - a)) & 3u;  // (s1 << 1) | s2
+    return (0x0212u >> (4 * bits)) & 3u;            // s2 = 0 -> 2; s2 = 1: s1 ? 0 : 1
   }
 };
 
@@ -114,7 +117,7 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
   }
 }
 
-template <int K, int R, int MAXT, int MINB, bool NB1>
+template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
            const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
@@ -217,9 +220,17 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
             const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
             const float d = dg + cv[r];
             const float left = st[k][r];
+#ifdef MR_DP_MIN3
             const float best = fminf(fminf(d, up), left);
             const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
             const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
+#else
+            // two 2-input mins so the new value can overwrite `left` in place (no register copy)
+            const float t = fminf(d, up);
+            const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
+            const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
+            const float best = fminf(t, left);
+#endif
             acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
             acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
             st[k][r] = best;
@@ -246,12 +257,12 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
         }
         // n < n_min: the reference reports the corner of the layer's window,
         // A(n, n+wA-1, n+wB-1) (dyn3d.cc:385, dyn3d.h:407-408): one layer per column
-        if (P.n_min > 1 && has_tile) {
+        if (WINDOWED && has_tile) {
           const int nq = s - w - P.wB + 1;
-          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && nq / K == c) {
+          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
             const int rho = nq + P.wA - 2 + pad;
-            if (rho / R == w) {
-              const int kq = nq - c * K, rq = rho - w * R;
+            if ((rho >> 3) == w) {
+              const int kq = nq & 3, rq = rho & 7;
               float v = 0.0f;
 #pragma unroll
               for (int k = 0; k < K; k++)
@@ -268,7 +279,9 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
         mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, pad, nB, nb, P.dp_cutoff, tid, nthreads);
       col = (col + 1) & (MR_CRING - 1);
       rd ^= wr; wr ^= rd; rd ^= wr;  // swap the parity sets
+#ifndef MR_EXP_NOSYNC
       __syncthreads();
+#endif
     }
   }
 }
@@ -365,6 +378,9 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   p->smem = smem;
   const int by_smem = (int)(prop.sharedMemPerMultiprocessor / (smem + 1024));
   int want = threads <= 256 ? 3 : (threads <= 384 ? 2 : 1);
+#ifdef MR_EXP_CTAS
+  want = MR_EXP_CTAS;
+#endif
   p->ctas_per_sm = std::max(1, std::min(by_smem, want));
   p->grid_cap = prop.multiProcessorCount * p->ctas_per_sm;
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
@@ -381,11 +397,15 @@ static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& 
                                        const float* B, const float* orient, const int* surv,
                                        const int* surv_count, uint32_t* tb, float* cost, int count,
                                        cudaStream_t stream) {
-  auto kern = (P.nb == 1) ? k_dp_tiles<4, 8, MAXT, MINB, true> : k_dp_tiles<4, 8, MAXT, MINB, false>;
+  typedef void (*kern_t)(MrDevParams, TbTiled, int, int, const MrTile*, const float*, const float*, const float*,
+                         const int*, const int*, uint32_t*, float*);
+  static const kern_t kerns[4] = {k_dp_tiles<4, 8, MAXT, MINB, false, false>, k_dp_tiles<4, 8, MAXT, MINB, false, true>,
+                                  k_dp_tiles<4, 8, MAXT, MINB, true, false>, k_dp_tiles<4, 8, MAXT, MINB, true, true>};
+  const kern_t kern = kerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
   static size_t attr_set = 0;
   if (attr_set < p.smem) {
-    if (cudaFuncSetAttribute(k_dp_tiles<4, 8, MAXT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(k_dp_tiles<4, 8, MAXT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
+    for (int q = 0; q < 4; q++)
+      if (cudaFuncSetAttribute(kerns[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
     attr_set = p.smem;
   }
   const int grid = std::min(count, p.grid_cap);

@@ -24,7 +24,9 @@ struct TbColumns {
     return ((size_t)(j - 1) * IW + ((i - 1) >> 4)) * NP + (n - 1);
   }
   __device__ __forceinline__ int shift(int i) const { return 2 * ((i - 1) & 15); }
-  __device__ __forceinline__ uint32_t code(const uint32_t* __restrict__ tbo, int n, int i, int j) const {
+  __host__ __device__ int table_ints() const { return 0; }
+  __device__ __forceinline__ void load_table(int*, int, int) const {}
+  __device__ __forceinline__ uint32_t code(const uint32_t* __restrict__ tbo, const int*, int n, int i, int j) const {
     return (tbo[word(n, i, j)] >> shift(i)) & 3u;
   }
 };
@@ -245,6 +247,8 @@ k_dp_columns(MrDevParams P, TbColumns L, const float* __restrict__ A, const floa
 // taken from the ORIGINAL coordinates (pair_alignment.cc:754-804) and form
 // ssd = SQR(rmsd)*n*nb (search_or_dyn3d.cc:587-588).  The pair list is staged in a
 // per-thread scratch slice so the sums run in ascending pair order like the reference.
+// The walk is branch-free (one dependent table word per step); the layout's lookup table
+// and both coordinate sets sit in shared memory.
 //   items == NULL: dense grid over (s, n in [n_lo, n_max]);  else explicit (s,n) list.
 //   EMIT: also write the transform and the pair list.
 // ---------------------------------------------------------------------------
@@ -256,6 +260,15 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
                    const float* __restrict__ cost, const int2* __restrict__ items, int n_items,
                    int n_lo, short2* __restrict__ scratch, float* __restrict__ ssd_out,
                    float* __restrict__ T_out, short* __restrict__ pairs_out) {
+  extern __shared__ int tb_smem[];
+  const int nb = P.nb;
+  int* tab = tb_smem;                                              // layout table
+  float* sA = reinterpret_cast<float*>(tab + L.table_ints());      // m*nb*3
+  float* sB = sA + P.m * nb * 3;                                   // nB*nb*3
+  L.load_table(tab, threadIdx.x, blockDim.x);
+  for (int k = threadIdx.x; k < P.m * nb * 3; k += blockDim.x) sA[k] = A[k];
+  for (int k = threadIdx.x; k < P.nB * nb * 3; k += blockDim.x) sB[k] = B[k];
+  __syncthreads();
   const int NP = L.NP;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   int s, n;
@@ -277,28 +290,34 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
   const uint32_t* tbo = tb + (size_t)s * L.words(P.nB);
   int cn = n, ci = P.m, cj = P.nB;
   while (cn > 0) {
-    const uint32_t code = L.code(tbo, cn, ci, cj);
-    if (code == 0) {
-      MY(cn - 1) = make_short2((short)(ci - 1), (short)(cj - 1));
-      cn--; ci--; cj--;
-    } else if (code == 1) {
-      ci--;
-    } else {
-      cj--;
-    }
+    const uint32_t code = L.code(tbo, tab, cn, ci, cj);  // 0 match, 1 skip-i, 2 skip-j
+    if (code == 0) MY(cn - 1) = make_short2((short)(ci - 1), (short)(cj - 1));
+    cn -= (code == 0);
+    ci -= (code != 2);
+    cj -= (code != 1);
   }
   float T[12];
   float ssd;
   if (P.refine_while_searching) {
-    const int nb = P.nb;
-    float rmsd = mr_superimpose(n * nb, [&](int a, float* pf, float* pm) {
-      const int k = a / nb, q = a - k * nb;
-      const short2 pr = MY(k);
-      const float* f = A + 3 * ((size_t)pr.x * nb + q);
-      const float* mv = B + 3 * ((size_t)pr.y * nb + q);
-      pf[0] = f[0]; pf[1] = f[1]; pf[2] = f[2];
-      pm[0] = mv[0]; pm[1] = mv[1]; pm[2] = mv[2];
-    }, T);
+    float rmsd;
+    if (nb == 1) {
+      rmsd = mr_superimpose(n, [&](int a, float* pf, float* pm) {
+        const short2 pr = MY(a);
+        const float* f = sA + 3 * pr.x;
+        const float* mv = sB + 3 * pr.y;
+        pf[0] = f[0]; pf[1] = f[1]; pf[2] = f[2];
+        pm[0] = mv[0]; pm[1] = mv[1]; pm[2] = mv[2];
+      }, T);
+    } else {
+      rmsd = mr_superimpose(n * nb, [&](int a, float* pf, float* pm) {
+        const int k = a / nb, q = a - k * nb;
+        const short2 pr = MY(k);
+        const float* f = sA + 3 * (pr.x * nb + q);
+        const float* mv = sB + 3 * (pr.y * nb + q);
+        pf[0] = f[0]; pf[1] = f[1]; pf[2] = f[2];
+        pm[0] = mv[0]; pm[1] = mv[1]; pm[2] = mv[2];
+      }, T);
+    }
     ssd = ((rmsd * rmsd) * (float)n) * (float)nb;
   } else {
     ssd = cost[slot];
@@ -320,7 +339,6 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
     }
   }
 }
-
 #undef MY
 
 // transforms of the winning orientations: out[k] = orient[idx[k]]
@@ -375,7 +393,9 @@ __global__ void k_select(MrDevParams P, int NP, const int* __restrict__ surv,
       if (valid) valid[slot] = 1;
       if (keys && v < MR_UB) {
         const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | oid;
-        atomicMin(&keys[n - P.n_min], key);
+        // most candidates lose: a plain (possibly stale, only ever too large) read first
+        // keeps the 64-bit atomics on the ~140 hot addresses rare
+        if (key < *(volatile unsigned long long*)&keys[n - P.n_min]) atomicMin(&keys[n - P.n_min], key);
       }
     }
   }
