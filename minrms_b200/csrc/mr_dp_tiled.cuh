@@ -419,6 +419,9 @@ static inline int mr_launch_dp_tiled(const MrTiledPlan& p, const MrDevParams& P,
                                      const int* surv_count, uint32_t* tb, float* cost, int count,
                                      cudaStream_t stream) {
   if (p.threads <= 256) return mr_launch_dp_tiles_t<256, 3>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+#ifdef MR_EXP_MINB
+  if (p.threads <= 384) return mr_launch_dp_tiles_t<384, MR_EXP_MINB>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+#endif
   if (p.threads <= 384) return mr_launch_dp_tiles_t<384, 2>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
   if (p.threads <= 640) return mr_launch_dp_tiles_t<640, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
   return mr_launch_dp_tiles_t<1024, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);

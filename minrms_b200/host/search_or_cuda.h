@@ -1,0 +1,45 @@
+// search_or_cuda.h -- the reference-side binding of the B200 search: a SearchOr
+// (bin/minrms/search_or.h:57-130) whose Search() and Refine() run on the GPU through the
+// C ABI of include/minrms_b200.h.  It derives from SearchOrDyn3d only to reuse the
+// reference's own result tables and writers (WriteMSF / WriteChimeraInfo,
+// bin/minrms/search_or_dyn3d.cc:2848-2996) unchanged.
+//
+// SearchOrDyn3d keeps aaSumSqdDists / aaTransforms / aaAlignments private
+// (bin/minrms/search_or_dyn3d.h:228-310).  A maintainer adopting this class changes that
+// one access specifier to `protected`; to build against the UNMODIFIED tree (as
+// oracle/build_ref.sh does) the specifier is redefined around the include below.
+#ifndef MINRMS_SEARCH_OR_CUDA_H
+#define MINRMS_SEARCH_OR_CUDA_H
+
+#define private protected
+#include "search_or_dyn3d.h"
+#undef private
+
+#include <vector>
+#include "minrms_b200.h"
+
+namespace minrms {
+
+class SearchOrCuda : public SearchOrDyn3d {
+ public:
+  explicit SearchOrCuda(SearchOrDyn3d::Settings const& s);
+  ~SearchOrCuda();
+
+  // SearchOr interface (bin/minrms/search_or.h:87-114)
+  void Search(OrientationGenerator const& og, long start, long stop);
+  void Refine();
+
+ private:
+  SearchOrCuda(SearchOrCuda const&);
+  SearchOrCuda& operator=(SearchOrCuda const&);
+  void TableToHost(mr_best& t);   // reference tables -> flat C-ABI table
+  void TableFromHost(mr_best const& t);
+  std::vector<mr_ctx*> ctx;       // one per GPU ($MINRMS_CUDA_GPUS, default 1)
+  std::vector<float> ssd, T;
+  std::vector<int16_t> pairs;
+  std::vector<int64_t> oid;
+  int N, R;
+};
+
+}  // namespace minrms
+#endif

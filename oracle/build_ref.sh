@@ -65,6 +65,14 @@ build_flavour() {
       g++ -std=c++11 $FLAGS -w $INC $HERE/$drv.cc $O/libminrms_bin.a $O/libminrms_ref.a -o $O/$drv
     fi
   done
+  # the drop-in binary: reference CLI + SearchOrCuda (minrms_b200/host) over libminrms_b200.so
+  HOST=$HERE/../minrms_b200/host
+  LIBDIR=$HERE/../minrms_b200
+  if [ -f $LIBDIR/libminrms_b200.so ]; then
+    g++ -std=c++11 $FLAGS -w $INC -I$HERE/../include $HOST/main_cuda.cc $HOST/search_or_cuda.cc \
+        $O/libminrms_bin.a $O/libminrms_ref.a -L$LIBDIR -lminrms_b200 -lpthread \
+        -Wl,-rpath,'$ORIGIN/../../../minrms_b200' -o $O/minrms_cuda
+  fi
   echo "built $O"
 }
 
