@@ -50,14 +50,14 @@ struct TbTiled {
     for (int k = tid; k < W * CN; k += nthreads) tab[k] = tile_of[k];
   }
   // K = 4 layers x R = 8 rows per tile (the only shape built): shifts instead of divisions
-  __device__ __forceinline__ uint32_t code(const uint32_t* __restrict__ tbo, const int* __restrict__ tab,
-                                           int n, int i, int j) const {
-    const int rho = i - 1 + pad;
-    const int t = tab[(rho >> 3) * CN + (n >> 2)];
-    const uint32_t word = tbo[((size_t)((j - 1) >> 1) * T + t) * 4 + (n & 3)];
-    const int a = ((j - 1) & 1) * 16 + 2 * (rho & 7);
+  __device__ __forceinline__ size_t addr(const int* __restrict__ tab, int n, int i, int j) const {
+    const int t = tab[((i - 1 + pad) >> 3) * CN + (n >> 2)];
+    return ((size_t)((j - 1) >> 1) * T + t) * 4 + (n & 3);
+  }
+  __device__ __forceinline__ uint32_t decode(uint32_t word, int i, int j) const {
+    const int a = ((j - 1) & 1) * 16 + 2 * ((i - 1 + pad) & 7);
     const uint32_t bits = (word >> (30 - a)) & 3u;  // (s1 << 1) | s2
-    return (0x0212u >> (4 * bits)) & 3u;            // s2 = 0 -> 2; s2 = 1: s1 ? 0 : 1
+    return (0x0212u >> (4 * bits)) & 3u;            // s2 = 0 -> 2 (skip-j); s2 = 1: s1 ? 0 (match) : 1 (skip-i)
   }
 };
 

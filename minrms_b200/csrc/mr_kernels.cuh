@@ -26,9 +26,8 @@ struct TbColumns {
   __device__ __forceinline__ int shift(int i) const { return 2 * ((i - 1) & 15); }
   __host__ __device__ int table_ints() const { return 0; }
   __device__ __forceinline__ void load_table(int*, int, int) const {}
-  __device__ __forceinline__ uint32_t code(const uint32_t* __restrict__ tbo, const int*, int n, int i, int j) const {
-    return (tbo[word(n, i, j)] >> shift(i)) & 3u;
-  }
+  __device__ __forceinline__ size_t addr(const int*, int n, int i, int j) const { return word(n, i, j); }
+  __device__ __forceinline__ uint32_t decode(uint32_t w, int i, int /*j*/) const { return (w >> shift(i)) & 3u; }
 };
 
 // ---------------------------------------------------------------------------
@@ -290,7 +289,7 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
   const uint32_t* tbo = tb + (size_t)s * L.words(P.nB);
   int cn = n, ci = P.m, cj = P.nB;
   while (cn > 0) {
-    const uint32_t code = L.code(tbo, tab, cn, ci, cj);  // 0 match, 1 skip-i, 2 skip-j
+    const uint32_t code = L.decode(tbo[L.addr(tab, cn, ci, cj)], ci, cj);  // 0 match, 1 skip-i, 2 skip-j
     if (code == 0) MY(cn - 1) = make_short2((short)(ci - 1), (short)(cj - 1));
     cn -= (code == 0);
     ci -= (code != 2);
