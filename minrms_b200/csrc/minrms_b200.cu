@@ -69,6 +69,7 @@ struct mr_ctx {
   int64_t opt_dp_kernel = 0;    // 0 auto, 1 general, 2 tiled
   int64_t opt_budget_mb = 16384;
   int64_t opt_chunk = 0;
+  int64_t opt_dp_only = 0;      // experiments: skip traceback/select (results invalid)
   mr_stats st;
   std::vector<EventPair> events;
   size_t events_used = 0;
@@ -295,6 +296,7 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
     CU(c, cudaMemcpyAsync(&c->h_pinned[slot], c->d_surv_count, 4, cudaMemcpyDeviceToHost, c->stream));
     c->pending_counts.push_back({slot, cnt});
     if (launch_dp(c, oc, cnt)) return 1;
+    if (c->opt_dp_only) { c->st.orientations += cnt; continue; }
     if (launch_tb<false>(c, oc, cnt, nullptr, 0)) return 1;
     k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->d_surv, c->d_surv_count,
                                                       c->d_cost, c->d_ssd, (long long)(first_id + start),
@@ -505,6 +507,7 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "dp_kernel")) c->opt_dp_kernel = value;
   else if (!strcmp(name, "budget_mb")) c->opt_budget_mb = std::max<int64_t>(64, value);
   else if (!strcmp(name, "chunk")) c->opt_chunk = value;
+  else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
   else MR_FAIL(c, "mr_set_option: unknown option %s", name);
   if (c->opt_dp_kernel == 2 && !c->tiled.ok) MR_FAIL(c, "tiled DP kernel not available for this problem: %s", c->tiled.why);
   return 0;

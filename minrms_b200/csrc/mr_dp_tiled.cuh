@@ -87,33 +87,57 @@ struct MrTiledPlan {
 
 #define MR_CRING 32  // columns in the C ring (>= strips + MR_CBATCH)
 #define MR_CBATCH 8  // columns of C produced at a time
+__host__ __device__ inline int mr_ring_stride(int WR) { return WR + ((36 - (WR & 31)) & 31); }
 
-// distance columns [j0, j0+MR_CBATCH) into the ring, all threads of the CTA
+// Distance columns [j0, j0 + MR_CBATCH) into the ring (j0 = 1 mod 8).
+// One atom per residue (NB1): molecule 2 is kept as x[], y[], z[] arrays so that a work item
+// = one row x 4 consecutive columns reads A_i once and B' as three float4; otherwise the
+// generic per-element loop.  Ring rows are WRp floats apart (WRp = 4 mod 32: the float4
+// reads of tiles in different strips / columns fall into different banks).
 template <bool NB1>
 __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float* __restrict__ sA,
-                                             const float* __restrict__ sB, int j0, int WR, int pad,
-                                             int nB, int nb, float cutoff, int tid, int nthreads) {
+                                             const float* __restrict__ sB, int j0, int WR, int WRp, int pad,
+                                             int nB, int nBp, int nb, float cutoff, int tid, int nthreads) {
   const float INF = __int_as_float(0x7f800000);
-  for (int e = tid; e < MR_CBATCH * WR; e += nthreads) {
-    const int dj = e / WR, rho = e - dj * WR;
-    const int jn = j0 + dj, i = rho - pad + 1;
-    float cc = INF;
-    if (i >= 1 && jn <= nB) {
-      if (NB1) {
-        const float* a = sA + 3 * (i - 1);
-        const float* b = sB + 3 * (jn - 1);
-        cc = mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
-      } else {
+  if (NB1) {
+    for (int item = tid; item < (MR_CBATCH / 4) * WR; item += nthreads) {
+      const int q4 = item / WR, rho = item - q4 * WR;
+      const int jn = j0 + 4 * q4, i = rho - pad + 1;
+      float cc[4] = {INF, INF, INF, INF};
+      if (i >= 1 && jn <= nB) {
+        const float ax = sA[3 * (i - 1)], ay = sA[3 * (i - 1) + 1], az = sA[3 * (i - 1) + 2];
+        const float4 bx = *reinterpret_cast<const float4*>(sB + (jn - 1));
+        const float4 by = *reinterpret_cast<const float4*>(sB + nBp + (jn - 1));
+        const float4 bz = *reinterpret_cast<const float4*>(sB + 2 * nBp + (jn - 1));
+        cc[0] = mr_d2(ax, ay, az, bx.x, by.x, bz.x);
+        cc[1] = mr_d2(ax, ay, az, bx.y, by.y, bz.y);
+        cc[2] = mr_d2(ax, ay, az, bx.z, by.z, bz.z);
+        cc[3] = mr_d2(ax, ay, az, bx.w, by.w, bz.w);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (cc[q] > cutoff) cc[q] = MR_UB;
+          if (jn + q > nB) cc[q] = INF;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) Cr[((jn + q) & (MR_CRING - 1)) * WRp + rho] = cc[q];
+    }
+  } else {
+    for (int e = tid; e < MR_CBATCH * WR; e += nthreads) {
+      const int dj = e / WR, rho = e - dj * WR;
+      const int jn = j0 + dj, i = rho - pad + 1;
+      float cc = INF;
+      if (i >= 1 && jn <= nB) {
         cc = 0.0f;
         for (int q = 0; q < nb; q++) {
           const float* a = sA + 3 * ((i - 1) * nb + q);
           const float* b = sB + 3 * ((jn - 1) * nb + q);
           cc += mr_d2(a[0], a[1], a[2], b[0], b[1], b[2]);
         }
+        if (cc > cutoff) cc = MR_UB;
       }
-      if (cc > cutoff) cc = MR_UB;
+      Cr[(jn & (MR_CRING - 1)) * WRp + rho] = cc;
     }
-    Cr[(jn & (MR_CRING - 1)) * WR + rho] = cc;
   }
 }
 
@@ -127,14 +151,16 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
   extern __shared__ float4 smem4[];
   const int m = P.m, nB = P.nB, nb = P.nb;
   const int W = L.W, WR = W * R, pad = L.pad;
+  const int WRp = mr_ring_stride(WR);         // ring row stride (floats), = 4 mod 32
+  const int nBp = (nB * nb + 11) & ~3;        // padded length of one coordinate array of molecule 2
   const int tid = threadIdx.x, nthreads = blockDim.x;
   // shared memory carve-up (all 16-byte aligned)
   float4* dgA = smem4;                 // [2][nslots] published top layer: {upper boundary, rows 0..2}
   float4* dgB = dgA + 2 * nslots;      // [2][nslots] rows 3..6
   float4* bnd = dgB + 2 * nslots;      // [2][nslots] published bottom rows (K = 4 layers)
   float* Cr = reinterpret_cast<float*>(bnd + 2 * nslots);  // [MR_CRING][WR] distance columns
-  float* sB = Cr + MR_CRING * WR;                           // rotated molecule 2: nB*nb*3
-  float* sA = sB + ((nB * nb * 3 + 3) & ~3);                // molecule 1: m*nb*3
+  float* sB = Cr + MR_CRING * WRp;                          // rotated molecule 2: x[], y[], z[] (NB1) or xyz triples
+  float* sA = sB + 3 * nBp;                                 // molecule 1: m*nb*3
   const float INF = __int_as_float(0x7f800000);
   const int nsurv = *surv_count;
 
@@ -146,16 +172,20 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
   const int tb_lo = has_tile ? me.s_lo : 0x3fffffff, tb_hi = has_tile ? me.s_hi : -1;
   const int cost_step = (has_tile && w == W - 1) ? nB + w : -1;
   const float4* const cbase = reinterpret_cast<const float4*>(Cr + w * R);
-  const int cstride4 = WR / 4;
+  const int cstride4 = WRp / 4;
   for (int k = tid; k < m * nb * 3; k += nthreads) sA[k] = A[k];
 
   for (int sv = blockIdx.x; sv < nsurv; sv += gridDim.x) {
     const float* T = orient + 12 * (size_t)surv[sv];
     __syncthreads();
-    for (int k = tid; k < nB * nb; k += nthreads) {
-      float x, y, z;
-      mr_xform(T, B[3 * k], B[3 * k + 1], B[3 * k + 2], x, y, z);
-      sB[3 * k] = x; sB[3 * k + 1] = y; sB[3 * k + 2] = z;
+    for (int k = tid; k < nBp; k += nthreads) {
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (k < nB * nb) mr_xform(T, B[3 * k], B[3 * k + 1], B[3 * k + 2], x, y, z);
+      if (NB1) {
+        sB[k] = x; sB[nBp + k] = y; sB[2 * nBp + k] = z;
+      } else if (k < nB * nb) {
+        sB[3 * k] = x; sB[3 * k + 1] = y; sB[3 * k + 2] = z;
+      }
     }
     // exchange slots start at the boundary values
     // (slot nslots-2: {0, inf, ..} above strip 0 for chunk 0; slot nslots-1: all +inf)
@@ -166,9 +196,9 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
       dgB[k] = make_float4(INF, INF, INF, INF);
       bnd[k] = make_float4(zero ? 0.0f : INF, INF, INF, INF);
     }
-    for (int k = tid; k < MR_CRING * WR; k += nthreads) Cr[k] = INF;
+    for (int k = tid; k < MR_CRING * WRp; k += nthreads) Cr[k] = INF;
     __syncthreads();
-    mr_produce_c<NB1>(Cr, sA, sB, 1, WR, pad, nB, nb, P.dp_cutoff, tid, nthreads);
+    mr_produce_c<NB1>(Cr, sA, sB, 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
 
     float st[K][R], bprev[K];
     uint32_t acc[K];
@@ -245,7 +275,11 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
 #pragma unroll
         for (int k = 0; k < K; k++) bprev[k] = bin[k];
         // traceback: the K words of this tile every second column (j = s - w even)
+#ifndef MR_EXP_NOTB
         if (((s - w) & 1) == 0 && s >= tb_lo && s <= tb_hi)
+#else
+        if (s == -5)
+#endif
           tbo[(size_t)((s - w - 1) >> 1) * nthreads] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
         // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
         if (s == cost_step) {
@@ -275,8 +309,12 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
         }
       }
       // every MR_CBATCH steps all threads produce the next MR_CBATCH columns of C
+#ifdef MR_EXP_NOC
+      if (s == -7)
+#else
       if ((s & (MR_CBATCH - 1)) == 0)
-        mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, pad, nB, nb, P.dp_cutoff, tid, nthreads);
+#endif
+        mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
       col = (col + 1) & (MR_CRING - 1);
       rd ^= wr; wr ^= rd; rd ^= wr;  // swap the parity sets
 #ifndef MR_EXP_NOSYNC
@@ -365,7 +403,7 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
       e.dg_slot = dg >= 0 ? dg : nslots - 1;
     }
   }
-  const size_t smem = 16 * (size_t)(6 * nslots) + 4 * (size_t)(MR_CRING * W * R + ((nB * P.nb * 3 + 3) & ~3) + m * P.nb * 3);
+  const size_t smem = 16 * (size_t)(6 * nslots) + 4 * (size_t)(MR_CRING * mr_ring_stride(W * R) + 3 * ((nB * P.nb + 11) & ~3) + ((m * P.nb * 3 + 3) & ~3));
   if (smem > prop.sharedMemPerBlockOptin) { p->why = "work space does not fit shared memory"; return; }
   mr_free_dp_tiled(p);
   if (cudaMalloc(&p->d_tiles, sizeof(MrTile) * tab.size()) != cudaSuccess) { p->why = "cudaMalloc"; return; }
