@@ -141,6 +141,16 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
   }
 }
 
+// 16-byte shared-memory accesses through 32-bit shared addresses (one register each)
+__device__ __forceinline__ float4 mr_lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mr_sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
@@ -151,28 +161,36 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
   extern __shared__ float4 smem4[];
   const int m = P.m, nB = P.nB, nb = P.nb;
   const int W = L.W, WR = W * R, pad = L.pad;
-  const int WRp = mr_ring_stride(WR);         // ring row stride (floats), = 4 mod 32
-  const int nBp = (nB * nb + 11) & ~3;        // padded length of one coordinate array of molecule 2
+  const int WRp = mr_ring_stride(WR);   // ring row stride (floats), = 4 mod 32
+  const int nBp = (nB * nb + 11) & ~3;  // padded length of one coordinate array of molecule 2
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  // shared memory carve-up (all 16-byte aligned)
-  float4* dgA = smem4;                 // [2][nslots] published top layer: {upper boundary, rows 0..2}
-  float4* dgB = dgA + 2 * nslots;      // [2][nslots] rows 3..6
-  float4* bnd = dgB + 2 * nslots;      // [2][nslots] published bottom rows (K = 4 layers)
-  float* Cr = reinterpret_cast<float*>(bnd + 2 * nslots);  // [MR_CRING][WR] distance columns
-  float* sB = Cr + MR_CRING * WRp;                          // rotated molecule 2: x[], y[], z[] (NB1) or xyz triples
-  float* sA = sB + 3 * nBp;                                 // molecule 1: m*nb*3
+  // shared memory carve-up (all 16-byte aligned).  Exchange slot (parity p, slot q) is the
+  // 48 bytes at exch[(p*nslots + q)*3]: {top layer: upper boundary, rows 0..2}, {rows 3..6},
+  // {bottom row of the K = 4 layers}.  Consecutive slots are 48 B apart: 16-byte reads of
+  // neighbouring slots by a quarter warp fall into distinct banks.
+  float4* exch = smem4;
+  float* Cr = reinterpret_cast<float*>(exch + 6 * nslots);  // [MR_CRING][WRp] distance columns
+  float* sB = Cr + MR_CRING * WRp;                           // rotated molecule 2: x[], y[], z[] (NB1) or xyz triples
+  float* sA = sB + 3 * nBp;                                  // molecule 1: m*nb*3
   const float INF = __int_as_float(0x7f800000);
   const int nsurv = *surv_count;
 
   const MrTile me = tiles[tid];
   const bool has_tile = me.w >= 0;
   const int w = has_tile ? me.w : 0, c = has_tile ? me.c : 0;
-  const int warp_lo = me.warp_lo, warp_hi = me.warp_hi;
+  const int warp_lo = me.warp_lo, warp_hi = min(me.warp_hi, nsteps);
   // steps at which this tile stores traceback words / reports costs
-  const int tb_lo = has_tile ? me.s_lo : 0x3fffffff, tb_hi = has_tile ? me.s_hi : -1;
+  const int tb_hi = has_tile ? me.s_hi : -1;
+  const int tb_first = has_tile ? me.s_lo + ((me.s_lo - w) & 1) : 0x3fffffff;  // first step with an even column
   const int cost_step = (has_tile && w == W - 1) ? nB + w : -1;
-  const float4* const cbase = reinterpret_cast<const float4*>(Cr + w * R);
-  const int cstride4 = WRp / 4;
+  // 32-bit shared addresses: parity set 0; set 1 is `par_bytes` further
+  const uint32_t exch0 = (uint32_t)__cvta_generic_to_shared(exch);
+  const uint32_t par_bytes = (uint32_t)nslots * 48u;
+  const uint32_t a_up = exch0 + (uint32_t)me.up_slot * 48u + 32u;  // bottom row of the tile above
+  const uint32_t a_dg = exch0 + (uint32_t)me.dg_slot * 48u;        // top layer of the tile one chunk down
+  const uint32_t a_me = exch0 + (uint32_t)tid * 48u;
+  const uint32_t a_c = (uint32_t)__cvta_generic_to_shared(Cr) + (uint32_t)(w * R) * 4u;
+  const uint32_t c_row = (uint32_t)WRp * 4u;
   for (int k = tid; k < m * nb * 3; k += nthreads) sA[k] = A[k];
 
   for (int sv = blockIdx.x; sv < nsurv; sv += gridDim.x) {
@@ -192,9 +210,9 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
     for (int k = tid; k < 2 * nslots; k += nthreads) {
       const int sl = k % nslots;
       const bool zero = sl == nslots - 2 || (sl < nslots - 2 && tiles[sl].c == 0);
-      dgA[k] = make_float4(INF, INF, INF, INF);
-      dgB[k] = make_float4(INF, INF, INF, INF);
-      bnd[k] = make_float4(zero ? 0.0f : INF, INF, INF, INF);
+      exch[3 * k] = make_float4(INF, INF, INF, INF);
+      exch[3 * k + 1] = make_float4(INF, INF, INF, INF);
+      exch[3 * k + 2] = make_float4(zero ? 0.0f : INF, INF, INF, INF);
     }
     for (int k = tid; k < MR_CRING * WRp; k += nthreads) Cr[k] = INF;
     __syncthreads();
@@ -210,116 +228,112 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
 #pragma unroll
       for (int r = 0; r < R; r++) st[k][r] = v;
     }
-    uint4* tbo = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid;
+    uint4* tbp = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid +
+                 (size_t)max(0, (tb_first - w - 1) >> 1) * nthreads;
+    int tb_next = tb_first;
     __syncthreads();
 
-    // read / write offsets of the parity-double-buffered exchange slots
-    int rd = nslots, wr = 0;  // step 1: read parity 0 ... wait: write parity (s&1), read the other
-    rd = 0; wr = nslots;      // s = 1: write slot set 1, read slot set 0
-    int col = (1 - w) & (MR_CRING - 1);
-    for (int s = 1; s <= nsteps; s++) {
-      if (s >= warp_lo && s <= warp_hi) {
-        // C(i, j) for my R rows: ring column j & 31 (columns <= 0 and > nB hold +inf)
-        float cv[R];
-        {
-          const float4* cp = cbase + col * cstride4;
-          const float4 v0 = cp[0], v1 = cp[1];
-          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
-          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
+    // steps before this warp has live cells: keep pace with the CTA (barrier + C production)
+    int s = 1;
+    for (; s < warp_lo && s <= nsteps; s++) {
+      if ((s & (MR_CBATCH - 1)) == 0)
+        mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
+      __syncthreads();
+    }
+    // parity of the exchange set written at step s: s & 1
+    uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
+    for (; s <= warp_hi; s++) {
+      // C(i, j) for my R rows: ring column j & 31 (columns <= 0 and > nB hold +inf)
+      float cv[R];
+      {
+        const uint32_t ca = a_c + (uint32_t)((s - w) & (MR_CRING - 1)) * c_row;
+        const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
+        cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
+        cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
+      }
+      // A(n, i_lo-1, j): the bottom row the tile above published last step
+      float bin[K];
+      {
+        const float4 v = mr_lds128(a_up + rd_off);
+        bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
+      }
+      // A(n_lo-1, i-1, j-1) for my lowest layer: what the lower-layer tile published last
+      // step = {its upper boundary, rows 0..6} of its top layer after column j-1
+      float dsh[R];
+      {
+        const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
+        dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+        dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
+      }
+#pragma unroll
+      for (int k = K - 1; k >= 0; k--) {
+        float up = bin[k];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
+          const float d = dg + cv[r];
+          const float left = st[k][r];
+          // two 2-input mins so the new value overwrites `left` in place (no register copy)
+          const float t = fminf(d, up);
+          const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
+          const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
+          const float best = fminf(t, left);
+          acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+          acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+          st[k][r] = best;
+          up = best;
         }
-        // A(n, i_lo-1, j): the bottom row the tile above published last step
-        float bin[K];
-        {
-          const float4 v = bnd[rd + me.up_slot];
-          bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
+      }
+      // publish: top layer shifted down one row (for the tile one chunk up, next column, next
+      // step) and bottom row (for the tile below, same column, next step)
+      mr_sts128(a_me + wr_off, bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
+      mr_sts128(a_me + wr_off + 16u, st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
+      mr_sts128(a_me + wr_off + 32u, st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
+#pragma unroll
+      for (int k = 0; k < K; k++) bprev[k] = bin[k];
+      // traceback: the K words of this tile every second column (j = s - w even)
+      if (s == tb_next) {
+        *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        tbp += nthreads;
+        tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
+      }
+      // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
+      if (s == cost_step) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const int n = c * K + k;
+          if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
         }
-        // A(n_lo-1, i-1, j-1) for my lowest layer: what the lower-layer tile published last
-        // step = {its upper boundary, rows 0..6} of its top layer after column j-1
-        float dsh[R];
-        {
-          const float4 a4 = dgA[rd + me.dg_slot];
-          const float4 b4 = dgB[rd + me.dg_slot];
-          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-        }
+      }
+      // n < n_min: the reference reports the corner of the layer's window,
+      // A(n, n+wA-1, n+wB-1) (dyn3d.cc:385, dyn3d.h:407-408): one layer per column
+      if (WINDOWED && has_tile) {
+        const int nq = s - w - P.wB + 1;
+        if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
+          const int rho = nq + P.wA - 2 + pad;
+          if ((rho >> 3) == w) {
+            const int kq = nq & 3, rq = rho & 7;
+            float v = 0.0f;
 #pragma unroll
-        for (int k = K - 1; k >= 0; k--) {
-          float up = bin[k];
+            for (int k = 0; k < K; k++)
 #pragma unroll
-          for (int r = 0; r < R; r++) {
-            const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
-            const float d = dg + cv[r];
-            const float left = st[k][r];
-#ifdef MR_DP_MIN3
-            const float best = fminf(fminf(d, up), left);
-            const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
-            const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
-#else
-            // two 2-input mins so the new value can overwrite `left` in place (no register copy)
-            const float t = fminf(d, up);
-            const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
-            const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
-            const float best = fminf(t, left);
-#endif
-            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
-            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
-            st[k][r] = best;
-            up = best;
-          }
-        }
-        // publish: bottom row (for the tile below, same column, next step) and top layer
-        // shifted down one row (for the tile one chunk up, next column, next step)
-        bnd[wr + tid] = make_float4(st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
-        dgA[wr + tid] = make_float4(bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
-        dgB[wr + tid] = make_float4(st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
-#pragma unroll
-        for (int k = 0; k < K; k++) bprev[k] = bin[k];
-        // traceback: the K words of this tile every second column (j = s - w even)
-#ifndef MR_EXP_NOTB
-        if (((s - w) & 1) == 0 && s >= tb_lo && s <= tb_hi)
-#else
-        if (s == -5)
-#endif
-          tbo[(size_t)((s - w - 1) >> 1) * nthreads] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-        // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
-        if (s == cost_step) {
-#pragma unroll
-          for (int k = 0; k < K; k++) {
-            const int n = c * K + k;
-            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
-          }
-        }
-        // n < n_min: the reference reports the corner of the layer's window,
-        // A(n, n+wA-1, n+wB-1) (dyn3d.cc:385, dyn3d.h:407-408): one layer per column
-        if (WINDOWED && has_tile) {
-          const int nq = s - w - P.wB + 1;
-          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
-            const int rho = nq + P.wA - 2 + pad;
-            if ((rho >> 3) == w) {
-              const int kq = nq & 3, rq = rho & 7;
-              float v = 0.0f;
-#pragma unroll
-              for (int k = 0; k < K; k++)
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                  if (k == kq && r == rq) v = st[k][r];
-              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
-            }
+              for (int r = 0; r < R; r++)
+                if (k == kq && r == rq) v = st[k][r];
+            cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
           }
         }
       }
       // every MR_CBATCH steps all threads produce the next MR_CBATCH columns of C
-#ifdef MR_EXP_NOC
-      if (s == -7)
-#else
       if ((s & (MR_CBATCH - 1)) == 0)
-#endif
         mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-      col = (col + 1) & (MR_CRING - 1);
-      rd ^= wr; wr ^= rd; rd ^= wr;  // swap the parity sets
-#ifndef MR_EXP_NOSYNC
+      { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
       __syncthreads();
-#endif
+    }
+    // steps after this warp's window
+    for (; s <= nsteps; s++) {
+      if ((s & (MR_CBATCH - 1)) == 0)
+        mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
+      __syncthreads();
     }
   }
 }
