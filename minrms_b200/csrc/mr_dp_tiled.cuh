@@ -50,6 +50,24 @@ struct TbTiled {
     for (int k = tid; k < W * CN; k += nthreads) tab[k] = tile_of[k];
   }
   // K = 4 layers x R = 8 rows per tile (the only shape built): shifts instead of divisions
+  // branch-free walk with 32-bit index math on (n, rho = i-1+pad, jm = j-1)
+  template <class Emit>
+  __device__ __forceinline__ void walk(const int* __restrict__ tab, const uint32_t* __restrict__ tbo, int n,
+                                       int m, int nB, Emit emit) const {
+    int cn = n, rho = m - 1 + pad, jm = nB - 1;
+    const int T4 = 4 * T;
+    while (cn > 0) {
+      const int t = tab[(rho >> 3) * CN + (cn >> 2)];
+      const uint32_t word = tbo[(jm >> 1) * T4 + t * 4 + (cn & 3)];
+      const int a = (jm & 1) * 16 + 2 * (rho & 7);
+      const uint32_t bits = (word >> (30 - a)) & 3u;      // (s1 << 1) | s2
+      const uint32_t code = (0x0212u >> (4 * bits)) & 3u;  // 0 match, 1 skip-i, 2 skip-j
+      if (code == 0) emit(cn - 1, rho - pad, jm);
+      cn -= (code == 0);
+      rho -= (code != 2);
+      jm -= (code != 1);
+    }
+  }
   __device__ __forceinline__ size_t addr(const int* __restrict__ tab, int n, int i, int j) const {
     const int t = tab[((i - 1 + pad) >> 3) * CN + (n >> 2)];
     return ((size_t)((j - 1) >> 1) * T + t) * 4 + (n & 3);
@@ -141,6 +159,8 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
   }
 }
 
+__device__ int mr_sm_arrivals[256];
+
 // 16-byte shared-memory accesses through 32-bit shared addresses (one register each)
 __device__ __forceinline__ float4 mr_lds128(uint32_t a) {
   float4 v;
@@ -192,6 +212,24 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
   const uint32_t a_c = (uint32_t)__cvta_generic_to_shared(Cr) + (uint32_t)(w * R) * 4u;
   const uint32_t c_row = (uint32_t)WRp * 4u;
   for (int k = tid; k < m * nb * 3; k += nthreads) sA[k] = A[k];
+#ifdef MR_EXP_PHASE
+  // the CTAs sharing an SM run identical work in lock step; delay every second arrival on an
+  // SM by about half an orientation so that their few-live-warps phases do not coincide
+  {
+    __shared__ int s_par;
+    if (tid == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      s_par = atomicAdd(&mr_sm_arrivals[smid & 255], 1) & 1;
+    }
+    __syncthreads();
+    if (s_par && tid == 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)MR_EXP_PHASE) {}
+    }
+    __syncthreads();
+  }
+#endif
 
   for (int sv = blockIdx.x; sv < nsurv; sv += gridDim.x) {
     const float* T = orient + 12 * (size_t)surv[sv];
@@ -273,11 +311,17 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
           const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
           const float d = dg + cv[r];
           const float left = st[k][r];
+#ifdef MR_DP_MIN3
+          const float best = fminf(fminf(d, up), left);
+          const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
+          const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
+#else
           // two 2-input mins so the new value overwrites `left` in place (no register copy)
           const float t = fminf(d, up);
           const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
           const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
           const float best = fminf(t, left);
+#endif
           acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
           acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
           st[k][r] = best;

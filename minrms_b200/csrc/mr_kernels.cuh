@@ -26,6 +26,19 @@ struct TbColumns {
   __device__ __forceinline__ int shift(int i) const { return 2 * ((i - 1) & 15); }
   __host__ __device__ int table_ints() const { return 0; }
   __device__ __forceinline__ void load_table(int*, int, int) const {}
+  // Dyn3d::ExportSolution (dyn3d.cc:391-431): from (n, m, nB) follow the codes; emit(k, i0, j0)
+  // for the k-th (0-based) matched pair with 0-based residue indices
+  template <class Emit>
+  __device__ __forceinline__ void walk(const int*, const uint32_t* __restrict__ tbo, int n, int m, int nB, Emit emit) const {
+    int cn = n, ci = m, cj = nB;
+    while (cn > 0) {
+      const uint32_t code = (tbo[word(cn, ci, cj)] >> shift(ci)) & 3u;  // 0 match, 1 skip-i, 2 skip-j
+      if (code == 0) emit(cn - 1, ci - 1, cj - 1);
+      cn -= (code == 0);
+      ci -= (code != 2);
+      cj -= (code != 1);
+    }
+  }
   __device__ __forceinline__ size_t addr(const int*, int n, int i, int j) const { return word(n, i, j); }
   __device__ __forceinline__ uint32_t decode(uint32_t w, int i, int /*j*/) const { return (w >> shift(i)) & 3u; }
 };
@@ -287,14 +300,7 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
   short2* my = scratch + (size_t)(tid >> 5) * 32 * P.N + (tid & 31);
 #define MY(k) my[(size_t)(k) * 32]
   const uint32_t* tbo = tb + (size_t)s * L.words(P.nB);
-  int cn = n, ci = P.m, cj = P.nB;
-  while (cn > 0) {
-    const uint32_t code = L.decode(tbo[L.addr(tab, cn, ci, cj)], ci, cj);  // 0 match, 1 skip-i, 2 skip-j
-    if (code == 0) MY(cn - 1) = make_short2((short)(ci - 1), (short)(cj - 1));
-    cn -= (code == 0);
-    ci -= (code != 2);
-    cj -= (code != 1);
-  }
+  L.walk(tab, tbo, n, P.m, P.nB, [&](int k, int i0, int j0) { MY(k) = make_short2((short)i0, (short)j0); });
   float T[12];
   float ssd;
   if (P.refine_while_searching) {
