@@ -162,6 +162,8 @@ def main():
     s = SearchOrCuda(A, B, st, device=local)
     if args.kernel:
         s.set_option("dp_kernel", args.kernel)
+    if os.environ.get("MR_CHUNK"):
+        s.set_option("chunk", int(os.environ["MR_CHUNK"]))
     if os.environ.get("MR_EXP_DP_ONLY"):
         s.set_option("exp_dp_only", 1)   # kernel experiments only: results are invalid
     og = OrientationGenerator(s)

@@ -473,7 +473,7 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   p->threads = threads; p->nslots = nslots; p->steps = steps;
   p->smem = smem;
   const int by_smem = (int)(prop.sharedMemPerMultiprocessor / (smem + 1024));
-  int want = threads <= 256 ? 3 : (threads <= 384 ? 2 : 1);
+  int want = threads <= 384 ? 2 : 1;
 #ifdef MR_EXP_CTAS
   want = MR_EXP_CTAS;
 #endif
@@ -510,15 +510,19 @@ static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& 
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// Launch-bound buckets: the register budget is 65536 / (MAXT * MINB); fewer threads per CTA
+// leave the 4x8 tile code more registers (no spills at <= 352 threads, 2 CTAs per SM).
 static inline int mr_launch_dp_tiled(const MrTiledPlan& p, const MrDevParams& P, const float* A,
                                      const float* B, const float* orient, const int* surv,
                                      const int* surv_count, uint32_t* tb, float* cost, int count,
                                      cudaStream_t stream) {
-  if (p.threads <= 256) return mr_launch_dp_tiles_t<256, 3>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-#ifdef MR_EXP_MINB
-  if (p.threads <= 384) return mr_launch_dp_tiles_t<384, MR_EXP_MINB>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-#endif
-  if (p.threads <= 384) return mr_launch_dp_tiles_t<384, 2>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
-  if (p.threads <= 640) return mr_launch_dp_tiles_t<640, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+#define MR_TRY(MAXT, MINB) \
+  if (p.threads <= MAXT) return mr_launch_dp_tiles_t<MAXT, MINB>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream)
+  MR_TRY(256, 2);
+  MR_TRY(320, 2);
+  MR_TRY(352, 2);
+  MR_TRY(384, 2);
+  MR_TRY(512, 1);
+#undef MR_TRY
   return mr_launch_dp_tiles_t<1024, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
 }
