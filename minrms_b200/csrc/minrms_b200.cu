@@ -69,6 +69,7 @@ struct mr_ctx {
   int64_t opt_dp_kernel = 0;    // 0 auto, 1 general, 2 tiled
   int64_t opt_budget_mb = 16384;
   int64_t opt_chunk = 0;
+  int64_t opt_nw_general = 0;   // force the thread-per-orientation NW filter
   int64_t opt_dp_only = 0;      // experiments: skip traceback/select (results invalid)
   mr_stats st;
   std::vector<EventPair> events;
@@ -265,9 +266,22 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
     EventPair* ev = next_events(c, 1);
     if (!ev) MR_FAIL(c, "cudaEventCreate failed");
     CU(c, cudaEventRecord(ev->a, c->stream));
-    const int grid = (count + 127) / 128;
-    k_nw_filter<<<grid, 128, 0, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, c->d_rowcost,
-                                            c->d_rowcnt, c->d_nw, c->d_surv, c->d_surv_count);
+    const int cpl = (c->nB + 31) / 32;
+    if (c->hp.nb == 1 && cpl <= 8 && !c->opt_nw_general) {
+      // warp per orientation, wavefront in registers
+      const int grid = (count + 3) / 4;
+      const size_t sm = 4 * 3 * (size_t)c->m;
+#define MR_NW(CPL) k_nw_filter_warp<CPL><<<grid, 128, sm, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, c->d_nw, c->d_surv, c->d_surv_count)
+      switch (cpl) {
+        case 1: MR_NW(1); break; case 2: MR_NW(2); break; case 3: MR_NW(3); break; case 4: MR_NW(4); break;
+        case 5: MR_NW(5); break; case 6: MR_NW(6); break; case 7: MR_NW(7); break; default: MR_NW(8); break;
+      }
+#undef MR_NW
+    } else {
+      const int grid = (count + 127) / 128;
+      k_nw_filter<<<grid, 128, 0, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, c->d_rowcost,
+                                              c->d_rowcnt, c->d_nw, c->d_surv, c->d_surv_count);
+    }
     CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(ev->b, c->stream));
     c->st.nw_cells += nw_cells(c->m, c->nB, c->hp.of_min) * (int64_t)count;
@@ -508,6 +522,7 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "budget_mb")) c->opt_budget_mb = std::max<int64_t>(64, value);
   else if (!strcmp(name, "chunk")) c->opt_chunk = value;
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
+  else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);
   else MR_FAIL(c, "mr_set_option: unknown option %s", name);
   if (c->opt_dp_kernel == 2 && !c->tiled.ok) MR_FAIL(c, "tiled DP kernel not available for this problem: %s", c->tiled.why);
   return 0;

@@ -162,6 +162,87 @@ k_nw_filter(MrDevParams P, const float* __restrict__ A, const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------
+// K1+K2, warp-per-orientation variant (nB <= 32*CPL): lane l owns columns l*CPL+1..(l+1)*CPL
+// of the NW table and walks the rows as a wavefront (lane l is at row t-l at time t); the
+// value to its left arrives by shuffle from lane l-1, everything else stays in registers.
+// The rotated coordinates of the lane's columns are computed once.  Cells outside the band
+// take the border formula (i+j)*G with count 0 -- exactly the border cells the reference
+// initialises (dynNW.cc:200-234) are the out-of-band cells that ever get read.
+// ---------------------------------------------------------------------------
+template <int CPL>
+__global__ void __launch_bounds__(128)
+k_nw_filter_warp(MrDevParams P, const float* __restrict__ A, const float* __restrict__ B,
+                 const float* __restrict__ orient, int count, int* __restrict__ nw_matches,
+                 int* __restrict__ surv, int* __restrict__ surv_count) {
+  extern __shared__ float nw_sA[];  // m*3 (one atom per residue)
+  const int m = P.m, nB = P.nB, w0 = P.w0, w1 = P.w1;
+  for (int k = threadIdx.x; k < m * 3; k += blockDim.x) nw_sA[k] = A[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= count) return;
+  const float G = P.nw_gap, cutoff = P.nw_cutoff;
+  float T[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) T[k] = orient[12 * (size_t)o + k];
+  const int j0 = lane * CPL;  // my columns are j0+1 .. j0+CPL
+  float bx[CPL], by[CPL], bz[CPL], up[CPL];
+  int upc[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; c++) {
+    const int j = j0 + 1 + c;
+    bx[c] = by[c] = bz[c] = 0.0f;
+    if (j <= nB) mr_xform(T, B[3 * (j - 1)], B[3 * (j - 1) + 1], B[3 * (j - 1) + 2], bx[c], by[c], bz[c]);
+    up[c] = (float)j * G;  // row 0
+    upc[c] = 0;
+  }
+  float last = 0.0f, diag_in = (float)j0 * G;  // my last column at my current row; A[i-1][j0]
+  int lastc = 0, diag_inc = 0;
+  int result = 0;
+  for (int t = 1; t <= m + 31; t++) {
+    // value / count to my left at the row I am about to process: lane-1 finished it last step
+    float left = __shfl_up_sync(0xffffffffu, last, 1);
+    int leftc = __shfl_up_sync(0xffffffffu, lastc, 1);
+    const int i = t - lane;
+    if (lane == 0) { left = (float)i * G; leftc = 0; }  // column 0
+    if (i >= 1 && i <= m) {
+      const int jlo = (i <= w0) ? 1 : i - w0 + 1;
+      const int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
+      const float ax = nw_sA[3 * (i - 1)], ay = nw_sA[3 * (i - 1) + 1], az = nw_sA[3 * (i - 1) + 2];
+      float diag = diag_in;
+      int diagc = diag_inc;
+      diag_in = left;  // A[i][j0] is the diagonal input of my first column at the next row
+      diag_inc = leftc;
+#pragma unroll
+      for (int c = 0; c < CPL; c++) {
+        const int j = j0 + 1 + c;
+        float cc = mr_d2(ax, ay, az, bx[c], by[c], bz[c]);
+        if (cc > cutoff) cc = MR_UB;
+        const float c_match = diag + cc, c_i = up[c] + G, c_j = left + G;
+        float best = c_i;  // tie order of dynNW.cc:350-363: skip-i, then skip-j (<), then match (<)
+        int bc = upc[c];
+        if (c_j < best) { best = c_j; bc = leftc; }
+        if (c_match < best) { best = c_match; bc = diagc + 1; }
+        if (j < jlo || j > jhi) { best = (float)(i + j) * G; bc = 0; }
+        diag = up[c]; diagc = upc[c];
+        up[c] = best; upc[c] = bc;
+        left = best; leftc = bc;
+        if (i == m && j == nB) result = bc;
+      }
+      last = left;
+      lastc = leftc;
+    }
+  }
+  // the lane that owns column nB holds the count at (m, nB)
+  const int owner = (nB - 1) / CPL;
+  result = __shfl_sync(0xffffffffu, result, owner);
+  if (lane == 0) {
+    nw_matches[o] = result;
+    if (result >= P.of_min) surv[atomicAdd(surv_count, 1)] = o;
+  }
+}
+
 // identity survivor list when the filter is off
 __global__ void k_iota(int* __restrict__ surv, int* __restrict__ surv_count, int count) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
