@@ -255,6 +255,12 @@ def main():
     peak_gcups_max = sms * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 3 / 1e9
     launches = max(stats["dp_kernel_launches"], 1)
     tb_bytes = 0.25 * stats["dp_cells"] / launches          # 2-bit traceback, algorithmic
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):                                # dram bytes from one ncu --set full capture
+        tj = json.load(open(tpath))
+        per_o = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["orientations_in_launch"]
+        traffic = per_o * stats["orientations_dp"] / launches
     roofline = {"bound": "alu_issue", "achieved": dp_gcups_kernel, "peak": peak_gcups, "unit": "GCUPS",
                 "frac": dp_gcups_kernel / peak_gcups if peak_gcups else None,
                 "frac_at_max_clock": dp_gcups_kernel / peak_gcups_max,
@@ -262,7 +268,10 @@ def main():
                 "kernel": "3-D DP (k_dp_*)", "launches": stats["dp_kernel_launches"],
                 "avg_launch_ms": dp_ms / launches,
                 "cells_per_launch": stats["dp_cells"] / launches,
-                "traffic": None,
+                "traffic": traffic,
+                "alu_pipe_ceiling": {"peak": sms * 64 * f_mhz * 1e6 / 2 / 1e9, "unit": "GCUPS",
+                                     "def": "2 FMIN per cell on the half-rate ALU pipe (64 lanes/clk/SM)",
+                                     "frac": dp_gcups_kernel / (sms * 64 * f_mhz * 1e6 / 2 / 1e9)},
                 "hbm": {"bound": "hbm", "achieved": tb_bytes / (dp_ms / launches * 1e-3) / 1e9 if dp_ms else 0.0,
                         "peak": pk["hbm_gbs"], "unit": "GB/s", "peak_kind": pk_kind,
                         "algorithmic_bytes_per_launch": tb_bytes,

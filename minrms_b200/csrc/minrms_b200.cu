@@ -67,7 +67,7 @@ struct mr_ctx {
   long long id_offset = 0;
   bool id_offset_set = false;
   int64_t opt_dp_kernel = 0;    // 0 auto, 1 general, 2 tiled
-  int64_t opt_budget_mb = 16384;
+  int64_t opt_budget_mb = 32768;
   int64_t opt_chunk = 0;
   int64_t opt_nw_general = 0;   // force the thread-per-orientation NW filter
   int64_t opt_dp_only = 0;      // experiments: skip traceback/select (results invalid)
