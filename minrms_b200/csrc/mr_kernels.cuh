@@ -345,8 +345,11 @@ k_dp_columns(MrDevParams P, TbColumns L, const float* __restrict__ A, const floa
 //   items == NULL: dense grid over (s, n in [n_lo, n_max]);  else explicit (s,n) list.
 //   EMIT: also write the transform and the pair list.
 // ---------------------------------------------------------------------------
+#ifndef MR_TB_MINB
+#define MR_TB_MINB 12
+#endif
 template <class Layout, bool EMIT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MR_TB_MINB)
 k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const float* __restrict__ B,
                    const float* __restrict__ orient, const int* __restrict__ surv,
                    const int* __restrict__ surv_count, const uint32_t* __restrict__ tb,
