@@ -50,6 +50,7 @@ def test_cli_two_gpu_slices_give_identical_files(tmp_path):
     env = dict(os.environ, MINRMS_CUDA_GPUS="2")
     for f in ("hemoglobin.pdb", "myoglobin.pdb"):
         subprocess.check_call(["cp", os.path.join(ROOT, "tests", "golden", f), str(tmp_path)])
-    subprocess.check_call([EXE] + CONFIGS["c1"] + ["hemoglobin.pdb,*.A", "myoglobin.pdb"], cwd=str(tmp_path),
-                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+    r = subprocess.run([EXE] + CONFIGS["c1"] + ["hemoglobin.pdb,*.A", "myoglobin.pdb"], cwd=str(tmp_path),
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-500:]
     assert digest_dir(str(tmp_path)) == want
