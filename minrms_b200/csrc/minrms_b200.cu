@@ -183,7 +183,6 @@ int ensure_chunk(mr_ctx* c, int64_t want) {
   cap = std::max<int64_t>(1, std::min<int64_t>(cap, 1 << 18));
   if (c->opt_chunk > 0) cap = std::min<int64_t>(cap, c->opt_chunk);
   int64_t need = std::min<int64_t>(want, cap);
-  need = std::max<int64_t>(need, (int64_t)std::max(c->R, 1));  // winners pass needs R slots
   if (need <= c->chunk_cap && words == c->tb_words) return 0;
   cudaStreamSynchronize(c->stream);
   harvest(c);
@@ -224,7 +223,7 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count) {
       MR_FAIL(c, "tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else {
     int grid = std::min(count, c->dp_grid_cap);
-    k_dp_columns<<<grid, c->NP, c->dp_smem, c->stream>>>(c->P, c->Lc, c->dA, c->dB, d_orient_chunk,
+    k_dp_columns<<<grid, std::min(c->NP, 1024), c->dp_smem, c->stream>>>(c->P, c->Lc, c->dA, c->dB, d_orient_chunk,
                                                         c->d_surv, c->d_surv_count, c->d_tb,
                                                         c->d_cost, c->d_gcol, c->use_gcol);
   }
@@ -368,29 +367,41 @@ int fetch_payload(mr_ctx* c, const float* d_orient, long long id_offset, mr_best
     item_r.push_back(r);
   }
   if (items.empty()) return 0;
-  const int nw = (int)idx.size(), ni = (int)items.size();
-  if (ensure_chunk(c, nw)) return 1;
-  CU(c, cudaMemcpyAsync(c->d_widx, idx.data(), 4 * (size_t)nw, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemcpyAsync(c->d_items, items.data(), sizeof(int2) * (size_t)ni, cudaMemcpyHostToDevice, c->stream));
-  k_gather_orient<<<(nw * 12 + 127) / 128, 128, 0, c->stream>>>(d_orient, c->d_widx, nw, c->d_orient_w);
-  CU(c, cudaGetLastError());
-  c->st.kernel_launches++;
-  if (launch_filter(c, c->d_orient_w, nw, false)) return 1;
-  if (launch_dp(c, c->d_orient_w, nw)) return 1;
-  if (launch_tb<true>(c, c->d_orient_w, nw, c->d_items, ni)) return 1;
-  std::vector<float> T((size_t)ni * 12);
-  std::vector<short> pairs((size_t)ni * 2 * c->N);
-  CU(c, cudaMemcpyAsync(T.data(), c->d_Tout, 4 * T.size(), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaMemcpyAsync(pairs.data(), c->d_pairs_out, 2 * pairs.size(), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  c->st.d2h_bytes += (int64_t)(4 * T.size() + 2 * pairs.size());
-  for (int k = 0; k < ni; k++) {
-    const int r = item_r[k], n = c->hp.n_min + r;
-    unsigned int bits = (unsigned int)(keys[r] >> 32);
-    memcpy(&out->ssd[r], &bits, 4);
-    memcpy(out->T + 12 * r, &T[12 * (size_t)k], 48);
-    memcpy(out->pairs + (size_t)r * 2 * c->N, &pairs[(size_t)k * 2 * c->N], sizeof(short) * 2 * (size_t)n);
-    if (out->o_id) out->o_id[r] = (long long)(keys[r] & 0xffffffffull);
+  if (ensure_chunk(c, (int64_t)idx.size())) return 1;
+  // the winners are re-evaluated in groups that fit the chunk work space
+  // (large problems hold only a few traceback tables at a time)
+  for (size_t g0 = 0; g0 < idx.size(); g0 += (size_t)c->chunk_cap) {
+    const int nw = (int)std::min<size_t>((size_t)c->chunk_cap, idx.size() - g0);
+    std::vector<int2> sub;
+    std::vector<int> sub_r;
+    for (size_t k = 0; k < items.size(); k++)
+      if (items[k].x >= (int)g0 && items[k].x < (int)g0 + nw) {
+        sub.push_back(make_int2(items[k].x - (int)g0, items[k].y));
+        sub_r.push_back(item_r[k]);
+      }
+    const int ni = (int)sub.size();
+    CU(c, cudaMemcpyAsync(c->d_widx, idx.data() + g0, 4 * (size_t)nw, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_items, sub.data(), sizeof(int2) * (size_t)ni, cudaMemcpyHostToDevice, c->stream));
+    k_gather_orient<<<(nw * 12 + 127) / 128, 128, 0, c->stream>>>(d_orient, c->d_widx, nw, c->d_orient_w);
+    CU(c, cudaGetLastError());
+    c->st.kernel_launches++;
+    if (launch_filter(c, c->d_orient_w, nw, false)) return 1;
+    if (launch_dp(c, c->d_orient_w, nw)) return 1;
+    if (launch_tb<true>(c, c->d_orient_w, nw, c->d_items, ni)) return 1;
+    std::vector<float> T((size_t)ni * 12);
+    std::vector<short> pairs((size_t)ni * 2 * c->N);
+    CU(c, cudaMemcpyAsync(T.data(), c->d_Tout, 4 * T.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(pairs.data(), c->d_pairs_out, 2 * pairs.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->st.d2h_bytes += (int64_t)(4 * T.size() + 2 * pairs.size());
+    for (int k = 0; k < ni; k++) {
+      const int r = sub_r[k], n = c->hp.n_min + r;
+      unsigned int bits = (unsigned int)(keys[r] >> 32);
+      memcpy(&out->ssd[r], &bits, 4);
+      memcpy(out->T + 12 * r, &T[12 * (size_t)k], 48);
+      memcpy(out->pairs + (size_t)r * 2 * c->N, &pairs[(size_t)k * 2 * c->N], sizeof(short) * 2 * (size_t)n);
+      if (out->o_id) out->o_id[r] = (long long)(keys[r] & 0xffffffffull);
+    }
   }
   return 0;
 }
@@ -458,7 +469,6 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   if (cudaMemcpy(c->dA, A, na * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail("memcpy");
   if (cudaMemcpy(c->dB, B, nbb * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail("memcpy");
   // general DP kernel: column buffers in shared memory when they fit
-  if (c->NP > 1024) { g_create_error = "mr_create: n_max > 1024 is not supported yet"; mr_destroy(c); return 1; }
   const size_t colbytes = 2 * (size_t)(m + 1) * c->NP * 4;
   const size_t coordbytes = (na + nbb) * 4;
   const size_t smem_max = c->prop.sharedMemPerBlockOptin;

@@ -266,7 +266,7 @@ k_dp_columns(MrDevParams P, TbColumns L, const float* __restrict__ A, const floa
              float* __restrict__ cost_out, float* __restrict__ gcol, int use_gcol) {
   extern __shared__ float smem[];
   const int m = P.m, nB = P.nB, nb = P.nb, NP = L.NP;
-  const int n = threadIdx.x + 1;
+  const int n0 = threadIdx.x + 1;
   float* sA = smem;                       // m*nb*3
   float* sB = sA + (size_t)m * nb * 3;     // nB*nb*3 rotated
   float* col0;
@@ -293,12 +293,14 @@ k_dp_columns(MrDevParams P, TbColumns L, const float* __restrict__ A, const floa
     }
     __syncthreads();
     uint32_t* tbo = tb + (size_t)s * L.words(nB);
-    const bool live_n = n <= P.n_max;
-    const int imax = min(m, n + P.wA - 1), jmax = min(nB, n + P.wB - 1);
     float* colA = col0;
     float* colB = col1;
     for (int j = 1; j <= nB; j++) {
-      if (live_n && j >= n && j <= jmax) {
+      // one layer per thread; more than blockDim layers (n_max > 1024): a thread takes
+      // layers n0, n0 + blockDim, ... (all state of a layer lives in the column buffers)
+      for (int n = n0; n <= P.n_max; n += blockDim.x) {
+        const int imax = min(m, n + P.wA - 1), jmax = min(nB, n + P.wB - 1);
+        if (j < n || j > jmax) continue;
         float up = INF;
         uint32_t acc = 0;
         float res = 0.f;

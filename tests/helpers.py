@@ -78,7 +78,7 @@ def random_chain(rng, n, nb=1):
     return np.round(pts, 3).astype(np.float32)
 
 
-def related_chain(rng, A, nB, nb=1, noise=1.0):
+def related_chain(rng, A, nB, nb=1, noise=1.0, return_idx=False):
     """a rigidly moved, noisy copy of A with indels, length nB residues"""
     m = A.shape[0] // nb
     idx = np.sort(rng.choice(m, size=min(m, nB), replace=False))
@@ -93,4 +93,5 @@ def related_chain(rng, A, nB, nb=1, noise=1.0):
                    [2*(b*c+a*d), a*a-b*b+c*c-d*d, 2*(c*d-a*b)],
                    [2*(b*d-a*c), 2*(c*d+a*b), a*a-b*b-c*c+d*d]])
     out = base.reshape(-1, 3) @ Rm.T + rng.normal(scale=10, size=3) + rng.normal(scale=noise, size=(nB * nb, 3))
-    return np.round(out, 3).astype(np.float32)
+    out = np.round(out, 3).astype(np.float32)
+    return (out, idx) if return_idx else out

@@ -201,3 +201,45 @@ def test_error_paths():
     s.Search(OrientationGenerator(s))
     with pytest.raises(MinrmsError, match="No solutions"):   # search_or_dyn3d.cc:1929-1941
         s.check_solutions()
+
+
+def test_config3_size_pair_matches_oracle():
+    """600 x 600 (BASELINE config 3 size): beyond the register-tiled kernel, served by the
+    general column-sweep kernel; single orientations and a small search against the oracle"""
+    from minrms_b200 import OrientationGenerator
+    rng = np.random.default_rng(3000)
+    A = random_chain(rng, 600)
+    B = related_chain(rng, A, 600, noise=1.5)
+    p = oc.make_params(n_min=1, m=600, nB=600)
+    s = make_search(A, B, settings_from_params(p, 3))
+    og = OrientationGenerator(s)
+    assert og.size() == 598 * 598                       # SURVEY.md 8 a1: 357 604 orientations
+    ws = oc.Workspace(A, B, p)
+    pick = og.orientations[[0, 177000]]
+    for T in pick:
+        ref = ws.eval(T)
+        res = s.eval_one(T)
+        assert_eval_equal(res, ref["n_last"], ref["cost"], ref["valid"], ref["ssd"], ref["T"], ref["pairs"])
+    best = ws.search(pick)
+    s.Search(pick)
+    t = s.best_table()
+    assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], 1, "search")
+
+
+def test_config4_size_pair_matches_oracle():
+    """2000 x 1500 with -of 8.0,0.33 (BASELINE config 4 size: 1500 layers, 1.69 G cells and a
+    1.1 GB traceback table per orientation): one orientation end to end against the oracle"""
+    rng = np.random.default_rng(4000)
+    A = random_chain(rng, 2000)
+    B, idx = related_chain(rng, A, 1500, noise=1.0, return_idx=True)
+    p = oc.make_params(n_min=1, m=2000, nB=1500, use_filter=True, of_dist=8.0, of_min=495)
+    s = make_search(A, B, settings_from_params(p, 4))
+    ws = oc.Workspace(A, B, p)
+    # an orientation that superimposes the related residues (passes the filter) and the identity
+    r, T = oc.superimpose(A[idx], B)
+    for Tq, expect_pass in ((T, True), (IDENT, False)):
+        ref = ws.eval(Tq)
+        res = s.eval_one(Tq)
+        assert (ref["n_last"] > 0) == expect_pass
+        assert res["nw_matches"] == ref["nw_matches"]
+        assert_eval_equal(res, ref["n_last"], ref["cost"], ref["valid"], ref["ssd"], ref["T"], ref["pairs"])
