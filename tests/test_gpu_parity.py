@@ -243,3 +243,43 @@ def test_config4_size_pair_matches_oracle():
         assert (ref["n_last"] > 0) == expect_pass
         assert res["nw_matches"] == ref["nw_matches"]
         assert_eval_equal(res, ref["n_last"], ref["cost"], ref["valid"], ref["ssd"], ref["T"], ref["pairs"])
+
+
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_exact_ties_identical_and_symmetric_structures(kernel):
+    """many exactly equal costs: identical chains, an exact lattice, a palindromic chain --
+    the reference's tie order (match < skip-i < skip-j on '<=') decides the alignment"""
+    from minrms_b200 import OrientationGenerator
+    rng = np.random.default_rng(99)
+    A = random_chain(rng, 28)
+    lattice = np.array([[x, y, 0.0] for x in range(6) for y in range(5)], np.float32) * 3.8
+    pal = np.concatenate([A[:12], A[:12][::-1]])
+    for (P1, P2) in ((A, A.copy()), (lattice, lattice[:24].copy()), (pal, pal.copy()), (A, A[::-1].copy())):
+        m, nB = P1.shape[0], P2.shape[0]
+        p = oc.make_params(n_min=1, m=m, nB=nB)
+        s = make_search(P1, P2, settings_from_params(p, 3), kernel)
+        ws = oc.Workspace(P1, P2, p)
+        og_ref = oc.gen_orientations(P1, P2, 1, 3, 1)
+        og = OrientationGenerator(s)
+        assert np.array_equal(bits(og.orientations), bits(og_ref))
+        for T in (IDENT, og_ref[0], og_ref[og_ref.shape[0] // 2]):
+            ref = ws.eval(T)
+            res = s.eval_one(T)
+            assert_eval_equal(res, ref["n_last"], ref["cost"], ref["valid"], ref["ssd"], ref["T"], ref["pairs"])
+        best = ws.search(og_ref)
+        s.Search(og)
+        t = s.best_table()
+        assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], 1, "ties")
+        assert np.array_equal(t["o_id"], best["o_id"])
+
+
+def test_single_residue_molecule_has_no_sizes():
+    """min(m, n) = 1: the n-loop starts at 2, so nothing is ever recorded (FirstPass ERRs)"""
+    from minrms_b200 import MinrmsError, Settings, SearchOrCuda
+    rng = np.random.default_rng(1)
+    s = SearchOrCuda(random_chain(rng, 1), random_chain(rng, 9), Settings(fm_fragment_size=1))
+    res = s.eval_one(IDENT)
+    assert res["n_last"] == 1 and not res["valid"].any()
+    s.Search(IDENT.reshape(1, 12))
+    with pytest.raises(MinrmsError):
+        s.check_solutions()
