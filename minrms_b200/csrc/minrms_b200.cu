@@ -14,6 +14,7 @@
 
 #include "mr_kernels.cuh"
 #include "mr_dp_tiled.cuh"
+#include "mr_dp_tiled_mp.cuh"
 
 namespace {
 
@@ -66,7 +67,7 @@ struct mr_ctx {
   int h_pinned_cap = 0;
   long long id_offset = 0;
   bool id_offset_set = false;
-  int64_t opt_dp_kernel = 0;    // 0 auto, 1 general, 2 tiled
+  int64_t opt_dp_kernel = 0;    // 0 auto, 1 general, 2 tiled (single pass), 3 tiled (multi-pass)
   int64_t opt_budget_mb = 32768;
   int64_t opt_chunk = 0;
   int64_t opt_nw_general = 0;   // force the thread-per-orientation NW filter
@@ -77,6 +78,8 @@ struct mr_ctx {
   std::vector<std::pair<int, int>> pending_counts;  // (pinned slot, chunk count)
   std::string err;
   MrTiledPlan tiled;
+  MrTiledMpPlan tiled_mp;
+  int64_t opt_mp_threads = 0;   // tests: threads per CTA of the multi-pass kernel (forces more passes)
   cudaEvent_t user_ev[16] = {};
 };
 
@@ -165,16 +168,22 @@ int ensure_orient_cap(mr_ctx* c, int64_t count) {
   return 0;
 }
 
-bool use_tiled(const mr_ctx* c) {
-  if (c->opt_dp_kernel == 1) return false;
-  return c->tiled.ok;
+// DP kernel in use: 0 general (k_dp_columns), 1 tiled single-pass, 2 tiled multi-pass
+int dp_path(const mr_ctx* c) {
+  if (c->opt_dp_kernel == 1) return 0;
+  if (c->opt_dp_kernel == 3) return c->tiled_mp.ok ? 2 : 0;
+  if (c->tiled.ok) return 1;
+  if (c->opt_dp_kernel == 2) return 0;
+  return c->tiled_mp.ok ? 2 : 0;
 }
+bool use_tiled(const mr_ctx* c) { return dp_path(c) != 0; }
+const TbTiled& tiled_layout(const mr_ctx* c) { return dp_path(c) == 2 ? c->tiled_mp.layout : c->tiled.layout; }
 
 // (re)allocate the per-chunk work space for chunks of up to `want` orientations
 int ensure_chunk(mr_ctx* c, int64_t want) {
   const size_t words_c = c->Lc.words(c->nB);
-  const size_t words_t = c->tiled.ok ? c->tiled.tb_words : 0;
-  const size_t words = std::max(words_c, words_t);
+  const int path = dp_path(c);
+  const size_t words = path == 2 ? c->tiled_mp.tb_words : path == 1 ? c->tiled.tb_words : words_c;
   const size_t per_thread_scr = (size_t)c->N * sizeof(short2);
   const int per = std::max(1, c->hp.n_max - std::max(2, c->hp.n_min) + 1);
   // bytes per orientation in a chunk
@@ -217,10 +226,15 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count) {
   EventPair* ev = next_events(c, 0);
   if (!ev) MR_FAIL(c, "cudaEventCreate failed");
   CU(c, cudaEventRecord(ev->a, c->stream));
-  if (use_tiled(c)) {
+  const int path = dp_path(c);
+  if (path == 1) {
     if (mr_launch_dp_tiled(c->tiled, c->P, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count,
                            c->d_tb, c->d_cost, count, c->stream) != 0)
       MR_FAIL(c, "tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  } else if (path == 2) {
+    if (mr_launch_dp_tiled_mp(c->tiled_mp, c->P, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count,
+                              c->d_tb, c->d_cost, count, c->stream) != 0)
+      MR_FAIL(c, "multi-pass tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else {
     int grid = std::min(count, c->dp_grid_cap);
     k_dp_columns<<<grid, std::min(c->NP, 1024), c->dp_smem, c->stream>>>(c->P, c->Lc, c->dA, c->dB, d_orient_chunk,
@@ -245,8 +259,8 @@ int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* ite
   const int grid = (int)((threads + 127) / 128);
   const size_t coords = 4 * 3 * (size_t)(c->m + c->nB) * c->hp.nb;
   if (use_tiled(c))
-    k_traceback_kabsch<TbTiled, EMIT><<<grid, 128, 4 * c->tiled.layout.table_ints() + coords, c->stream>>>(
-        c->P, c->tiled.layout, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb,
+    k_traceback_kabsch<TbTiled, EMIT><<<grid, 128, 4 * tiled_layout(c).table_ints() + coords, c->stream>>>(
+        c->P, tiled_layout(c), c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb,
         c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, c->d_Tout, c->d_pairs_out);
   else
     k_traceback_kabsch<TbColumns, EMIT><<<grid, 128, coords, c->stream>>>(
@@ -486,6 +500,7 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   if (cudaFuncSetAttribute(k_dp_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dp_smem) != cudaSuccess)
     return bail("smem attribute");
   mr_plan_dp_tiled(&c->tiled, P, c->prop, c->NP);
+  if (!c->tiled.ok) mr_plan_dp_tiled_mp(&c->tiled_mp, P, c->prop, c->NP);
   const int RR = std::max(c->R, 1), slots = std::max(RR, c->NP);
   if (cudaMalloc(&c->d_keys, 8 * (size_t)RR) != cudaSuccess) return bail("malloc");
   if (cudaMalloc(&c->d_surv_count, 4) != cudaSuccess) return bail("malloc");
@@ -515,6 +530,7 @@ void mr_destroy(mr_ctx* c) {
   cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
   cudaFree(c->d_pairs_in);
   mr_free_dp_tiled(&c->tiled);
+  mr_free_dp_tiled_mp(&c->tiled_mp);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -533,8 +549,20 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "chunk")) c->opt_chunk = value;
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
   else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);
+  else if (!strcmp(name, "mp_threads")) {
+    if (value != 0 && (value < 32 || value > 1024 || value % 32)) MR_FAIL(c, "mr_set_option: mp_threads must be a multiple of 32 in [32, 1024]");
+    c->opt_mp_threads = value;
+    if (cudaSetDevice(c->device) != cudaSuccess) MR_FAIL(c, "cudaSetDevice failed");
+    cudaStreamSynchronize(c->stream);
+    if (c->tiled_mp.ok || c->opt_dp_kernel == 3) mr_plan_dp_tiled_mp(&c->tiled_mp, c->P, c->prop, c->NP, (int)c->opt_mp_threads);
+  }
   else MR_FAIL(c, "mr_set_option: unknown option %s", name);
   if (c->opt_dp_kernel == 2 && !c->tiled.ok) MR_FAIL(c, "tiled DP kernel not available for this problem: %s", c->tiled.why);
+  if (c->opt_dp_kernel == 3) {
+    if (cudaSetDevice(c->device) != cudaSuccess) MR_FAIL(c, "cudaSetDevice failed");
+    if (!c->tiled_mp.ok) mr_plan_dp_tiled_mp(&c->tiled_mp, c->P, c->prop, c->NP, (int)c->opt_mp_threads);
+    if (!c->tiled_mp.ok) MR_FAIL(c, "multi-pass tiled DP kernel not available for this problem: %s", c->tiled_mp.why);
+  }
   return 0;
 }
 

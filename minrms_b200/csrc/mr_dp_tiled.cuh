@@ -44,9 +44,13 @@
 struct TbTiled {
   int K, R, W, JP, pad, NP, CN, T;  // layers/tile, rows/tile, strips, column pairs, top pad rows, cost pitch, chunks, threads
   const int* tile_of;
+  // the (strip, chunk) -> tile table is staged in shared memory by the traceback kernel when
+  // it is small (<= 8 KB); larger tables are read through L1/L2
   __host__ __device__ size_t words(int /*nB*/) const { return (size_t)JP * T * K; }
-  __host__ __device__ int table_ints() const { return (W * CN + 3) & ~3; }
+  __host__ __device__ bool table_in_smem() const { return W * CN <= 2048; }
+  __host__ __device__ int table_ints() const { return table_in_smem() ? ((W * CN + 3) & ~3) : 0; }
   __device__ __forceinline__ void load_table(int* tab, int tid, int nthreads) const {
+    if (!table_in_smem()) return;
     for (int k = tid; k < W * CN; k += nthreads) tab[k] = tile_of[k];
   }
   // K = 4 layers x R = 8 rows per tile (the only shape built): shifts instead of divisions
@@ -54,6 +58,12 @@ struct TbTiled {
   template <class Emit>
   __device__ __forceinline__ void walk(const int* __restrict__ tab, const uint32_t* __restrict__ tbo, int n,
                                        int m, int nB, Emit emit) const {
+    if (table_in_smem()) walk_t(tab, tbo, n, m, nB, emit);
+    else walk_t(tile_of, tbo, n, m, nB, emit);
+  }
+  template <class Emit>
+  __device__ __forceinline__ void walk_t(const int* __restrict__ tab, const uint32_t* __restrict__ tbo, int n,
+                                         int m, int nB, Emit emit) const {
     int cn = n, rho = m - 1 + pad, jm = nB - 1;
     const int T4 = 4 * T;
     while (cn > 0) {
@@ -115,12 +125,13 @@ __host__ __device__ inline int mr_ring_stride(int WR) { return WR + ((36 - (WR &
 template <bool NB1>
 __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float* __restrict__ sA,
                                              const float* __restrict__ sB, int j0, int WR, int WRp, int pad,
-                                             int nB, int nBp, int nb, float cutoff, int tid, int nthreads) {
+                                             int nB, int nBp, int nb, float cutoff, int tid, int nthreads,
+                                             int rho0 = 0) {
   const float INF = __int_as_float(0x7f800000);
   if (NB1) {
     for (int item = tid; item < (MR_CBATCH / 4) * WR; item += nthreads) {
       const int q4 = item / WR, rho = item - q4 * WR;
-      const int jn = j0 + 4 * q4, i = rho - pad + 1;
+      const int jn = j0 + 4 * q4, i = rho0 + rho - pad + 1;
       float cc[4] = {INF, INF, INF, INF};
       if (i >= 1 && jn <= nB) {
         const float ax = sA[3 * (i - 1)], ay = sA[3 * (i - 1) + 1], az = sA[3 * (i - 1) + 2];
@@ -143,7 +154,7 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
   } else {
     for (int e = tid; e < MR_CBATCH * WR; e += nthreads) {
       const int dj = e / WR, rho = e - dj * WR;
-      const int jn = j0 + dj, i = rho - pad + 1;
+      const int jn = j0 + dj, i = rho0 + rho - pad + 1;
       float cc = INF;
       if (i >= 1 && jn <= nB) {
         cc = 0.0f;
@@ -158,8 +169,6 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
     }
   }
 }
-
-__device__ int mr_sm_arrivals[256];
 
 // 16-byte shared-memory accesses through 32-bit shared addresses (one register each)
 __device__ __forceinline__ float4 mr_lds128(uint32_t a) {
@@ -212,24 +221,6 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
   const uint32_t a_c = (uint32_t)__cvta_generic_to_shared(Cr) + (uint32_t)(w * R) * 4u;
   const uint32_t c_row = (uint32_t)WRp * 4u;
   for (int k = tid; k < m * nb * 3; k += nthreads) sA[k] = A[k];
-#ifdef MR_EXP_PHASE
-  // the CTAs sharing an SM run identical work in lock step; delay every second arrival on an
-  // SM by about half an orientation so that their few-live-warps phases do not coincide
-  {
-    __shared__ int s_par;
-    if (tid == 0) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      s_par = atomicAdd(&mr_sm_arrivals[smid & 255], 1) & 1;
-    }
-    __syncthreads();
-    if (s_par && tid == 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < (long long)MR_EXP_PHASE) {}
-    }
-    __syncthreads();
-  }
-#endif
 
   for (int sv = blockIdx.x; sv < nsurv; sv += gridDim.x) {
     const float* T = orient + 12 * (size_t)surv[sv];

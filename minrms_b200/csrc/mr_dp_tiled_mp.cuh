@@ -1,0 +1,429 @@
+// mr_dp_tiled_mp.cuh -- multi-pass form of the register-tiled 3-D DP kernel (mr_dp_tiled.cuh)
+// for problems whose (layer,row) cross-section has more live 4x8 tiles than one CTA has
+// threads (roughly: chains longer than ~190 residues).
+//
+// Same recurrence, tie order, tile shape, exchange-slot protocol and traceback word format
+// as k_dp_tiles (Dyn3d::Solve_IncrN, lib/dyn/dyn3d.cc:183-387).  The row strips are cut into
+// PASSES of consecutive strips [w0, w1); a CTA still owns one orientation and sweeps the
+// columns once per pass, top strips first.  Between passes only the bottom row of the pass's
+// last strip, A(n, i_hi, j) for every layer and column, has to survive: it is written to a
+// per-CTA carry buffer in global memory (carry[j * CN + chunk] = 4 layers as one float4,
+// L2-resident) and read back, one column ahead, as the upper boundary of the first strip of
+// the next pass.  The buffer is updated in place: the reader of column j runs at step j-1,
+// the writer of column j at step j + (w1-1-w0), separated by at least one barrier.
+// Tiles that write the carry run over every column so that no entry is left over from an
+// earlier orientation.
+//
+// Global tile ids (pass offset + thread) index the same traceback layout as the single-pass
+// kernel (TbTiled with T = tiles of all passes), so K5 (k_traceback_kabsch) is unchanged.
+#pragma once
+#include "mr_dp_tiled.cuh"
+
+struct MrPass {
+  int w0, nstrips;   // first strip and number of strips of the pass
+  int nsteps;        // columns (even) + strips - 1
+  int gid_off;       // global id of thread 0's tile
+};
+
+struct MrTileMp {
+  int w, c;              // global row strip, layer chunk (-1: idle thread)
+  int s_lo, s_hi;        // first / last step of the pass at which this tile runs
+  int up_slot, dg_slot;  // exchange slots (up_slot = -1: upper boundary comes from the carry buffer)
+  int warp_lo, warp_hi;  // step window of the whole warp
+  int out;               // 1: publishes its bottom row to the carry buffer
+  int pad_;
+};
+
+template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, const MrPass* __restrict__ passes,
+              const MrTileMp* __restrict__ tiles, const float* __restrict__ A, const float* __restrict__ B,
+              const float* __restrict__ orient, const int* __restrict__ surv,
+              const int* __restrict__ surv_count, float4* carry_all, size_t carry_pitch,
+              uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
+  static_assert(R == 8 && K == 4, "traceback word packing assumes 4 x 8 tiles");
+  extern __shared__ float4 smem4[];
+  const int m = P.m, nB = P.nB, nb = P.nb;
+  const int W = L.W, pad = L.pad, CN = L.CN;
+  const int nBe = 2 * L.JP;
+  const int WRp = mr_ring_stride(wl_max * R);  // ring row stride (floats), = 4 mod 32
+  const int nBp = (nB * nb + 11) & ~3;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  float4* exch = smem4;
+  float* Cr = reinterpret_cast<float*>(exch + 6 * nslots);
+  float* sB = Cr + MR_CRING * WRp;
+  float* sA = sB + 3 * nBp;
+  const float INF = __int_as_float(0x7f800000);
+  const int nsurv = *surv_count;
+  float4* carry = carry_all + (size_t)blockIdx.x * carry_pitch;
+
+  const uint32_t exch0 = (uint32_t)__cvta_generic_to_shared(exch);
+  const uint32_t par_bytes = (uint32_t)nslots * 48u;
+  const uint32_t a_me = exch0 + (uint32_t)tid * 48u;
+  const uint32_t c_row = (uint32_t)WRp * 4u;
+  const uint32_t cr0 = (uint32_t)__cvta_generic_to_shared(Cr);
+  for (int k = tid; k < m * nb * 3; k += nthreads) sA[k] = A[k];
+
+  for (int sv = blockIdx.x; sv < nsurv; sv += gridDim.x) {
+    const float* T = orient + 12 * (size_t)surv[sv];
+    __syncthreads();
+    for (int k = tid; k < nBp; k += nthreads) {
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (k < nB * nb) mr_xform(T, B[3 * k], B[3 * k + 1], B[3 * k + 2], x, y, z);
+      if (NB1) {
+        sB[k] = x; sB[nBp + k] = y; sB[2 * nBp + k] = z;
+      } else if (k < nB * nb) {
+        sB[3 * k] = x; sB[3 * k + 1] = y; sB[3 * k + 2] = z;
+      }
+    }
+    uint4* const tb_o = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB));
+
+    for (int ps = 0; ps < npasses; ps++) {
+      const MrPass pass = passes[ps];
+      const MrTileMp* ptiles = tiles + (size_t)ps * nthreads;
+      const MrTileMp me = ptiles[tid];
+      const bool has_tile = me.w >= 0;
+      const int w = has_tile ? me.w : pass.w0, c = has_tile ? me.c : 0;
+      const int wl = w - pass.w0;  // strip within the pass: this tile runs wl columns behind
+      const int nsteps = pass.nsteps;
+      const int WR = pass.nstrips * R, rho0 = pass.w0 * R;
+      const int warp_lo = me.warp_lo, warp_hi = min(me.warp_hi, nsteps);
+      const int tb_hi = has_tile ? me.s_hi : -1;
+      const int tb_first = has_tile ? me.s_lo + ((me.s_lo - wl) & 1) : 0x3fffffff;
+      const int cost_step = (has_tile && w == W - 1) ? nB + wl : -1;
+      const bool from_carry = has_tile && me.up_slot < 0;
+      const int out_lo = (has_tile && me.out) ? 1 + wl : 0x3fffffff;  // carry columns 1..nBe
+      const uint32_t a_up = exch0 + (uint32_t)max(me.up_slot, 0) * 48u + 32u;
+      const uint32_t a_dg = exch0 + (uint32_t)me.dg_slot * 48u;
+      const uint32_t a_c = cr0 + (uint32_t)(wl * R) * 4u;
+      float4* const cme = carry + c;
+
+      __syncthreads();  // previous pass (or the rotation) is complete
+      for (int k = tid; k < 2 * nslots; k += nthreads) {
+        const int sl = k % nslots;
+        const bool zero = sl == nslots - 2 || (sl < nslots - 2 && ptiles[sl].c == 0);
+        exch[3 * k] = make_float4(INF, INF, INF, INF);
+        exch[3 * k + 1] = make_float4(INF, INF, INF, INF);
+        exch[3 * k + 2] = make_float4(zero ? 0.0f : INF, INF, INF, INF);
+      }
+      for (int k = tid; k < MR_CRING * WRp; k += nthreads) Cr[k] = INF;
+      __syncthreads();
+      mr_produce_c<NB1>(Cr, sA, sB, 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+
+      float st[K][R], bprev[K];
+      uint32_t acc[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const float v = (c * K + k == 0) ? 0.0f : INF;
+        bprev[k] = v;
+        acc[k] = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) st[k][r] = v;
+      }
+      uint4* tbp = tb_o + (pass.gid_off + tid) + (size_t)max(0, (tb_first - wl - 1) >> 1) * L.T;
+      int tb_next = tb_first;
+      __syncthreads();
+
+      int s = 1;
+      for (; s < warp_lo && s <= nsteps; s++) {
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+        __syncthreads();
+      }
+      uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
+      // upper boundary of the first strip: column j = s of the carry, fetched one step ahead
+      float4 gnext = make_float4(INF, INF, INF, INF);
+      if (from_carry) gnext = __ldcg(cme + (size_t)min(s, nBe + 1) * CN);
+      for (; s <= warp_hi; s++) {
+        float cv[R];
+        {
+          const uint32_t ca = a_c + (uint32_t)((s - wl) & (MR_CRING - 1)) * c_row;
+          const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
+          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
+          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
+        }
+        float bin[K];
+        {
+          float4 v = mr_lds128(a_up + rd_off);
+          if (from_carry) {
+            v = gnext;
+            gnext = __ldcg(cme + (size_t)min(s + 1, nBe + 1) * CN);
+          }
+          bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
+        }
+        float dsh[R];
+        {
+          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
+          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
+        }
+#pragma unroll
+        for (int k = K - 1; k >= 0; k--) {
+          float up = bin[k];
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
+            const float d = dg + cv[r];
+            const float left = st[k][r];
+            const float t = fminf(d, up);
+            const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
+            const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
+            const float best = fminf(t, left);
+            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+            st[k][r] = best;
+            up = best;
+          }
+        }
+        mr_sts128(a_me + wr_off, bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
+        mr_sts128(a_me + wr_off + 16u, st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
+        mr_sts128(a_me + wr_off + 32u, st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
+#pragma unroll
+        for (int k = 0; k < K; k++) bprev[k] = bin[k];
+        // bottom row of the pass -> carry[column j = s - wl]
+        if ((unsigned)(s - out_lo) < (unsigned)nBe)
+          __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]));
+        if (s == tb_next) {
+          *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+          tbp += L.T;
+          tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
+        }
+        if (s == cost_step) {
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const int n = c * K + k;
+            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
+          }
+        }
+        // n < n_min: corner of the layer's window (dyn3d.cc:385, dyn3d.h:407-408)
+        if (WINDOWED && has_tile) {
+          const int nq = s - wl - P.wB + 1;
+          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
+            const int rho = nq + P.wA - 2 + pad;
+            if ((rho >> 3) == w) {
+              const int kq = nq & 3, rq = rho & 7;
+              float v = 0.0f;
+#pragma unroll
+              for (int k = 0; k < K; k++)
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                  if (k == kq && r == rq) v = st[k][r];
+              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+            }
+          }
+        }
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+        { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
+        __syncthreads();
+      }
+      for (; s <= nsteps; s++) {
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- host
+struct MrTiledMpPlan {
+  bool ok = false;
+  const char* why = "not planned";
+  int W = 0, CN = 0, nBe = 0;
+  int threads = 0, minb = 1, nslots = 0, npasses = 0, wl_max = 0;
+  size_t smem = 0;
+  int grid_cap = 0;
+  size_t tb_words = 0, carry_pitch = 0;
+  double lane_efficiency = 0.0;
+  TbTiled layout;
+  MrPass* d_passes = nullptr;
+  MrTileMp* d_tiles = nullptr;
+  int* d_tile_of = nullptr;
+  float4* d_carry = nullptr;
+};
+
+static inline void mr_free_dp_tiled_mp(MrTiledMpPlan* p) {
+  if (p->d_passes) cudaFree(p->d_passes);
+  if (p->d_tiles) cudaFree(p->d_tiles);
+  if (p->d_tile_of) cudaFree(p->d_tile_of);
+  if (p->d_carry) cudaFree(p->d_carry);
+  p->d_passes = nullptr; p->d_tiles = nullptr; p->d_tile_of = nullptr; p->d_carry = nullptr;
+}
+
+static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, const cudaDeviceProp& prop, int NP,
+                                       int max_threads = 0) {
+  p->ok = false;
+  const int R = 8, K = 4;
+  const int m = P.m, nB = P.nB;
+  const int W = (m + R - 1) / R, pad = W * R - m;
+  const int CN = (P.n_max + 1 + K - 1) / K;
+  const int nBe = (nB + 1) & ~1;
+  const int WL_MAX = MR_CRING - MR_CBATCH;  // strips per pass the C ring can hold
+  struct T { int w, c, jlo, jhi; };         // window in columns
+  std::vector<T> all;
+  std::vector<int> have((size_t)W * CN, -1);
+  long long live_cells = 0;
+  for (int n = 1; n <= P.n_max; n++)
+    live_cells += (long long)(std::min(m, n + P.wA - 1) - n + 1) * (std::min(nB, n + P.wB - 1) - n + 1);
+  for (int w = 0; w < W; w++) {
+    const int i_lo = w * R + 1 - pad, i_hi = w * R + R - pad;
+    for (int c = 0; c < CN; c++) {
+      int jlo = 1 << 30, jhi = -1;
+      for (int n = std::max(1, c * K); n <= std::min(P.n_max, c * K + K - 1); n++) {
+        const int imax = std::min(m, n + P.wA - 1);
+        if (std::max(n, i_lo) > std::min(imax, i_hi)) continue;
+        jlo = std::min(jlo, n);
+        jhi = std::max(jhi, std::min(nB, n + P.wB - 1));
+      }
+      if (c == 0) { jlo = std::min(jlo, 1); jhi = std::max(jhi, 1); }
+      if (jhi < 0) continue;
+      jhi = (jhi + 1) & ~1;
+      have[(size_t)w * CN + c] = (int)all.size();
+      all.push_back({w, c, jlo, jhi});
+    }
+  }
+  // closure (see mr_plan_dp_tiled): tile (w,c-1) relays the corner value tile (w,c) needs
+  {
+    const size_t n0 = all.size();
+    for (size_t t = 0; t < n0; t++) {
+      const T x = all[t];
+      if (x.c >= 1 && have[(size_t)x.w * CN + x.c - 1] < 0) {
+        have[(size_t)x.w * CN + x.c - 1] = (int)all.size();
+        all.push_back({x.w, x.c - 1, std::max(1, x.jlo - 1), x.jhi});
+      }
+    }
+  }
+  std::vector<int> per_strip(W, 0);
+  for (const T& x : all) per_strip[x.w]++;
+  const int widest = *std::max_element(per_strip.begin(), per_strip.end());
+  int threads = 352, minb = 2;
+  if (widest > 352) { threads = 384; }
+  if (widest > 384) { threads = 512; minb = 1; }
+  if (widest > 512) { threads = 1024; }
+  if (max_threads > 0 && widest <= max_threads) { threads = max_threads; minb = threads <= 384 ? 2 : 1; }
+  if (widest > 1024) { p->why = "more than 1024 live tiles in one row strip"; return; }
+  // passes: consecutive strips while the tiles fit one CTA
+  std::vector<MrPass> passes;
+  for (int w0 = 0; w0 < W;) {
+    int w1 = w0, cnt = 0;
+    while (w1 < W && w1 - w0 < WL_MAX && cnt + per_strip[w1] <= threads) cnt += per_strip[w1++];
+    MrPass ps;
+    ps.w0 = w0; ps.nstrips = w1 - w0; ps.nsteps = nBe + (w1 - w0) - 1; ps.gid_off = 0;
+    passes.push_back(ps);
+    w0 = w1;
+  }
+  const int npasses = (int)passes.size();
+  const int nslots = threads + 2;
+  std::vector<MrTileMp> tab((size_t)npasses * threads);
+  std::vector<int> index((size_t)W * CN, 0);
+  int gid = 0, wl_max = 0;
+  long long warp_steps = 0;
+  for (int q = 0; q < npasses; q++) {
+    MrPass& ps = passes[q];
+    const int w0 = ps.w0, w1 = ps.w0 + ps.nstrips;
+    wl_max = std::max(wl_max, ps.nstrips);
+    struct S { int w, c, lo, hi, out; };
+    std::vector<S> ts;
+    for (const T& x : all) {
+      if (x.w < w0 || x.w >= w1) continue;
+      const int wl = x.w - w0;
+      const bool out = (x.w == w1 - 1) && (q + 1 < npasses);
+      const int jlo = out ? 1 : x.jlo, jhi = out ? nBe : x.jhi;
+      ts.push_back({x.w, x.c, jlo + wl, jhi + wl, out ? 1 : 0});
+    }
+    std::stable_sort(ts.begin(), ts.end(), [](const S& a, const S& b) { return a.lo != b.lo ? a.lo < b.lo : a.hi < b.hi; });
+    const int ntiles = (int)ts.size();
+    std::vector<int> local((size_t)W * CN, -1);
+    for (int t = 0; t < ntiles; t++) {
+      local[(size_t)ts[t].w * CN + ts[t].c] = t;
+      index[(size_t)ts[t].w * CN + ts[t].c] = gid + t;
+    }
+    ps.gid_off = gid;
+    const int used = ((ntiles + 31) / 32) * 32;
+    gid += used;
+    for (int wp = 0; wp < threads / 32; wp++) {
+      int lo = 1 << 30, hi = -1;
+      for (int t = wp * 32; t < std::min(ntiles, wp * 32 + 32); t++) { lo = std::min(lo, ts[t].lo); hi = std::max(hi, ts[t].hi); }
+      if (hi >= lo) warp_steps += hi - lo + 1;
+      for (int t = wp * 32; t < wp * 32 + 32; t++) {
+        MrTileMp& e = tab[(size_t)q * threads + t];
+        e.warp_lo = lo; e.warp_hi = hi; e.out = 0; e.pad_ = 0;
+        if (t >= ntiles) { e.w = -1; e.c = -1; e.s_lo = 1 << 30; e.s_hi = -1; e.up_slot = nslots - 1; e.dg_slot = nslots - 1; continue; }
+        e.w = ts[t].w; e.c = ts[t].c; e.s_lo = ts[t].lo; e.s_hi = ts[t].hi; e.out = ts[t].out;
+        int up;
+        if (e.w > w0) up = local[(size_t)(e.w - 1) * CN + e.c];
+        else up = (e.w > 0 && have[(size_t)(e.w - 1) * CN + e.c] >= 0) ? -2 : -1;  // -2: carry
+        const int dg = (e.c > 0) ? local[(size_t)e.w * CN + e.c - 1] : -1;
+        e.up_slot = up >= 0 ? up : (up == -2 ? -1 : ((e.c == 0) ? nslots - 2 : nslots - 1));
+        e.dg_slot = dg >= 0 ? dg : nslots - 1;
+      }
+    }
+  }
+  const int T_total = gid;
+  const size_t smem = 16 * (size_t)(6 * nslots) +
+                      4 * (size_t)(MR_CRING * mr_ring_stride(wl_max * R) + 3 * ((nB * P.nb + 11) & ~3) + ((m * P.nb * 3 + 3) & ~3));
+  if (smem > prop.sharedMemPerBlockOptin) { p->why = "work space does not fit shared memory"; return; }
+  const int by_smem = (int)(prop.sharedMemPerMultiprocessor / (smem + 1024));
+  const int ctas_per_sm = std::max(1, std::min(by_smem, minb));
+  const int grid_cap = prop.multiProcessorCount * ctas_per_sm;
+  const size_t carry_pitch = (size_t)(nBe + 2) * CN;
+  mr_free_dp_tiled_mp(p);
+  auto fail = [&](const char* why) { mr_free_dp_tiled_mp(p); p->why = why; };
+  if (cudaMalloc(&p->d_passes, sizeof(MrPass) * passes.size()) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMemcpy(p->d_passes, passes.data(), sizeof(MrPass) * passes.size(), cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy");
+  if (cudaMalloc(&p->d_tiles, sizeof(MrTileMp) * tab.size()) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMemcpy(p->d_tiles, tab.data(), sizeof(MrTileMp) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy");
+  if (cudaMalloc(&p->d_tile_of, sizeof(int) * index.size()) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMemcpy(p->d_tile_of, index.data(), sizeof(int) * index.size(), cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy");
+  if (cudaMalloc(&p->d_carry, sizeof(float4) * carry_pitch * grid_cap) != cudaSuccess) { cudaGetLastError(); return fail("cudaMalloc (carry buffer)"); }
+  if (cudaMemset(p->d_carry, 0x7f, sizeof(float4) * carry_pitch * grid_cap) != cudaSuccess) return fail("cudaMemset");
+  p->W = W; p->CN = CN; p->nBe = nBe;
+  p->threads = threads; p->minb = minb; p->nslots = nslots; p->npasses = npasses; p->wl_max = wl_max;
+  p->smem = smem; p->grid_cap = grid_cap; p->carry_pitch = carry_pitch;
+  p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
+  p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = T_total;
+  p->layout.tile_of = p->d_tile_of;
+  p->tb_words = p->layout.words(nB);
+  p->lane_efficiency = (double)live_cells / ((double)warp_steps * 32 * K * R);
+  p->ok = true;
+  p->why = "";
+}
+
+template <int MAXT, int MINB>
+static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevParams& P, const float* A,
+                                          const float* B, const float* orient, const int* surv,
+                                          const int* surv_count, uint32_t* tb, float* cost, int count,
+                                          cudaStream_t stream) {
+  typedef void (*kern_t)(MrDevParams, TbTiled, int, int, int, const MrPass*, const MrTileMp*, const float*,
+                         const float*, const float*, const int*, const int*, float4*, size_t, uint32_t*, float*);
+  static const kern_t kerns[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true>,
+                                  k_dp_tiles_mp<4, 8, MAXT, MINB, true, false>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true>};
+  const kern_t kern = kerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
+  static size_t attr_set[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_set[dev & 63] < p.smem) {
+    for (int q = 0; q < 4; q++)
+      if (cudaFuncSetAttribute(kerns[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
+    attr_set[dev & 63] = p.smem;
+  }
+  const int grid = std::min(count, p.grid_cap);
+  kern<<<grid, p.threads, p.smem, stream>>>(P, p.layout, p.nslots, p.npasses, p.wl_max, p.d_passes, p.d_tiles, A, B,
+                                           orient, surv, surv_count, p.d_carry, p.carry_pitch, tb, cost);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+static inline int mr_launch_dp_tiled_mp(const MrTiledMpPlan& p, const MrDevParams& P, const float* A,
+                                        const float* B, const float* orient, const int* surv,
+                                        const int* surv_count, uint32_t* tb, float* cost, int count,
+                                        cudaStream_t stream) {
+#define MR_TRY(MAXT, MINB) \
+  if (p.threads == MAXT) return mr_launch_dp_tiles_mp_t<MAXT, MINB>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream)
+  MR_TRY(320, 2);
+  MR_TRY(352, 2);
+  MR_TRY(384, 2);
+  MR_TRY(512, 1);
+#undef MR_TRY
+  return mr_launch_dp_tiles_mp_t<1024, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+}

@@ -16,6 +16,10 @@ IDENT = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
 def make_search(A, B, settings, kernel=None):
     from minrms_b200 import SearchOrCuda
     s = SearchOrCuda(A, B, settings)
+    if kernel == 3:
+        # multi-pass tiled kernel with 64-thread CTAs: small problems still take several
+        # passes, so the carry buffer between passes is exercised
+        s.set_option("mp_threads", 64)
     if kernel is not None:
         s.set_option("dp_kernel", kernel)
     return s
@@ -32,7 +36,7 @@ def test_orientation_generation_matches_reference(cfg, request):
     assert np.array_equal(sha(og.orientations), g["orient_sha256"])
 
 
-@pytest.mark.parametrize("kernel", [1, 0])
+@pytest.mark.parametrize("kernel", [1, 0, 3])
 @pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2"])
 def test_single_orientation_values_match_reference(cfg, kernel, request):
     g = request.getfixturevalue(cfg)
@@ -43,7 +47,7 @@ def test_single_orientation_values_match_reference(cfg, kernel, request):
                           g["sample_ssd"][k], g["sample_T"][k], g["sample_pairs"][k], "o=%d" % o)
 
 
-@pytest.mark.parametrize("kernel", [1, 0])
+@pytest.mark.parametrize("kernel", [1, 0, 3])
 @pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2"])
 def test_full_search_and_refine_match_reference(cfg, kernel, request):
     """configs 1 and 2 end to end: orientation generation, FirstPass, Refine; the per-size
@@ -101,7 +105,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", [1, 0])
+@pytest.mark.parametrize("kernel", [1, 0, 3])
 @pytest.mark.parametrize("case", CASES)
 def test_synthetic_pairs_match_oracle(case, kernel):
     from minrms_b200 import OrientationGenerator
@@ -203,9 +207,39 @@ def test_error_paths():
         s.check_solutions()
 
 
+@pytest.mark.parametrize("shape", [(300, 280, 1), (233, 310, 40), (200, 200, 150)])
+def test_mid_size_pairs_match_oracle(shape):
+    """typical protein sizes (200-300 residues): more live tiles than one CTA holds, served
+    by the multi-pass tiled kernel at its production CTA size"""
+    from minrms_b200 import OrientationGenerator
+    m, nB, n_min = shape
+    rng = np.random.default_rng(7 * m + nB)
+    A = random_chain(rng, m)
+    B = related_chain(rng, A, nB, noise=1.2)
+    p = oc.make_params(n_min=n_min, m=m, nB=nB)
+    s = make_search(A, B, settings_from_params(p, 4))
+    og = OrientationGenerator(s)
+    ws = oc.Workspace(A, B, p)
+    pick = og.orientations[np.linspace(0, og.size() - 1, 6).astype(int)]
+    for T in pick[:2]:
+        ref = ws.eval(T)
+        res = s.eval_one(T)
+        assert_eval_equal(res, ref["n_last"], ref["cost"], ref["valid"], ref["ssd"], ref["T"], ref["pairs"])
+    best = ws.search(pick)
+    s.Search(pick)
+    t = s.best_table()
+    assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "search")
+    assert np.array_equal(t["o_id"], best["o_id"])
+    s.set_option("dp_kernel", 1)                          # general kernel: same table
+    s.reset_best()
+    s.Search(pick)
+    t1 = s.best_table()
+    assert_table_equal(t1["ssd"], t1["T"], t1["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "general")
+
+
 def test_config3_size_pair_matches_oracle():
-    """600 x 600 (BASELINE config 3 size): beyond the register-tiled kernel, served by the
-    general column-sweep kernel; single orientations and a small search against the oracle"""
+    """600 x 600 (BASELINE config 3 size): multi-pass tiled kernel; single orientations and
+    a small search against the oracle"""
     from minrms_b200 import OrientationGenerator
     rng = np.random.default_rng(3000)
     A = random_chain(rng, 600)
@@ -245,7 +279,7 @@ def test_config4_size_pair_matches_oracle():
         assert_eval_equal(res, ref["n_last"], ref["cost"], ref["valid"], ref["ssd"], ref["T"], ref["pairs"])
 
 
-@pytest.mark.parametrize("kernel", [1, 0])
+@pytest.mark.parametrize("kernel", [1, 0, 3])
 def test_exact_ties_identical_and_symmetric_structures(kernel):
     """many exactly equal costs: identical chains, an exact lattice, a palindromic chain --
     the reference's tie order (match < skip-i < skip-j on '<=') decides the alignment"""
