@@ -11,12 +11,18 @@
 // L2-resident) and read back, one column ahead, as the upper boundary of the first strip of
 // the next pass.  The buffer is updated in place: the reader of column j runs at step j-1,
 // the writer of column j at step j + (w1-1-w0), separated by at least one barrier.
-// Tiles that write the carry run over every column so that no entry is left over from an
-// earlier orientation.
+// (A 4-deep cp.async ring instead of the one-column register prefetch was measured 3-6 %
+// slower at 300..2000 residues: the carry latency is not what bounds the kernel.)
+// A reader takes carry values only inside its own column window (outside it substitutes the
+// boundary constants, like an exchange slot that was never written), and the window of a
+// writer is widened to cover its reader's, so every value read was written for this
+// orientation.
 //
 // Global tile ids (pass offset + thread) index the same traceback layout as the single-pass
 // kernel (TbTiled with T = tiles of all passes), so K5 (k_traceback_kabsch) is unchanged.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include "mr_dp_tiled.cuh"
 
 struct MrPass {
@@ -92,7 +98,8 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
       const int tb_first = has_tile ? me.s_lo + ((me.s_lo - wl) & 1) : 0x3fffffff;
       const int cost_step = (has_tile && w == W - 1) ? nB + wl : -1;
       const bool from_carry = has_tile && me.up_slot < 0;
-      const int out_lo = (has_tile && me.out) ? 1 + wl : 0x3fffffff;  // carry columns 1..nBe
+      const int out_lo = (has_tile && me.out) ? me.s_lo : 0x3fffffff;
+      const unsigned own_span = has_tile ? (unsigned)(me.s_hi - me.s_lo) : 0u;
       const uint32_t a_up = exch0 + (uint32_t)max(me.up_slot, 0) * 48u + 32u;
       const uint32_t a_dg = exch0 + (uint32_t)me.dg_slot * 48u;
       const uint32_t a_c = cr0 + (uint32_t)(wl * R) * 4u;
@@ -146,7 +153,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
         {
           float4 v = mr_lds128(a_up + rd_off);
           if (from_carry) {
-            v = gnext;
+            v = ((unsigned)(s - me.s_lo) <= own_span) ? gnext : make_float4(c == 0 ? 0.0f : INF, INF, INF, INF);
             gnext = __ldcg(cme + (size_t)min(s + 1, nBe + 1) * CN);
           }
           bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
@@ -181,7 +188,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
 #pragma unroll
         for (int k = 0; k < K; k++) bprev[k] = bin[k];
         // bottom row of the pass -> carry[column j = s - wl]
-        if ((unsigned)(s - out_lo) < (unsigned)nBe)
+        if ((unsigned)(s - out_lo) <= own_span)
           __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]));
         if (s == tb_next) {
           *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
@@ -297,10 +304,12 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
   std::vector<int> per_strip(W, 0);
   for (const T& x : all) per_strip[x.w]++;
   const int widest = *std::max_element(per_strip.begin(), per_strip.end());
-  int threads = 352, minb = 2;
-  if (widest > 352) { threads = 384; }
-  if (widest > 384) { threads = 512; minb = 1; }
-  if (widest > 512) { threads = 1024; }
+  // 512 threads, one CTA per SM (128 registers per thread: the tile code does not spill);
+  // measured on B200 against 320 x 2, 352 x 2, 640 and 768 at 300..2000 residues
+  int threads = 512, minb = 1;
+  if (widest > 512) threads = 640;
+  if (widest > 640) threads = 768;
+  if (widest > 768) threads = 1024;
   if (max_threads > 0 && widest <= max_threads) { threads = max_threads; minb = threads <= 384 ? 2 : 1; }
   if (widest > 1024) { p->why = "more than 1024 live tiles in one row strip"; return; }
   // passes: consecutive strips while the tiles fit one CTA
@@ -314,6 +323,17 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
     w0 = w1;
   }
   const int npasses = (int)passes.size();
+  // a writer (last strip of a pass) covers the window of its reader (first strip of the next
+  // pass, same chunk); bottom-up, so chains of one-strip passes are covered too
+  for (int q = npasses - 2; q >= 0; q--) {
+    const int wlast = passes[q].w0 + passes[q].nstrips - 1;
+    for (int c = 0; c < CN; c++) {
+      const int a = have[(size_t)wlast * CN + c], b = have[(size_t)(wlast + 1) * CN + c];
+      if (a < 0 || b < 0) continue;
+      all[a].jlo = std::min(all[a].jlo, all[b].jlo);
+      all[a].jhi = std::max(all[a].jhi, all[b].jhi);
+    }
+  }
   const int nslots = threads + 2;
   std::vector<MrTileMp> tab((size_t)npasses * threads);
   std::vector<int> index((size_t)W * CN, 0);
@@ -328,9 +348,8 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
     for (const T& x : all) {
       if (x.w < w0 || x.w >= w1) continue;
       const int wl = x.w - w0;
-      const bool out = (x.w == w1 - 1) && (q + 1 < npasses);
-      const int jlo = out ? 1 : x.jlo, jhi = out ? nBe : x.jhi;
-      ts.push_back({x.w, x.c, jlo + wl, jhi + wl, out ? 1 : 0});
+      const bool out = (x.w == w1 - 1) && (q + 1 < npasses) && have[(size_t)(x.w + 1) * CN + x.c] >= 0;
+      ts.push_back({x.w, x.c, x.jlo + wl, x.jhi + wl, out ? 1 : 0});
     }
     std::stable_sort(ts.begin(), ts.end(), [](const S& a, const S& b) { return a.lo != b.lo ? a.lo < b.lo : a.hi < b.hi; });
     const int ntiles = (int)ts.size();
@@ -388,6 +407,13 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
   p->lane_efficiency = (double)live_cells / ((double)warp_steps * 32 * K * R);
   p->ok = true;
   p->why = "";
+  if (getenv("MR_DEBUG_PLAN")) {
+    fprintf(stderr, "[mr] multi-pass plan: %d x %d, layers %d: %d threads x %d CTAs/SM, %d passes (", m, nB, P.n_max,
+            threads, ctas_per_sm, npasses);
+    for (int q = 0; q < npasses; q++) fprintf(stderr, "%s%d", q ? "," : "", passes[q].nstrips);
+    fprintf(stderr, " strips), %d tiles, lane efficiency %.3f, smem %zu B, carry %.1f MB/CTA, traceback %.1f MB/orientation\n",
+            T_total, p->lane_efficiency, smem, carry_pitch * 16.0 / 1048576.0, p->tb_words * 4.0 / 1048576.0);
+  }
 }
 
 template <int MAXT, int MINB>
@@ -424,6 +450,8 @@ static inline int mr_launch_dp_tiled_mp(const MrTiledMpPlan& p, const MrDevParam
   MR_TRY(352, 2);
   MR_TRY(384, 2);
   MR_TRY(512, 1);
+  MR_TRY(640, 1);
+  MR_TRY(768, 1);
 #undef MR_TRY
   return mr_launch_dp_tiles_mp_t<1024, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
 }
