@@ -68,7 +68,8 @@ struct mr_ctx {
   long long id_offset = 0;
   bool id_offset_set = false;
   int64_t opt_dp_kernel = 0;    // 0 auto, 1 general, 2 tiled (single pass), 3 tiled (multi-pass)
-  int64_t opt_budget_mb = 32768;
+  int64_t opt_budget_mb = 32768;  // chunk work space; raised automatically (see ensure_chunk) unless set by the caller
+  bool budget_is_default = true;
   int64_t opt_chunk = 0;
   int64_t opt_nw_general = 0;   // force the thread-per-orientation NW filter
   int64_t opt_dp_only = 0;      // experiments: skip traceback/select (results invalid)
@@ -179,6 +180,12 @@ int dp_path(const mr_ctx* c) {
 bool use_tiled(const mr_ctx* c) { return dp_path(c) != 0; }
 const TbTiled& tiled_layout(const mr_ctx* c) { return dp_path(c) == 2 ? c->tiled_mp.layout : c->tiled.layout; }
 
+// bytes per orientation of the chunk buffers currently allocated
+size_t per_o_held(const mr_ctx* c) {
+  const int per = std::max(1, c->hp.n_max - std::max(2, c->hp.n_min) + 1);
+  return c->tb_words * 4 + (size_t)c->NP * 4 * 2 + (size_t)per * (size_t)c->N * sizeof(short2) + 64;
+}
+
 // (re)allocate the per-chunk work space for chunks of up to `want` orientations
 int ensure_chunk(mr_ctx* c, int64_t want) {
   const size_t words_c = c->Lc.words(c->nB);
@@ -188,8 +195,22 @@ int ensure_chunk(mr_ctx* c, int64_t want) {
   const int per = std::max(1, c->hp.n_max - std::max(2, c->hp.n_min) + 1);
   // bytes per orientation in a chunk
   const size_t per_o = words * 4 + (size_t)c->NP * 4 * 2 + (size_t)per * per_thread_scr + 64;
-  int64_t cap = (int64_t)((size_t)c->opt_budget_mb * 1024 * 1024 / per_o);
+  size_t budget = (size_t)c->opt_budget_mb * 1024 * 1024;
+  // one wave of the DP kernel (one orientation per resident CTA) should fit a chunk: long
+  // chains need hundreds of MB of traceback words per orientation, and a chunk smaller than
+  // the wave leaves SMs idle.  Use up to 80 % of the free HBM for that.
+  const int64_t wave = path == 2 ? c->tiled_mp.grid_cap : path == 1 ? c->tiled.grid_cap : c->dp_grid_cap;
+  if (c->budget_is_default && budget < per_o * (size_t)wave && want > (int64_t)(budget / per_o)) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      // memory held by the current chunk buffers is returned before the new ones are made
+      const size_t held = (size_t)c->chunk_cap * per_o_held(c);
+      budget = std::max(budget, std::min(per_o * (size_t)wave, (size_t)(0.8 * (double)(free_b + held))));
+    }
+  }
+  int64_t cap = (int64_t)(budget / per_o);
   cap = std::max<int64_t>(1, std::min<int64_t>(cap, 1 << 18));
+  if (cap > wave && want > cap) cap -= cap % wave;  // several chunks: whole waves
   if (c->opt_chunk > 0) cap = std::min<int64_t>(cap, c->opt_chunk);
   int64_t need = std::min<int64_t>(want, cap);
   if (need <= c->chunk_cap && words == c->tb_words) return 0;
@@ -545,7 +566,7 @@ int mr_best_init(const mr_ctx* c, mr_best* best) {
 int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   if (!c || !name) return 1;
   if (!strcmp(name, "dp_kernel")) c->opt_dp_kernel = value;
-  else if (!strcmp(name, "budget_mb")) c->opt_budget_mb = std::max<int64_t>(64, value);
+  else if (!strcmp(name, "budget_mb")) { c->opt_budget_mb = std::max<int64_t>(64, value); c->budget_is_default = false; }
   else if (!strcmp(name, "chunk")) c->opt_chunk = value;
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
   else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);

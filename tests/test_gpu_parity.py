@@ -261,8 +261,9 @@ def test_config3_size_pair_matches_oracle():
 
 
 def test_config4_size_pair_matches_oracle():
-    """2000 x 1500 with -of 8.0,0.33 (BASELINE config 4 size: 1500 layers, 1.69 G cells and a
-    1.1 GB traceback table per orientation): one orientation end to end against the oracle"""
+    """2000 x 1500 with -of 8.0,0.33 (BASELINE config 4 size: 1500 layers, 1.69 G cells per
+    orientation, 160 passes of the multi-pass tiled kernel, 0.7 GB of traceback words): one
+    orientation end to end against the oracle"""
     rng = np.random.default_rng(4000)
     A = random_chain(rng, 2000)
     B, idx = related_chain(rng, A, 1500, noise=1.0, return_idx=True)
