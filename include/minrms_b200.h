@@ -140,6 +140,8 @@ typedef struct mr_stats {
   double  nw_kernel_ms;
   double  tb_kernel_ms;      /* traceback + Kabsch kernel */
   int64_t h2d_bytes, d2h_bytes;
+  int64_t refine_batches;         /* batched launches made by mr_refine */
+  int64_t refine_evals_launched;  /* evaluations in those batches (>= evaluations consumed) */
 } mr_stats;
 int mr_get_stats(mr_ctx *ctx, mr_stats *out);
 int mr_reset_stats(mr_ctx *ctx);
@@ -149,7 +151,10 @@ int mr_reset_stats(mr_ctx *ctx);
 int mr_event_record(mr_ctx *ctx, int32_t slot);
 int mr_event_elapsed_ms(mr_ctx *ctx, int32_t slot_a, int32_t slot_b, float *ms);
 
-/* Tuning knobs (by name), e.g. "dp_kernel" = 0 auto / 1 general / 2 tiled. */
+/* Tuning knobs (by name): "dp_kernel" = 0 auto / 1 general / 2 tiled single-pass /
+ * 3 tiled multi-pass; "budget_mb", "chunk" (work space per chunk of orientations);
+ * "refine_batch" = 0 all flagged sizes per Refine batch / k at most k (1 = sequential);
+ * "nw_kernel" = 1 thread-per-orientation filter; "mp_threads" (tests). */
 int mr_set_option(mr_ctx *ctx, const char *name, int64_t value);
 
 /* number of Dyn3d cells per orientation for all layers 1..n_max */

@@ -24,7 +24,8 @@ class MrStats(C.Structure):
                 ("orientations_dp", C.c_int64), ("dp_cells", C.c_int64), ("nw_cells", C.c_int64),
                 ("dp_kernel_ms", C.c_double), ("dp_kernel_launches", C.c_int64),
                 ("nw_kernel_ms", C.c_double), ("tb_kernel_ms", C.c_double),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("refine_batches", C.c_int64), ("refine_evals_launched", C.c_int64)]
 
 
 EXPORTS = ["mr_create", "mr_destroy", "mr_last_error", "mr_best_init", "mr_search",

@@ -62,7 +62,16 @@ struct mr_ctx {
   int2* d_items = nullptr;
   float* d_Tout = nullptr;      // [max(R,NP)*12]
   short* d_pairs_out = nullptr; // [max(R,NP)*2N]
-  short2* d_pairs_in = nullptr; // [N]
+  // Refine batches (allocated on first use)
+  int ref_kcap = 0;
+  short2* d_ref_pairs_in = nullptr;  // [kcap][N]
+  int* d_ref_n = nullptr;            // [kcap]
+  float* d_ref_orient = nullptr;     // [kcap][12]
+  float* d_ref_T = nullptr;          // [kcap][NP][12]
+  short* d_ref_pairs = nullptr;      // [kcap][NP][2N]
+  char* h_ref = nullptr;             // pinned staging
+  size_t ref_off_n = 0, ref_off_ssd = 0, ref_off_valid = 0, ref_off_nlast = 0, ref_off_T = 0, ref_off_pairs = 0;
+  int64_t opt_refine_batch = 0;      // 0: all flagged sizes per batch; k > 0: at most k (1 = sequential)
   int* h_pinned = nullptr;      // surv counts per chunk
   int h_pinned_cap = 0;
   long long id_offset = 0;
@@ -269,7 +278,10 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count) {
 }
 
 template <bool EMIT>
-int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* items, int n_items) {
+int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* items, int n_items,
+              float* d_T = nullptr, short* d_pairs = nullptr) {
+  if (!d_T) d_T = c->d_Tout;
+  if (!d_pairs) d_pairs = c->d_pairs_out;
   const int n_lo = std::max(2, c->hp.n_min);
   const int per = c->hp.n_max - n_lo + 1;
   const int64_t threads = items ? n_items : (int64_t)count * std::max(per, 0);
@@ -282,11 +294,11 @@ int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* ite
   if (use_tiled(c))
     k_traceback_kabsch<TbTiled, EMIT><<<grid, 128, 4 * tiled_layout(c).table_ints() + coords, c->stream>>>(
         c->P, tiled_layout(c), c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb,
-        c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, c->d_Tout, c->d_pairs_out);
+        c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs);
   else
     k_traceback_kabsch<TbColumns, EMIT><<<grid, 128, coords, c->stream>>>(
         c->P, c->Lc, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb, c->d_cost,
-        items, n_items, n_lo, c->d_scratch, c->d_ssd, c->d_Tout, c->d_pairs_out);
+        items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs);
   CU(c, cudaGetLastError());
   CU(c, cudaEventRecord(ev->b, c->stream));
   c->st.kernel_launches++;
@@ -530,7 +542,6 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   if (cudaMalloc(&c->d_items, sizeof(int2) * (size_t)RR) != cudaSuccess) return bail("malloc");
   if (cudaMalloc(&c->d_Tout, 48 * (size_t)slots) != cudaSuccess) return bail("malloc");
   if (cudaMalloc(&c->d_pairs_out, sizeof(short) * 2 * (size_t)N * slots) != cudaSuccess) return bail("malloc");
-  if (cudaMalloc(&c->d_pairs_in, sizeof(short2) * (size_t)N) != cudaSuccess) return bail("malloc");
   c->h_pinned_cap = 4096;
   if (cudaMallocHost(&c->h_pinned, 4 * (size_t)c->h_pinned_cap) != cudaSuccess) return bail("pinned");
   if (reset_keys(c)) { g_create_error = c->err; mr_destroy(c); return 1; }
@@ -549,7 +560,8 @@ void mr_destroy(mr_ctx* c) {
   cudaFree(c->d_nlast); cudaFree(c->d_valid); cudaFree(c->d_rowcost); cudaFree(c->d_rowcnt);
   cudaFree(c->d_scratch); cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w);
   cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
-  cudaFree(c->d_pairs_in);
+  cudaFree(c->d_ref_pairs_in); cudaFree(c->d_ref_n); cudaFree(c->d_ref_orient); cudaFree(c->d_ref_T); cudaFree(c->d_ref_pairs);
+  if (c->h_ref) cudaFreeHost(c->h_ref);
   mr_free_dp_tiled(&c->tiled);
   mr_free_dp_tiled_mp(&c->tiled_mp);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -570,6 +582,7 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "chunk")) c->opt_chunk = value;
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
   else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);
+  else if (!strcmp(name, "refine_batch")) c->opt_refine_batch = std::max<int64_t>(0, value);
   else if (!strcmp(name, "mp_threads")) {
     if (value != 0 && (value < 32 || value > 1024 || value % 32)) MR_FAIL(c, "mr_set_option: mp_threads must be a multiple of 32 in [32, 1024]");
     c->opt_mp_threads = value;
@@ -744,40 +757,140 @@ static int find_median(const std::vector<char>& in_set, int n_min, int n_max) {
   return n;
 }
 
+// ---- Refine (SearchOrDyn3d::Refine, search_or_dyn3d.cc:2318-2638) -------------------------
+// The reference loop is sequential: pick the median flagged size n, superimpose its current
+// alignment, run the whole DP at that orientation, take every strictly better size, flag the
+// sizes that changed.  One evaluation depends only on the alignment it starts from, so the
+// evaluations of ALL currently flagged sizes are launched as one batch (one orientation per
+// CTA: a batch costs about the latency of a single evaluation) and the loop is replayed on
+// the host in the reference's order.  A batch result is used only while the alignment it was
+// computed from is still the stored one; otherwise a new batch is launched.  Same
+// evaluations, same order, same comparisons as the sequential loop.
+static int refine_alloc(mr_ctx* c) {
+  if (c->ref_kcap > 0) return 0;
+  const size_t N = (size_t)c->N, NP = (size_t)c->NP;
+  const size_t per_item = NP * (48 + 4 * N);
+  int kcap = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->R, ((size_t)1 << 30) / per_item));
+  CU(c, cudaMalloc(&c->d_ref_pairs_in, sizeof(short2) * N * kcap));
+  CU(c, cudaMalloc(&c->d_ref_n, sizeof(int) * kcap));
+  CU(c, cudaMalloc(&c->d_ref_orient, 48 * (size_t)kcap));
+  CU(c, cudaMalloc(&c->d_ref_T, 48 * NP * kcap));
+  CU(c, cudaMalloc(&c->d_ref_pairs, 4 * N * NP * kcap));
+  // pinned staging: pairs_in | n | ssd | valid | n_last | T (one item) | pairs (one item)
+  c->ref_off_n = sizeof(short2) * N * kcap;
+  c->ref_off_ssd = c->ref_off_n + sizeof(int) * kcap;
+  c->ref_off_valid = c->ref_off_ssd + 4 * NP * kcap;
+  c->ref_off_nlast = (c->ref_off_valid + NP * kcap + 15) & ~(size_t)15;
+  c->ref_off_T = c->ref_off_nlast + sizeof(int) * kcap;
+  c->ref_off_pairs = (c->ref_off_T + 48 * NP + 15) & ~(size_t)15;
+  CU(c, cudaMallocHost(&c->h_ref, c->ref_off_pairs + 4 * N * NP));
+  c->ref_kcap = kcap;
+  return 0;
+}
+
+// evaluate the stored alignments of the sizes n_min + r, r in `rs`, as one batch
+static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* best) {
+  const int N = c->N, NP = c->NP, n_min = c->hp.n_min, k = (int)rs.size();
+  short2* hp = reinterpret_cast<short2*>(c->h_ref);
+  int* hn = reinterpret_cast<int*>(c->h_ref + c->ref_off_n);
+  for (int b = 0; b < k; b++) {
+    const int n = n_min + rs[b];
+    hn[b] = n;
+    memcpy(hp + (size_t)b * N, best->pairs + (size_t)rs[b] * 2 * N, sizeof(short2) * (size_t)n);
+  }
+  CU(c, cudaMemcpyAsync(c->d_ref_pairs_in, hp, sizeof(short2) * (size_t)N * k, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_ref_n, hn, sizeof(int) * (size_t)k, cudaMemcpyHostToDevice, c->stream));
+  c->st.h2d_bytes += (int64_t)k * (4 * N + 4);
+  // orientation that optimally superimposes each alignment (:2401-2407)
+  k_superimpose_pairs_batch<<<k, 32, 0, c->stream>>>(c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N, c->d_ref_orient);
+  CU(c, cudaGetLastError());
+  c->st.kernel_launches++;
+  if (launch_filter(c, c->d_ref_orient, k, false)) return 1;
+  CU(c, cudaMemsetAsync(c->d_valid, 0, (size_t)NP * k, c->stream));
+  CU(c, cudaMemsetAsync(c->d_cost, 0, (size_t)NP * 4 * k, c->stream));
+  CU(c, cudaMemsetAsync(c->d_ssd, 0, (size_t)NP * 4 * k, c->stream));
+  CU(c, cudaMemsetAsync(c->d_nlast, 0, 4 * (size_t)k, c->stream));
+  if (launch_dp(c, c->d_ref_orient, k)) return 1;
+  if (launch_tb<true>(c, c->d_ref_orient, k, nullptr, 0, c->d_ref_T, c->d_ref_pairs)) return 1;
+  k_select<<<(k + 31) / 32, 32, 0, c->stream>>>(c->P, NP, c->d_surv, c->d_surv_count, c->d_cost, c->d_ssd, 0ll,
+                                              nullptr, c->d_valid, c->d_nlast);
+  CU(c, cudaGetLastError());
+  c->st.kernel_launches++;
+  CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_ssd, c->d_ssd, 4 * (size_t)NP * k, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_valid, c->d_valid, (size_t)NP * k, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_nlast, c->d_nlast, 4 * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->st.d2h_bytes += (int64_t)k * (5 * NP + 4);
+  c->events_used = 0;  // Refine evaluations are not part of the search throughput stats
+  c->st.refine_batches++;
+  c->st.refine_evals_launched += k;
+  return 0;
+}
+
 int mr_refine(mr_ctx* c, mr_best* best, int32_t max_iters, int32_t* n_evals) {
   if (!c || !best) return 1;
   CU(c, cudaSetDevice(c->device));
-  const int N = c->N, n_min = c->hp.n_min, n_max = c->hp.n_max, R = c->R;
+  const int N = c->N, NP = c->NP, n_min = c->hp.n_min, n_max = c->hp.n_max, R = c->R;
   std::vector<char> need((size_t)R);
   for (int r = 0; r < R; r++) need[r] = best->ssd[r] < MR_UPPER_BOUND;  // :2348-2358
-  std::vector<float> ssd((size_t)N), T((size_t)N * 12);
-  std::vector<uint8_t> valid((size_t)N);
-  std::vector<int16_t> pairs((size_t)N * 2 * N), old((size_t)2 * N);
+  if (refine_alloc(c)) return 1;
+  std::vector<int> item_of((size_t)R, -1);  // batch item evaluated from the CURRENT alignment of a size
+  std::vector<int> rs;
+  std::vector<int16_t> old((size_t)2 * N);
+  const float* h_ssd = reinterpret_cast<const float*>(c->h_ref + c->ref_off_ssd);
+  const uint8_t* h_valid = reinterpret_cast<const uint8_t*>(c->h_ref + c->ref_off_valid);
+  const int* h_nlast = reinterpret_cast<const int*>(c->h_ref + c->ref_off_nlast);
+  const float* h_T = reinterpret_cast<const float*>(c->h_ref + c->ref_off_T);
+  const int16_t* h_pairs = reinterpret_cast<const int16_t*>(c->h_ref + c->ref_off_pairs);
   int evals = 0;
   for (int it = 1; it <= max_iters || max_iters < 0; it++) {
     const int n = find_median(need, n_min, n_max);
     if (n == n_min - 1) break;
-    int16_t* cur = best->pairs + (size_t)(n - n_min) * 2 * N;
-    // orientation that optimally superimposes the current size-n alignment (:2401-2407)
-    CU(c, cudaMemcpyAsync(c->d_pairs_in, cur, sizeof(short2) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    c->st.h2d_bytes += 4 * n;
-    k_superimpose_pairs<<<1, 32, 0, c->stream>>>(c->P, c->dA, c->dB, c->d_pairs_in, n, c->d_orient_w);
-    CU(c, cudaGetLastError());
-    c->st.kernel_launches++;
-    memcpy(old.data(), cur, sizeof(int16_t) * 2 * (size_t)n);
-    int32_t nl = 0;
-    if (eval_w0(c, false, &nl, nullptr, nullptr, valid.data(), ssd.data(), T.data(), pairs.data())) return 1;
+    const int rn = n - n_min;
+    if (item_of[rn] < 0) {
+      // new batch: every flagged size (the window of flagged sizes around n if they do not fit)
+      if (ensure_chunk(c, std::min(R, c->ref_kcap))) return 1;
+      int kmax = std::min(c->ref_kcap, c->chunk_cap);
+      if (c->opt_refine_batch > 0) kmax = std::min<int>(kmax, (int)c->opt_refine_batch);
+      std::vector<int> flagged;
+      int pos = 0;
+      for (int r = 0; r < R; r++)
+        if (need[r]) { if (r == rn) pos = (int)flagged.size(); flagged.push_back(r); }
+      int lo = std::max(0, pos - kmax / 2);
+      lo = std::min(lo, std::max(0, (int)flagged.size() - kmax));
+      rs.assign(flagged.begin() + lo, flagged.begin() + std::min<int>((int)flagged.size(), lo + kmax));
+      if (refine_launch(c, rs, best)) return 1;
+      std::fill(item_of.begin(), item_of.end(), -1);
+      for (int b = 0; b < (int)rs.size(); b++) item_of[rs[b]] = b;
+    }
+    const int b = item_of[rn];
+    item_of[rn] = -1;
     evals++;
+    int16_t* cur = best->pairs + (size_t)rn * 2 * N;
+    memcpy(old.data(), cur, sizeof(int16_t) * 2 * (size_t)n);
+    const int nl = h_nlast[b];
+    bool fetched = false;
     for (int m2 = std::max(2, n_min); m2 <= nl; m2++) {
-      if (!valid[m2 - 1] || !(ssd[m2 - 1] < best->ssd[m2 - n_min])) continue;  // strict <, :2515
+      const size_t slot = (size_t)b * NP + (m2 - 1);
+      if (m2 > n_max || !h_valid[slot] || !(h_ssd[slot] < best->ssd[m2 - n_min])) continue;  // strict <, :2515
+      if (!fetched) {  // transforms and alignments of this item, once
+        CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_T, c->d_ref_T + 12 * (size_t)NP * b, 48 * (size_t)NP,
+                              cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_pairs, c->d_ref_pairs + 2 * (size_t)N * NP * b,
+                              4 * (size_t)N * NP, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        c->st.d2h_bytes += (int64_t)NP * (48 + 4 * N);
+        fetched = true;
+      }
       const int r = m2 - n_min;
-      best->ssd[r] = ssd[m2 - 1];
-      memcpy(best->T + 12 * r, &T[12 * (size_t)(m2 - 1)], 48);
-      memcpy(best->pairs + (size_t)r * 2 * N, &pairs[(size_t)(m2 - 1) * 2 * N], sizeof(int16_t) * 2 * (size_t)m2);
+      best->ssd[r] = h_ssd[slot];
+      memcpy(best->T + 12 * r, h_T + 12 * (size_t)(m2 - 1), 48);
+      memcpy(best->pairs + (size_t)r * 2 * N, h_pairs + (size_t)(m2 - 1) * 2 * N, sizeof(int16_t) * 2 * (size_t)m2);
       if (best->o_id) best->o_id[r] = -2;
       if (m2 != n) need[r] = 1;  // :2546
+      item_of[r] = -1;           // its alignment changed: a result computed from the old one is void
     }
-    need[n - n_min] = memcmp(old.data(), cur, sizeof(int16_t) * 2 * (size_t)n) != 0;  // :2619-2629
+    need[rn] = memcmp(old.data(), cur, sizeof(int16_t) * 2 * (size_t)n) != 0;  // :2619-2629
   }
   if (n_evals) *n_evals = evals;
   return 0;

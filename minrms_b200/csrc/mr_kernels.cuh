@@ -439,23 +439,25 @@ __global__ void k_gather_orient(const float* __restrict__ orient, const int* __r
   if (t < n * 12) out[t] = orient[12 * (size_t)idx[t / 12] + t % 12];
 }
 
-// Refine: orientation that optimally superimposes one alignment
-// (PairwiseAlignment::CalcMinRMSD, pair_alignment.cc:714-820); single thread.
-__global__ void k_superimpose_pairs(MrDevParams P, const float* __restrict__ A,
-                                    const float* __restrict__ B, const short2* __restrict__ pairs,
-                                    int n, float* __restrict__ T_out) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  const int nb = P.nb;
+// Refine: orientation that optimally superimposes an alignment
+// (PairwiseAlignment::CalcMinRMSD, pair_alignment.cc:714-820), one single-threaded problem per
+// block: block b superimposes the n[b] pairs at pairs[b * N ...]
+__global__ void k_superimpose_pairs_batch(MrDevParams P, const float* __restrict__ A,
+                                          const float* __restrict__ B, const short2* __restrict__ pairs,
+                                          const int* __restrict__ n_of, int N, float* __restrict__ T_out) {
+  if (threadIdx.x != 0) return;
+  const int nb = P.nb, b = blockIdx.x, n = n_of[b];
+  const short2* mine = pairs + (size_t)b * N;
   float T[12];
   mr_superimpose(n * nb, [&](int a, float* pf, float* pm) {
     const int k = a / nb, q = a - k * nb;
-    const short2 pr = pairs[k];
+    const short2 pr = mine[k];
     const float* f = A + 3 * ((size_t)pr.x * nb + q);
     const float* mv = B + 3 * ((size_t)pr.y * nb + q);
     pf[0] = f[0]; pf[1] = f[1]; pf[2] = f[2];
     pm[0] = mv[0]; pm[1] = mv[1]; pm[2] = mv[2];
   }, T);
-  for (int k = 0; k < 12; k++) T_out[k] = T[k];
+  for (int k = 0; k < 12; k++) T_out[12 * (size_t)b + k] = T[k];
 }
 
 // ---------------------------------------------------------------------------

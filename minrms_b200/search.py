@@ -151,11 +151,13 @@ class SearchOrCuda:
         if not np.any(self.aSumSqdDists[:self.R] < UPPER_BOUND):
             raise MinrmsError("Error: No solutions were found satisfying your criteria.")
 
-    def Refine(self):
-        """SearchOr::Refine (search_or_dyn3d.cc:2261-2658); returns #evaluations."""
+    def Refine(self, max_iters=None):
+        """SearchOr::Refine (search_or_dyn3d.cc:2261-2658); returns #evaluations.
+        max_iters defaults to settings.refine_max_iters (-1: until nothing changes)."""
         n = C.c_int32(0)
-        self._check(self.lib.mr_refine(self.ctx, C.byref(self._best),
-                                       self.settings.refine_max_iters, C.byref(n)))
+        if max_iters is None:
+            max_iters = self.settings.refine_max_iters
+        self._check(self.lib.mr_refine(self.ctx, C.byref(self._best), max_iters, C.byref(n)))
         return n.value
 
     # -- device-resident variant (kernel timing, multi-GPU reduction) -----------

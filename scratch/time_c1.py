@@ -11,4 +11,4 @@ for cfg in ('c1','c2'):
         t2=time.perf_counter(); s.Search(og); t3=time.perf_counter()
         st=s.stats()
         t4=time.perf_counter(); ev=s.Refine(); t5=time.perf_counter()
-    print(cfg,'orient gen %.1f ms; search %.2f ms (nw %.2f dp %.2f tb %.2f) orientations %d dp %d; refine %.1f ms (%d evals)'%((t1-t0)*1e3,(t3-t2)*1e3,st['nw_kernel_ms'],st['dp_kernel_ms'],st['tb_kernel_ms'],st['orientations'],st['orientations_dp'],(t5-t4)*1e3,ev))
+    print(cfg,'orient gen %.1f ms; search %.2f ms (nw %.2f dp %.2f tb %.2f) orientations %d dp %d; refine %.1f ms (%d evals, %d batches, %d launched)'%((t1-t0)*1e3,(t3-t2)*1e3,st['nw_kernel_ms'],st['dp_kernel_ms'],st['tb_kernel_ms'],st['orientations'],st['orientations_dp'],(t5-t4)*1e3,ev,s.stats()['refine_batches'],s.stats()['refine_evals_launched']))

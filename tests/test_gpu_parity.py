@@ -75,6 +75,36 @@ def test_full_search_and_refine_match_reference(cfg, kernel, request):
     assert np.max(np.abs(rg - rf)[rf >= 0.01]) < 1.5e-4
 
 
+@pytest.mark.parametrize("batch", [0, 1, 7])
+def test_refine_batches_replay_the_sequential_loop(batch, golden_c1):
+    """Refine launches the evaluations of all flagged sizes as one batch and replays the
+    reference's sequential loop on the host: whatever the batch size (1 = one evaluation per
+    launch, like the reference), the table and the number of evaluations consumed equal the
+    oracle's sequential Refine -- also when the loop is cut short by max_iters"""
+    from minrms_b200 import OrientationGenerator
+    g = golden_c1
+    n_min = int(g["n_min"])
+    s = make_search(g["A"], g["B"], settings_from_golden(g))
+    s.set_option("refine_batch", batch)
+    og = OrientationGenerator(s)
+    ws = oc.Workspace(g["A"], g["B"], params_from_golden(g))
+    for max_iters in (5, -1):
+        s.reset_best()
+        s.Search(og)
+        t = s.best_table()
+        best = dict(ssd=t["ssd"].copy(), T=t["T"].copy(), pairs=t["pairs"].copy(), o_id=t["o_id"].copy())
+        ev_ref = ws.refine(best, max_iters)
+        s.stats(reset=True)
+        ev = s.Refine(max_iters)
+        t = s.best_table()
+        assert ev == ev_ref
+        assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "refine")
+        st = s.stats()
+        assert st["refine_batches"] <= ev and st["refine_evals_launched"] >= ev
+        if batch == 1:
+            assert st["refine_batches"] == ev == st["refine_evals_launched"]
+
+
 def test_split_ranges_merge_to_sequential_result(golden_c1):
     """Search(og, start, stop) over disjoint ranges in arbitrary order == one pass"""
     from minrms_b200 import OrientationGenerator
