@@ -323,6 +323,18 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
         case 5: MR_NW(5); break; case 6: MR_NW(6); break; case 7: MR_NW(7); break; default: MR_NW(8); break;
       }
 #undef MR_NW
+    } else if (c->hp.nb == 1 && c->nB <= 8192 && !c->opt_nw_general) {
+      // CTA per orientation: warps split the columns (256 per warp at most)
+      const int nw = (c->nB + 255) / 256, cp = (c->nB + 32 * nw - 1) / (32 * nw);
+      const size_t sm = 4 * (size_t)((3 * c->m + 3) & ~3) + 8 * 128 * (size_t)(nw - 1);
+      const int grid = std::min(count, c->prop.multiProcessorCount * 16);
+      typedef void (*nwk_t)(MrDevParams, const float*, const float*, const float*, int, int*, int*, int*);
+      static const nwk_t ks[2][4] = {{k_nw_filter_cta<5, 256>, k_nw_filter_cta<6, 256>, k_nw_filter_cta<7, 256>, k_nw_filter_cta<8, 256>},
+                                     {k_nw_filter_cta<5, 1024>, k_nw_filter_cta<6, 1024>, k_nw_filter_cta<7, 1024>, k_nw_filter_cta<8, 1024>}};
+      const nwk_t k = ks[nw > 8 ? 1 : 0][std::max(cp, 5) - 5];
+      if (sm > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+        MR_FAIL(c, "NW filter: shared memory attribute failed");
+      k<<<grid, 32 * nw, sm, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, c->d_nw, c->d_surv, c->d_surv_count);
     } else {
       const int grid = (count + 127) / 128;
       k_nw_filter<<<grid, 128, 0, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, c->d_rowcost,

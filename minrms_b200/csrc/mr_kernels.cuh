@@ -243,6 +243,102 @@ k_nw_filter_warp(MrDevParams P, const float* __restrict__ A, const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------
+// K1+K2, CTA-per-orientation variant for long chains (nB > 256): the warps of the CTA split
+// the columns (warp v owns columns 32*CPL*v+1 ..), each warp runs the register wavefront of
+// k_nw_filter_warp, and the last lane of warp v-1 hands A(i, last column) and its match
+// count to lane 0 of warp v through a 128-row ring in shared memory.  Time is cut into
+// blocks of 32 steps with one __syncthreads per block; warp v runs two blocks behind warp
+// v-1 (row i leaves warp v-1 at its step i+31 and enters warp v at step i), so every value
+// is written at least one barrier before it is read and read before its slot is reused.
+// ---------------------------------------------------------------------------
+template <int CPL, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_nw_filter_cta(MrDevParams P, const float* __restrict__ A, const float* __restrict__ B,
+                const float* __restrict__ orient, int count, int* __restrict__ nw_matches,
+                int* __restrict__ surv, int* __restrict__ surv_count) {
+  extern __shared__ float nw_sA[];  // m*3 floats, then the rings
+  const int m = P.m, nB = P.nB, w0 = P.w0, w1 = P.w1;
+  float2* ring = reinterpret_cast<float2*>(nw_sA + ((m * 3 + 3) & ~3));  // [warps-1][128] {cost, count}
+  for (int k = threadIdx.x; k < m * 3; k += blockDim.x) nw_sA[k] = A[k];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float G = P.nw_gap, cutoff = P.nw_cutoff;
+  const int nblk_local = (m + 31 + 31) / 32;
+  const int nblk = nblk_local + 2 * (nwarps - 1);
+  const int j0 = (warp * 32 + lane) * CPL;  // my columns are j0+1 .. j0+CPL
+  for (int o = blockIdx.x; o < count; o += gridDim.x) {
+    __syncthreads();
+    float T[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) T[k] = orient[12 * (size_t)o + k];
+    float bx[CPL], by[CPL], bz[CPL], up[CPL];
+    int upc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      const int j = j0 + 1 + c;
+      bx[c] = by[c] = bz[c] = 0.0f;
+      if (j <= nB) mr_xform(T, B[3 * (j - 1)], B[3 * (j - 1) + 1], B[3 * (j - 1) + 2], bx[c], by[c], bz[c]);
+      up[c] = (float)j * G;  // row 0
+      upc[c] = 0;
+    }
+    float last = 0.0f, diag_in = (float)j0 * G;
+    int lastc = 0, diag_inc = 0;
+    int result = 0;
+    for (int g = 0; g < nblk; g++) {
+      const int beta = g - 2 * warp;
+      if (beta >= 0 && beta < nblk_local) {
+        for (int t = 32 * beta + 1; t <= 32 * beta + 32; t++) {
+          float left = __shfl_up_sync(0xffffffffu, last, 1);
+          int leftc = __shfl_up_sync(0xffffffffu, lastc, 1);
+          const int i = t - lane;
+          const bool live = i >= 1 && i <= m;
+          if (lane == 0) {
+            if (warp == 0) { left = (float)i * G; leftc = 0; }  // column 0
+            else if (live) {
+              const float2 v = ring[(warp - 1) * 128 + (i & 127)];
+              left = v.x; leftc = __float_as_int(v.y);
+            }
+          }
+          if (live) {
+            const int jlo = (i <= w0) ? 1 : i - w0 + 1;
+            const int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
+            const float ax = nw_sA[3 * (i - 1)], ay = nw_sA[3 * (i - 1) + 1], az = nw_sA[3 * (i - 1) + 2];
+            float diag = diag_in;
+            int diagc = diag_inc;
+            diag_in = left;
+            diag_inc = leftc;
+#pragma unroll
+            for (int c = 0; c < CPL; c++) {
+              const int j = j0 + 1 + c;
+              float cc = mr_d2(ax, ay, az, bx[c], by[c], bz[c]);
+              if (cc > cutoff) cc = MR_UB;
+              const float c_match = diag + cc, c_i = up[c] + G, c_j = left + G;
+              float best = c_i;  // tie order of dynNW.cc:350-363: skip-i, then skip-j (<), then match (<)
+              int bc = upc[c];
+              if (c_j < best) { best = c_j; bc = leftc; }
+              if (c_match < best) { best = c_match; bc = diagc + 1; }
+              if (j < jlo || j > jhi) { best = (float)(i + j) * G; bc = 0; }
+              diag = up[c]; diagc = upc[c];
+              up[c] = best; upc[c] = bc;
+              left = best; leftc = bc;
+              if (i == m && j == nB) result = bc;
+            }
+            last = left;
+            lastc = leftc;
+            if (lane == 31 && warp + 1 < nwarps) ring[warp * 128 + (i & 127)] = make_float2(last, __int_as_float(lastc));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // the thread that owns column nB holds the count at (m, nB)
+    if (warp * 32 + lane == (nB - 1) / CPL) {
+      nw_matches[o] = result;
+      if (result >= P.of_min) surv[atomicAdd(surv_count, 1)] = o;
+    }
+  }
+}
+
 // identity survivor list when the filter is off
 __global__ void k_iota(int* __restrict__ surv, int* __restrict__ surv_count, int count) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;

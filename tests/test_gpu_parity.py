@@ -195,6 +195,35 @@ def test_nw_filter_counts_match_oracle(golden_c1):
         assert s.eval_one(T)["nw_matches"] == oc.nw_num_matches(g["A"], Bp, 1, p.of_dist, p.of_min)
 
 
+@pytest.mark.parametrize("shape", [(300, 280, 0.33), (233, 310, 0.6), (600, 600, 0.33), (700, 1100, 0.5)])
+def test_nw_filter_long_chains_match_oracle(shape):
+    """nB > 256: the CTA-per-orientation filter kernel (warps split the columns and hand the
+    boundary column over through shared memory) against the oracle's DynNW, for orientations
+    that pass and that fail, and against the thread-per-orientation kernel"""
+    from minrms_b200 import OrientationGenerator
+    m, nB, frac = shape
+    rng = np.random.default_rng(11 * m + nB)
+    A = random_chain(rng, m)
+    B, idx = related_chain(rng, A, nB, noise=1.0, return_idx=True)
+    of_min = int(frac * min(m, nB))
+    p = oc.make_params(n_min=1, m=m, nB=nB, use_filter=True, of_dist=8.0, of_min=of_min)
+    s = make_search(A, B, settings_from_params(p, 4))
+    og = OrientationGenerator(s)
+    r, Tgood = oc.superimpose(A[idx], B)
+    Ts = [Tgood, IDENT] + [og.orientations[k] for k in np.linspace(0, og.size() - 1, 6).astype(int)]
+    want = [oc.nw_num_matches(A, oc.apply_transform(T, B), 1, p.of_dist, p.of_min) for T in Ts]
+    assert want[0] >= of_min                       # the good orientation passes
+    for kern in (0, 1):
+        s.set_option("nw_kernel", kern)
+        got = [s.eval_one(T)["nw_matches"] for T in Ts]
+        assert got == want
+    # batch path: survivors of a search over the same list
+    s.set_option("nw_kernel", 0)
+    s.stats(reset=True)
+    s.Search(np.stack(Ts))
+    assert s.stats()["orientations_dp"] == sum(w >= of_min for w in want)
+
+
 def test_properties_full_size(golden_c2):
     """size-independent properties at the benchmark's full size (config 2)"""
     from minrms_b200 import OrientationGenerator
