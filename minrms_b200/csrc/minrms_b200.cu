@@ -45,6 +45,9 @@ struct mr_ctx {
   uint32_t* d_tb = nullptr;
   float *d_cost = nullptr, *d_ssd = nullptr;
   int *d_surv = nullptr, *d_surv_count = nullptr, *d_nw = nullptr, *d_nlast = nullptr;
+  int* surv = nullptr;           // survivor list the DP / traceback / select kernels read (d_surv or a window of d_surv_all)
+  int *d_surv_all = nullptr, *d_nw_all = nullptr;  // filter results over a whole orientation list
+  int64_t filter_cap = 0;
   unsigned char* d_valid = nullptr;
   float* d_rowcost = nullptr;
   unsigned short* d_rowcnt = nullptr;
@@ -258,17 +261,17 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count) {
   CU(c, cudaEventRecord(ev->a, c->stream));
   const int path = dp_path(c);
   if (path == 1) {
-    if (mr_launch_dp_tiled(c->tiled, c->P, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count,
+    if (mr_launch_dp_tiled(c->tiled, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
                            c->d_tb, c->d_cost, count, c->stream) != 0)
       MR_FAIL(c, "tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else if (path == 2) {
-    if (mr_launch_dp_tiled_mp(c->tiled_mp, c->P, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count,
+    if (mr_launch_dp_tiled_mp(c->tiled_mp, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
                               c->d_tb, c->d_cost, count, c->stream) != 0)
       MR_FAIL(c, "multi-pass tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else {
     int grid = std::min(count, c->dp_grid_cap);
     k_dp_columns<<<grid, std::min(c->NP, 1024), c->dp_smem, c->stream>>>(c->P, c->Lc, c->dA, c->dB, d_orient_chunk,
-                                                        c->d_surv, c->d_surv_count, c->d_tb,
+                                                        c->surv, c->d_surv_count, c->d_tb,
                                                         c->d_cost, c->d_gcol, c->use_gcol);
   }
   CU(c, cudaGetLastError());
@@ -293,11 +296,11 @@ int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* ite
   const size_t coords = 4 * 3 * (size_t)(c->m + c->nB) * c->hp.nb;
   if (use_tiled(c))
     k_traceback_kabsch<TbTiled, EMIT><<<grid, 128, 4 * tiled_layout(c).table_ints() + coords, c->stream>>>(
-        c->P, tiled_layout(c), c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb,
+        c->P, tiled_layout(c), c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb,
         c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs);
   else
     k_traceback_kabsch<TbColumns, EMIT><<<grid, 128, coords, c->stream>>>(
-        c->P, c->Lc, c->dA, c->dB, d_orient_chunk, c->d_surv, c->d_surv_count, c->d_tb, c->d_cost,
+        c->P, c->Lc, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb, c->d_cost,
         items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs);
   CU(c, cudaGetLastError());
   CU(c, cudaEventRecord(ev->b, c->stream));
@@ -306,7 +309,11 @@ int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* ite
 }
 
 // filter (or identity) -> survivors of the chunk
-int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_filter) {
+int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_filter,
+                  int* surv_out = nullptr, int* nw_out = nullptr) {
+  int* const surv = surv_out ? surv_out : c->d_surv;
+  int* const nwm = nw_out ? nw_out : c->d_nw;
+  c->surv = surv;
   if (apply_filter && c->hp.use_filter) {
     CU(c, cudaMemsetAsync(c->d_surv_count, 0, 4, c->stream));
     EventPair* ev = next_events(c, 1);
@@ -317,7 +324,7 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
       // warp per orientation, wavefront in registers
       const int grid = (count + 3) / 4;
       const size_t sm = 4 * 3 * (size_t)c->m;
-#define MR_NW(CPL) k_nw_filter_warp<CPL><<<grid, 128, sm, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, c->d_nw, c->d_surv, c->d_surv_count)
+#define MR_NW(CPL) k_nw_filter_warp<CPL><<<grid, 128, sm, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, nwm, surv, c->d_surv_count)
       switch (cpl) {
         case 1: MR_NW(1); break; case 2: MR_NW(2); break; case 3: MR_NW(3); break; case 4: MR_NW(4); break;
         case 5: MR_NW(5); break; case 6: MR_NW(6); break; case 7: MR_NW(7); break; default: MR_NW(8); break;
@@ -334,17 +341,20 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
       const nwk_t k = ks[nw > 8 ? 1 : 0][std::max(cp, 5) - 5];
       if (sm > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
         MR_FAIL(c, "NW filter: shared memory attribute failed");
-      k<<<grid, 32 * nw, sm, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, c->d_nw, c->d_surv, c->d_surv_count);
+      k<<<grid, 32 * nw, sm, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, nwm, surv, c->d_surv_count);
     } else {
-      const int grid = (count + 127) / 128;
-      k_nw_filter<<<grid, 128, 0, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, c->d_rowcost,
-                                              c->d_rowcnt, c->d_nw, c->d_surv, c->d_surv_count);
+      // thread per orientation; the row scratch holds nw_threads_cap orientations at a time
+      for (int base = 0; base < count; base += c->nw_threads_cap) {
+        const int sub = std::min(c->nw_threads_cap, count - base);
+        k_nw_filter<<<(sub + 127) / 128, 128, 0, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, sub, c->d_rowcost,
+                                                             c->d_rowcnt, nwm, surv, c->d_surv_count, base);
+      }
     }
     CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(ev->b, c->stream));
     c->st.nw_cells += nw_cells(c->m, c->nB, c->hp.of_min) * (int64_t)count;
   } else {
-    k_iota<<<(count + 255) / 256, 256, 0, c->stream>>>(c->d_surv, c->d_surv_count, count);
+    k_iota<<<(count + 255) / 256, 256, 0, c->stream>>>(surv, c->d_surv_count, count);
     CU(c, cudaGetLastError());
   }
   c->st.kernel_launches++;
@@ -354,13 +364,54 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
 // FirstPass over a device-resident list
 int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first_id) {
   if (count <= 0) return 0;
+  if (c->hp.use_filter) {
+    // Phase 1: filter the whole list (it needs nothing per orientation but two ints), so that
+    // phase 2 runs the DP over full chunks of survivors whatever the pass rate -- at config-4
+    // size one orientation in 25 000 passes and a DP launch per list chunk would idle the GPU.
+    if (count > 0x7fffffff) MR_FAIL(c, "orientation list too long");
+    if (count > c->filter_cap) {
+      CU(c, cudaStreamSynchronize(c->stream));
+      cudaFree(c->d_surv_all); cudaFree(c->d_nw_all);
+      c->d_surv_all = c->d_nw_all = nullptr;
+      c->filter_cap = 0;
+      CU(c, cudaMalloc(&c->d_surv_all, 4 * (size_t)count));
+      CU(c, cudaMalloc(&c->d_nw_all, 4 * (size_t)count));
+      c->filter_cap = count;
+    }
+    if (c->chunk_cap == 0 && ensure_chunk(c, std::min<int64_t>(count, 4096))) return 1;  // row scratch of the fallback filter
+    if (launch_filter(c, d_orient, (int)count, true, c->d_surv_all, c->d_nw_all)) return 1;
+    int* h_total = &c->h_pinned[c->h_pinned_cap - 1];
+    CU(c, cudaMemcpyAsync(h_total, c->d_surv_count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const int64_t total = *h_total;
+    c->st.orientations += count;
+    c->st.orientations_dp += total;
+    c->st.dp_cells += dp_cells(c->m, c->nB, c->hp.n_min, c->hp.n_max) * total;
+    c->st.d2h_bytes += 4;
+    if (total > 0 && ensure_chunk(c, total)) return 1;
+    for (int64_t s0 = 0; s0 < total; s0 += c->chunk_cap) {
+      const int cnt = (int)std::min<int64_t>(c->chunk_cap, total - s0);
+      k_set_int<<<1, 1, 0, c->stream>>>(c->d_surv_count, cnt);
+      CU(c, cudaGetLastError());
+      c->surv = c->d_surv_all + s0;  // indices into the whole list
+      if (launch_dp(c, d_orient, cnt)) return 1;
+      if (c->opt_dp_only) continue;
+      if (launch_tb<false>(c, d_orient, cnt, nullptr, 0)) return 1;
+      k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->surv, c->d_surv_count, c->d_cost, c->d_ssd,
+                                                        (long long)first_id, c->d_keys, nullptr, nullptr);
+      CU(c, cudaGetLastError());
+      c->st.kernel_launches += 2;
+    }
+    c->surv = c->d_surv;
+    return 0;
+  }
   if (ensure_chunk(c, count)) return 1;
   for (int64_t start = 0; start < count; start += c->chunk_cap) {
     const int cnt = (int)std::min<int64_t>(c->chunk_cap, count - start);
     const float* oc = d_orient + 12 * (size_t)start;
-    if (launch_filter(c, oc, cnt, true)) return 1;
+    if (launch_filter(c, oc, cnt, false)) return 1;
     // survivor count -> pinned host (for the stats only; nothing waits on it)
-    if ((int)c->pending_counts.size() >= c->h_pinned_cap) {
+    if ((int)c->pending_counts.size() >= c->h_pinned_cap - 1) {
       CU(c, cudaStreamSynchronize(c->stream));
       harvest(c);
     }
@@ -370,7 +421,7 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
     if (launch_dp(c, oc, cnt)) return 1;
     if (c->opt_dp_only) { c->st.orientations += cnt; continue; }
     if (launch_tb<false>(c, oc, cnt, nullptr, 0)) return 1;
-    k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->d_surv, c->d_surv_count,
+    k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->surv, c->d_surv_count,
                                                       c->d_cost, c->d_ssd, (long long)(first_id + start),
                                                       c->d_keys, nullptr, nullptr);
     CU(c, cudaGetLastError());
@@ -569,6 +620,7 @@ void mr_destroy(mr_ctx* c) {
   for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
   cudaFree(c->dA); cudaFree(c->dB); cudaFree(c->d_orient); cudaFree(c->d_tb); cudaFree(c->d_cost);
   cudaFree(c->d_ssd); cudaFree(c->d_surv); cudaFree(c->d_surv_count); cudaFree(c->d_nw);
+  cudaFree(c->d_surv_all); cudaFree(c->d_nw_all);
   cudaFree(c->d_nlast); cudaFree(c->d_valid); cudaFree(c->d_rowcost); cudaFree(c->d_rowcnt);
   cudaFree(c->d_scratch); cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w);
   cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
@@ -862,7 +914,10 @@ int mr_refine(mr_ctx* c, mr_best* best, int32_t max_iters, int32_t* n_evals) {
     if (item_of[rn] < 0) {
       // new batch: every flagged size (the window of flagged sizes around n if they do not fit)
       if (ensure_chunk(c, std::min(R, c->ref_kcap))) return 1;
-      int kmax = std::min(c->ref_kcap, c->chunk_cap);
+      // at most one wave of the DP kernel: up to that size a batch costs the time of one evaluation
+      const int path = dp_path(c);
+      const int wave = path == 2 ? c->tiled_mp.grid_cap : path == 1 ? c->tiled.grid_cap : c->dp_grid_cap;
+      int kmax = std::min(std::min(c->ref_kcap, c->chunk_cap), std::max(wave, 1));
       if (c->opt_refine_batch > 0) kmax = std::min<int>(kmax, (int)c->opt_refine_batch);
       std::vector<int> flagged;
       int pos = 0;

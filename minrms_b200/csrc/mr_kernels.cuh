@@ -93,13 +93,14 @@ __global__ void __launch_bounds__(128)
 k_nw_filter(MrDevParams P, const float* __restrict__ A, const float* __restrict__ B,
             const float* __restrict__ orient, int count, float* __restrict__ row_cost,
             unsigned short* __restrict__ row_cnt, int* __restrict__ nw_matches,
-            int* __restrict__ surv, int* __restrict__ surv_count) {
+            int* __restrict__ surv, int* __restrict__ surv_count, int o_base) {
+  // orientations o_base .. o_base + count - 1 of the list (the row scratch holds one batch)
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   if (tid >= count) return;
   float T[12];
 #pragma unroll
-  for (int k = 0; k < 12; k++) T[k] = orient[12 * (size_t)tid + k];
+  for (int k = 0; k < 12; k++) T[k] = orient[12 * (size_t)(o_base + tid) + k];
   const int m = P.m, nB = P.nB, nb = P.nb, w0 = P.w0, w1 = P.w1;
   const float G = P.nw_gap, cutoff = P.nw_cutoff;
   float left = 0.f;
@@ -155,10 +156,10 @@ k_nw_filter(MrDevParams P, const float* __restrict__ A, const float* __restrict_
       left = best; leftc = bc;
     }
   }
-  nw_matches[tid] = leftc;
+  nw_matches[o_base + tid] = leftc;
   if (leftc >= P.of_min) {
     int slot = atomicAdd(surv_count, 1);
-    surv[slot] = tid;
+    surv[slot] = o_base + tid;
   }
 }
 
@@ -338,6 +339,8 @@ k_nw_filter_cta(MrDevParams P, const float* __restrict__ A, const float* __restr
     }
   }
 }
+
+__global__ void k_set_int(int* __restrict__ p, int v) { *p = v; }
 
 // identity survivor list when the filter is off
 __global__ void k_iota(int* __restrict__ surv, int* __restrict__ surv_count, int count) {
