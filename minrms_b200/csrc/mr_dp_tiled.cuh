@@ -180,6 +180,12 @@ __device__ __forceinline__ void mr_sts128(uint32_t a, float x, float y, float z,
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
+#ifdef MR_EXP_NOSYNC
+#define MR_STEP_SYNC() __syncwarp()  // timing experiment only (results are wrong): cost of the per-step CTA barrier
+#else
+#define MR_STEP_SYNC() __syncthreads()
+#endif
+
 template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
@@ -267,7 +273,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
     for (; s < warp_lo && s <= nsteps; s++) {
       if ((s & (MR_CBATCH - 1)) == 0)
         mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-      __syncthreads();
+      MR_STEP_SYNC();
     }
     // parity of the exchange set written at step s: s & 1
     uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
@@ -362,13 +368,13 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
       if ((s & (MR_CBATCH - 1)) == 0)
         mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
       { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
-      __syncthreads();
+      MR_STEP_SYNC();
     }
     // steps after this warp's window
     for (; s <= nsteps; s++) {
       if ((s & (MR_CBATCH - 1)) == 0)
         mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-      __syncthreads();
+      MR_STEP_SYNC();
     }
   }
 }
