@@ -130,7 +130,8 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
   const float INF = __int_as_float(0x7f800000);
   if (NB1) {
     for (int item = tid; item < (MR_CBATCH / 4) * WR; item += nthreads) {
-      const int q4 = item / WR, rho = item - q4 * WR;
+      static_assert(MR_CBATCH == 8, "two groups of 4 columns per batch");
+      const int q4 = item >= WR ? 1 : 0, rho = item - q4 * WR;  // item < 2 * WR: no division
       const int jn = j0 + 4 * q4, i = rho0 + rho - pad + 1;
       float cc[4] = {INF, INF, INF, INF};
       if (i >= 1 && jn <= nB) {

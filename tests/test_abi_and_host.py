@@ -77,3 +77,27 @@ def test_partition_covers_everything():
                 a, b = partition(count, r, world)
                 seen.extend(range(a, b))
             assert seen == list(range(count))
+
+
+def test_all_vs_all_schedule_covers_every_pair_once_and_balances():
+    """minrms_b200/batch.py: LPT partition of the unordered pairs (config 5 driver)"""
+    from minrms_b200 import Settings
+    from minrms_b200.batch import pair_cost, pair_settings, schedule
+    rng = np.random.default_rng(5000)
+    lengths = [int(x) for x in rng.integers(150, 401, 24)]
+    st = Settings(fm_fragment_size=4)
+    all_pairs = {(i, j) for i in range(24) for j in range(i + 1, 24)}
+    for world in (1, 2, 8):
+        parts = schedule(lengths, world, st)
+        assert len(parts) == world
+        flat = [p for part in parts for p in part]
+        assert len(flat) == len(all_pairs) and set(flat) == all_pairs
+        assert schedule(lengths, world, st) == parts                      # deterministic
+        loads = [sum(pair_cost(lengths[i], lengths[j], st) for i, j in part) for part in parts]
+        biggest = max(pair_cost(lengths[i], lengths[j], st) for i, j in all_pairs)
+        assert max(loads) - min(loads) <= biggest                         # LPT bound
+    # (m-L+1)(n-L+1) orientations x closed-form cell count (SURVEY.md 8 a1, a7)
+    assert pair_cost(141, 151, st) == 138 * 148 * 1044481
+    assert pair_cost(3, 200, st) == 0                                     # shorter than the fragment
+    ps = pair_settings(st, 141, 151, min_n=0.33, of_min=0.33)
+    assert ps.n_min == 47 and ps.orientation_filter_nw_min_num_matches == 47 and st.n_min == 1
