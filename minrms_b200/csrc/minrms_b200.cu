@@ -5,11 +5,13 @@
 #include "../../include/minrms_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "mr_kernels.cuh"
@@ -26,6 +28,8 @@ struct EventPair {
 };
 
 }  // namespace
+
+struct Arena { char* base = nullptr; size_t size = 0; };
 
 struct mr_ctx {
   int device = 0;
@@ -48,6 +52,8 @@ struct mr_ctx {
   int* surv = nullptr;           // survivor list the DP / traceback / select kernels read (d_surv or a window of d_surv_all)
   int *d_surv_all = nullptr, *d_nw_all = nullptr;  // filter results over a whole orientation list
   int64_t filter_cap = 0;
+  struct Arena arena;            // chunk work space (see arena_reserve)
+  size_t gcol_bytes = 0;         // column work space of the general DP kernel (lazy)
   unsigned char* d_valid = nullptr;
   float* d_rowcost = nullptr;
   unsigned short* d_rowcnt = nullptr;
@@ -192,10 +198,48 @@ int dp_path(const mr_ctx* c) {
 bool use_tiled(const mr_ctx* c) { return dp_path(c) != 0; }
 const TbTiled& tiled_layout(const mr_ctx* c) { return dp_path(c) == 2 ? c->tiled_mp.layout : c->tiled.layout; }
 
-// bytes per orientation of the chunk buffers currently allocated
-size_t per_o_held(const mr_ctx* c) {
-  const int per = std::max(1, c->hp.n_max - std::max(2, c->hp.n_min) + 1);
-  return c->tb_words * 4 + (size_t)c->NP * 4 * 2 + (size_t)per * (size_t)c->N * sizeof(short2) + 64;
+// The per-chunk work space (tens of GB; ~100 GB for long chains) is ONE device allocation, the
+// arena, carved up by ensure_chunk.  A destroyed context parks its arena in a per-device cache
+// and the next context on that device picks it up: in an all-vs-all run cudaMalloc +
+// cudaFree of 32 GB cost ~0.5 s per pair, as much as the search itself.
+static std::mutex g_arena_mu;
+static Arena g_arena_cache[64];
+
+static void arena_release(mr_ctx* c) {  // stream must be idle
+  if (!c->arena.base) return;
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  Arena& slot = g_arena_cache[c->device & 63];
+  if (slot.size < c->arena.size) std::swap(slot, c->arena);
+  if (c->arena.base) cudaFree(c->arena.base);
+  c->arena = Arena();
+}
+static size_t arena_cached_bytes(const mr_ctx* c) {
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  return g_arena_cache[c->device & 63].size;
+}
+// make c->arena at least `bytes` large (contents are lost)
+static int arena_reserve(mr_ctx* c, size_t bytes) {
+  if (c->arena.size >= bytes) return 0;
+  cudaStreamSynchronize(c->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    Arena& slot = g_arena_cache[c->device & 63];
+    if (slot.size >= bytes) {
+      std::swap(slot, c->arena);  // ours (smaller or none) is parked instead
+      if (slot.base) { cudaFree(slot.base); slot = Arena(); }
+      return 0;
+    }
+    if (slot.base) { cudaFree(slot.base); slot = Arena(); }
+  }
+  if (c->arena.base) cudaFree(c->arena.base);
+  c->arena = Arena();
+  bytes = (bytes + ((size_t)256 << 20) - 1) & ~(((size_t)256 << 20) - 1);
+  if (cudaMalloc(&c->arena.base, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    MR_FAIL(c, "out of device memory: %zu MB of chunk work space", bytes >> 20);
+  }
+  c->arena.size = bytes;
+  return 0;
 }
 
 // (re)allocate the per-chunk work space for chunks of up to `want` orientations
@@ -215,12 +259,14 @@ int ensure_chunk(mr_ctx* c, int64_t want) {
   if (c->budget_is_default && budget < per_o * (size_t)wave && want > (int64_t)(budget / per_o)) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      // memory held by the current chunk buffers is returned before the new ones are made
-      const size_t held = (size_t)c->chunk_cap * per_o_held(c);
+      // our arena and the parked one are given back before a larger one is made
+      const size_t held = c->arena.size + arena_cached_bytes(c);
       budget = std::max(budget, std::min(per_o * (size_t)wave, (size_t)(0.8 * (double)(free_b + held))));
     }
   }
-  int64_t cap = (int64_t)(budget / per_o);
+  // (64 MB of the budget cover alignment and rounding of the sub-buffers, so that a chunk at
+  // the cap always fits an arena of exactly `budget` bytes)
+  int64_t cap = (int64_t)((budget - std::min<size_t>(budget / 8, (size_t)64 << 20)) / per_o);
   cap = std::max<int64_t>(1, std::min<int64_t>(cap, 1 << 18));
   if (cap > wave && want > cap) cap -= cap % wave;  // several chunks: whole waves
   if (c->opt_chunk > 0) cap = std::min<int64_t>(cap, c->opt_chunk);
@@ -228,27 +274,35 @@ int ensure_chunk(mr_ctx* c, int64_t want) {
   if (need <= c->chunk_cap && words == c->tb_words) return 0;
   cudaStreamSynchronize(c->stream);
   harvest(c);
-  cudaFree(c->d_tb); cudaFree(c->d_cost); cudaFree(c->d_ssd); cudaFree(c->d_surv);
-  cudaFree(c->d_nw); cudaFree(c->d_nlast); cudaFree(c->d_valid); cudaFree(c->d_scratch);
-  cudaFree(c->d_rowcost); cudaFree(c->d_rowcnt);
   c->d_tb = nullptr; c->d_cost = c->d_ssd = nullptr; c->d_surv = c->d_nw = c->d_nlast = nullptr;
   c->d_valid = nullptr; c->d_scratch = nullptr; c->d_rowcost = nullptr; c->d_rowcnt = nullptr;
   c->chunk_cap = 0;
   c->tb_words = words;
-  CU(c, cudaMalloc(&c->d_tb, words * 4 * (size_t)need));
-  CU(c, cudaMalloc(&c->d_cost, (size_t)need * c->NP * 4));
-  CU(c, cudaMalloc(&c->d_ssd, (size_t)need * c->NP * 4));
-  CU(c, cudaMalloc(&c->d_valid, (size_t)need * c->NP));
-  CU(c, cudaMalloc(&c->d_surv, (size_t)need * 4));
-  CU(c, cudaMalloc(&c->d_nw, (size_t)need * 4));
-  CU(c, cudaMalloc(&c->d_nlast, (size_t)need * 4));
-  // traceback scratch: one slice of N pairs per (orientation,size) thread, warp-interleaved
-  c->scratch_threads = (((size_t)need * per + 127) / 128) * 128;
-  CU(c, cudaMalloc(&c->d_scratch, c->scratch_threads * per_thread_scr));
+  c->scratch_threads = (((size_t)need * per + 127) / 128) * 128;  // one slice of N pairs per (orientation,size) thread
+  c->nw_threads_cap = c->hp.use_filter ? (int)(((need + 127) / 128) * 128) : 0;
+  // carve the arena (256-byte aligned sub-buffers)
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_tb = take(words * 4 * (size_t)need), o_cost = take((size_t)need * c->NP * 4),
+               o_ssd = take((size_t)need * c->NP * 4), o_valid = take((size_t)need * c->NP),
+               o_surv = take((size_t)need * 4), o_nw = take((size_t)need * 4), o_nlast = take((size_t)need * 4),
+               o_scr = take(c->scratch_threads * per_thread_scr),
+               o_rc = take((size_t)(c->nB + 1) * c->nw_threads_cap * 4),
+               o_rn = take((size_t)(c->nB + 1) * c->nw_threads_cap * 2);
+  // a chunk at the budget keeps the arena the same size from pair to pair (reusable as is)
+  if (arena_reserve(c, std::max(off, need == cap && want > cap ? budget : (size_t)0))) return 1;
+  char* base = c->arena.base;
+  c->d_tb = reinterpret_cast<uint32_t*>(base + o_tb);
+  c->d_cost = reinterpret_cast<float*>(base + o_cost);
+  c->d_ssd = reinterpret_cast<float*>(base + o_ssd);
+  c->d_valid = reinterpret_cast<unsigned char*>(base + o_valid);
+  c->d_surv = reinterpret_cast<int*>(base + o_surv);
+  c->d_nw = reinterpret_cast<int*>(base + o_nw);
+  c->d_nlast = reinterpret_cast<int*>(base + o_nlast);
+  c->d_scratch = reinterpret_cast<short2*>(base + o_scr);
   if (c->hp.use_filter) {
-    c->nw_threads_cap = (int)(((need + 127) / 128) * 128);
-    CU(c, cudaMalloc(&c->d_rowcost, (size_t)(c->nB + 1) * c->nw_threads_cap * 4));
-    CU(c, cudaMalloc(&c->d_rowcnt, (size_t)(c->nB + 1) * c->nw_threads_cap * 2));
+    c->d_rowcost = reinterpret_cast<float*>(base + o_rc);
+    c->d_rowcnt = reinterpret_cast<unsigned short*>(base + o_rn);
   }
   c->chunk_cap = (int)need;
   return 0;
@@ -269,6 +323,7 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count) {
                               c->d_tb, c->d_cost, count, c->stream) != 0)
       MR_FAIL(c, "multi-pass tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else {
+    if (c->use_gcol && !c->d_gcol) CU(c, cudaMalloc(&c->d_gcol, c->gcol_bytes));
     int grid = std::min(count, c->dp_grid_cap);
     k_dp_columns<<<grid, std::min(c->NP, 1024), c->dp_smem, c->stream>>>(c->P, c->Lc, c->dA, c->dB, d_orient_chunk,
                                                         c->surv, c->d_surv_count, c->d_tb,
@@ -548,7 +603,22 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(cudaGetErrorString(e));
   mr_ctx* c = new mr_ctx();
   c->device = device;
-  cudaGetDeviceProperties(&c->prop, device);
+  const bool dbg = getenv("MR_DEBUG_PLAN") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (!dbg) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mr] create: %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
+  {  // cudaGetDeviceProperties costs 2-11 ms: once per device and process
+    static cudaDeviceProp props[64];
+    static bool have[64] = {false};
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (!have[device & 63]) { cudaGetDeviceProperties(&props[device & 63], device); have[device & 63] = true; }
+    c->prop = props[device & 63];
+  }
+  tick("device properties");
   c->hp = *p;
   c->m = m; c->nB = nB; c->N = N; c->R = p->n_max - p->n_min + 1;
   c->NP = ((p->n_max + 31) / 32) * 32;
@@ -578,6 +648,7 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   if (cudaMalloc(&c->dA, na * 4) != cudaSuccess || cudaMalloc(&c->dB, nbb * 4) != cudaSuccess) return bail("malloc");
   if (cudaMemcpy(c->dA, A, na * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail("memcpy");
   if (cudaMemcpy(c->dB, B, nbb * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail("memcpy");
+  tick("stream + coordinates");
   // general DP kernel: column buffers in shared memory when they fit
   const size_t colbytes = 2 * (size_t)(m + 1) * c->NP * 4;
   const size_t coordbytes = (na + nbb) * 4;
@@ -591,12 +662,14 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
     c->use_gcol = 1;
     c->dp_smem = coordbytes;
     c->dp_grid_cap = c->prop.multiProcessorCount * 2;
-    if (cudaMalloc(&c->d_gcol, colbytes * c->dp_grid_cap) != cudaSuccess) return bail("malloc gcol");
+    c->gcol_bytes = colbytes * c->dp_grid_cap;  // allocated when the general kernel first runs
   }
   if (cudaFuncSetAttribute(k_dp_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dp_smem) != cudaSuccess)
     return bail("smem attribute");
+  tick("general kernel setup");
   mr_plan_dp_tiled(&c->tiled, P, c->prop, c->NP);
   if (!c->tiled.ok) mr_plan_dp_tiled_mp(&c->tiled_mp, P, c->prop, c->NP);
+  tick("tiled plan");
   const int RR = std::max(c->R, 1), slots = std::max(RR, c->NP);
   if (cudaMalloc(&c->d_keys, 8 * (size_t)RR) != cudaSuccess) return bail("malloc");
   if (cudaMalloc(&c->d_surv_count, 4) != cudaSuccess) return bail("malloc");
@@ -608,6 +681,7 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   c->h_pinned_cap = 4096;
   if (cudaMallocHost(&c->h_pinned, 4 * (size_t)c->h_pinned_cap) != cudaSuccess) return bail("pinned");
   if (reset_keys(c)) { g_create_error = c->err; mr_destroy(c); return 1; }
+  tick("small buffers");
   *out = c;
   return 0;
 }
@@ -618,11 +692,10 @@ void mr_destroy(mr_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
-  cudaFree(c->dA); cudaFree(c->dB); cudaFree(c->d_orient); cudaFree(c->d_tb); cudaFree(c->d_cost);
-  cudaFree(c->d_ssd); cudaFree(c->d_surv); cudaFree(c->d_surv_count); cudaFree(c->d_nw);
+  arena_release(c);
+  cudaFree(c->dA); cudaFree(c->dB); cudaFree(c->d_orient); cudaFree(c->d_surv_count);
   cudaFree(c->d_surv_all); cudaFree(c->d_nw_all);
-  cudaFree(c->d_nlast); cudaFree(c->d_valid); cudaFree(c->d_rowcost); cudaFree(c->d_rowcnt);
-  cudaFree(c->d_scratch); cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w);
+  cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w);
   cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
   cudaFree(c->d_ref_pairs_in); cudaFree(c->d_ref_n); cudaFree(c->d_ref_orient); cudaFree(c->d_ref_T); cudaFree(c->d_ref_pairs);
   if (c->h_ref) cudaFreeHost(c->h_ref);
