@@ -296,6 +296,42 @@ def test_mid_size_pairs_match_oracle(shape):
     assert_table_equal(t1["ssd"], t1["T"], t1["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "general")
 
 
+@pytest.mark.parametrize("case", [
+    # m, nB, nb, n_min, max_dist, max_rmsd, filter(of_dist, of_min), ir
+    (260, 240, 1, 80, 9.0, 5.0, (8.0, 80), 1),     # every cut-off at once, banded windows
+    (210, 200, 2, 1, -1.0, -1.0, None, 1),         # two atoms per residue in the multi-pass kernel
+    (230, 250, 1, 60, 12.0, -1.0, None, 0),        # -IR: the DP cost is the score
+])
+def test_mid_size_options_match_oracle(case):
+    """the multi-pass kernel under the options of the synthetic small cases"""
+    from minrms_b200 import OrientationGenerator
+    m, nB, nb, n_min, max_dist, max_rmsd, filt, ir = case
+    rng = np.random.default_rng(13 * m + nB)
+    A = random_chain(rng, m, nb)
+    B, idx = related_chain(rng, A, nB, nb, noise=0.9, return_idx=True)
+    p = oc.make_params(nb=nb, n_min=n_min, n_max=min(m, nB), max_dist=max_dist, max_rmsd=max_rmsd,
+                       use_filter=filt is not None, of_dist=filt[0] if filt else 0.0,
+                       of_min=filt[1] if filt else 0, refine_while_searching=bool(ir))
+    s = make_search(A, B, settings_from_params(p, 4))
+    og = OrientationGenerator(s)
+    ws = oc.Workspace(A, B, p)
+    # an orientation that superimposes the related residues, and a spread of fragment fits
+    Ar, Br = A.reshape(m, nb, 3), B.reshape(nB, nb, 3)
+    r, Tgood = oc.superimpose(Ar[idx].reshape(-1, 3), Br[:len(idx)].reshape(-1, 3))
+    pick = np.concatenate([Tgood[None], og.orientations[np.linspace(0, og.size() - 1, 5).astype(int)]])
+    for T in pick[:3]:
+        ref = ws.eval(T)
+        res = s.eval_one(T)
+        assert res["nw_matches"] == ref["nw_matches"]
+        assert_eval_equal(res, ref["n_last"], ref["cost"], ref["valid"], ref["ssd"], ref["T"], ref["pairs"])
+    best = ws.search(pick)
+    s.Search(pick)
+    t = s.best_table()
+    assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "search")
+    assert np.array_equal(t["o_id"], best["o_id"])
+    assert np.any(best["ssd"] < 1e26)
+
+
 def test_config3_size_pair_matches_oracle():
     """600 x 600 (BASELINE config 3 size): multi-pass tiled kernel; single orientations and
     a small search against the oracle"""
