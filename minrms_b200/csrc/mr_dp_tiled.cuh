@@ -31,6 +31,7 @@
 //     3 FADD (FMA pipes) + FMNMX3 + 2 SHF (ALU pipe) per cell.
 #pragma once
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 #include "mr_device.cuh"
 
@@ -102,6 +103,7 @@ struct MrTiledPlan {
   const char* why = "not planned";
   int K = 0, R = 8, W = 0, CN = 0;
   int nBe = 0;  // columns rounded up to even
+  bool pp = false;  // ping-pong form of the tile update (even step windows)
   int threads = 0, nslots = 0, steps = 0;
   size_t smem = 0;
   int ctas_per_sm = 1;
@@ -187,7 +189,7 @@ __device__ __forceinline__ void mr_sts128(uint32_t a, float x, float y, float z,
 #define MR_STEP_SYNC() __syncthreads()
 #endif
 
-template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED>
+template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
            const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
@@ -254,122 +256,221 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
     __syncthreads();
     mr_produce_c<NB1>(Cr, sA, sB, 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
 
-    float st[K][R], bprev[K];
-    uint32_t acc[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      const float v = (c * K + k == 0) ? 0.0f : INF;
-      bprev[k] = v;
-      acc[k] = 0;
-#pragma unroll
-      for (int r = 0; r < R; r++) st[k][r] = v;
-    }
-    uint4* tbp = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid +
-                 (size_t)max(0, (tb_first - w - 1) >> 1) * nthreads;
-    int tb_next = tb_first;
-    __syncthreads();
-
-    // steps before this warp has live cells: keep pace with the CTA (barrier + C production)
     int s = 1;
-    for (; s < warp_lo && s <= nsteps; s++) {
-      if ((s & (MR_CBATCH - 1)) == 0)
-        mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-      MR_STEP_SYNC();
-    }
-    // parity of the exchange set written at step s: s & 1
-    uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
-    for (; s <= warp_hi; s++) {
-      // C(i, j) for my R rows: ring column j & 31 (columns <= 0 and > nB hold +inf)
-      float cv[R];
-      {
-        const uint32_t ca = a_c + (uint32_t)((s - w) & (MR_CRING - 1)) * c_row;
-        const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
-        cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
-        cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
+    if constexpr (PP) {
+      // Ping-pong form: two copies of the tile state, read from one and written to
+      // the other, so that best = min3(d, up, left) can be ONE instruction (FMNMX3) and the tie
+      // predicate still sees the old value: s2 = best - left.  3 ALU-pipe + 3 FMA-pipe
+      // instructions per cell instead of 4 + 3; needs ~40 more registers (1 CTA per SM).
+      float st[2][K][R], bprev[2][K];
+      uint32_t acc[K];
+  #pragma unroll
+      for (int k = 0; k < K; k++) {
+        const float v = (c * K + k == 0) ? 0.0f : INF;
+        bprev[0][k] = bprev[1][k] = v;
+        acc[k] = 0;
+  #pragma unroll
+        for (int r = 0; r < R; r++) st[0][k][r] = st[1][k][r] = v;
       }
-      // A(n, i_lo-1, j): the bottom row the tile above published last step
-      float bin[K];
-      {
-        const float4 v = mr_lds128(a_up + rd_off);
-        bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
+      uint4* tbp = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid +
+                   (size_t)max(0, (tb_first - w - 1) >> 1) * nthreads;
+      int tb_next = tb_first;
+      __syncthreads();
+      s = 1;
+      for (; s < warp_lo && s <= nsteps; s++) {
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
+        MR_STEP_SYNC();
       }
-      // A(n_lo-1, i-1, j-1) for my lowest layer: what the lower-layer tile published last
-      // step = {its upper boundary, rows 0..6} of its top layer after column j-1
-      float dsh[R];
-      {
-        const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
-        dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-        dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-      }
-#pragma unroll
-      for (int k = K - 1; k >= 0; k--) {
-        float up = bin[k];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
-          const float d = dg + cv[r];
-          const float left = st[k][r];
-#ifdef MR_DP_MIN3
-          const float best = fminf(fminf(d, up), left);
-          const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
-          const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
-#else
-          // two 2-input mins so the new value overwrites `left` in place (no register copy)
-          const float t = fminf(d, up);
-          const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
-          const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
-          const float best = fminf(t, left);
-#endif
-          acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
-          acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
-          st[k][r] = best;
-          up = best;
+      const uint32_t off_a = (s & 1) ? 0u : par_bytes, off_b = par_bytes - off_a;
+      auto step = [&](auto src_tag, const int s, const uint32_t rd_off, const uint32_t wr_off) {
+        constexpr int S = decltype(src_tag)::value, D = 1 - S;
+        float cv[R];
+        {
+          const uint32_t ca = a_c + (uint32_t)((s - w) & (MR_CRING - 1)) * c_row;
+          const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
+          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
+          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
         }
-      }
-      // publish: top layer shifted down one row (for the tile one chunk up, next column, next
-      // step) and bottom row (for the tile below, same column, next step)
-      mr_sts128(a_me + wr_off, bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
-      mr_sts128(a_me + wr_off + 16u, st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
-      mr_sts128(a_me + wr_off + 32u, st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
-#pragma unroll
-      for (int k = 0; k < K; k++) bprev[k] = bin[k];
-      // traceback: the K words of this tile every second column (j = s - w even)
-      if (s == tb_next) {
-        *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-        tbp += nthreads;
-        tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
-      }
-      // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
-      if (s == cost_step) {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          const int n = c * K + k;
-          if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
+        {
+          const float4 v = mr_lds128(a_up + rd_off);
+          bprev[D][0] = v.x; bprev[D][1] = v.y; bprev[D][2] = v.z; bprev[D][3] = v.w;
         }
-      }
-      // n < n_min: the reference reports the corner of the layer's window,
-      // A(n, n+wA-1, n+wB-1) (dyn3d.cc:385, dyn3d.h:407-408): one layer per column
-      if (WINDOWED && has_tile) {
-        const int nq = s - w - P.wB + 1;
-        if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
-          const int rho = nq + P.wA - 2 + pad;
-          if ((rho >> 3) == w) {
-            const int kq = nq & 3, rq = rho & 7;
-            float v = 0.0f;
-#pragma unroll
-            for (int k = 0; k < K; k++)
-#pragma unroll
-              for (int r = 0; r < R; r++)
-                if (k == kq && r == rq) v = st[k][r];
-            cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+        float dsh[R];
+        {
+          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
+          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
+        }
+  #pragma unroll
+        for (int k = K - 1; k >= 0; k--) {
+          float up = bprev[D][k];
+  #pragma unroll
+          for (int r = 0; r < R; r++) {
+            const float dg = (k > 0) ? ((r > 0) ? st[S][k - 1][r - 1] : bprev[S][k - 1]) : dsh[r];
+            const float d = dg + cv[r];
+            const float left = st[S][k][r];
+            const float best = fminf(fminf(d, up), left);
+            const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
+            const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
+            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+            st[D][k][r] = best;
+            up = best;
           }
         }
+        mr_sts128(a_me + wr_off, bprev[D][K - 1], st[D][K - 1][0], st[D][K - 1][1], st[D][K - 1][2]);
+        mr_sts128(a_me + wr_off + 16u, st[D][K - 1][3], st[D][K - 1][4], st[D][K - 1][5], st[D][K - 1][6]);
+        mr_sts128(a_me + wr_off + 32u, st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1], st[D][3][R - 1]);
+        if (s == tb_next) {
+          *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+          tbp += nthreads;
+          tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
+        }
+        if (s == cost_step) {
+  #pragma unroll
+          for (int k = 0; k < K; k++) {
+            const int n = c * K + k;
+            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[D][k][R - 1];
+          }
+        }
+        if (WINDOWED && has_tile) {
+          const int nq = s - w - P.wB + 1;
+          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
+            const int rho = nq + P.wA - 2 + pad;
+            if ((rho >> 3) == w) {
+              const int kq = nq & 3, rq = rho & 7;
+              float v = 0.0f;
+  #pragma unroll
+              for (int k = 0; k < K; k++)
+  #pragma unroll
+                for (int r = 0; r < R; r++)
+                  if (k == kq && r == rq) v = st[D][k][r];
+              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+            }
+          }
+        }
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
+        MR_STEP_SYNC();
+      };
+      // the plan makes every warp window an even number of steps
+      for (; s < warp_hi; s += 2) {
+        step(std::integral_constant<int, 0>(), s, off_a, off_b);
+        step(std::integral_constant<int, 1>(), s + 1, off_b, off_a);
       }
-      // every MR_CBATCH steps all threads produce the next MR_CBATCH columns of C
-      if ((s & (MR_CBATCH - 1)) == 0)
-        mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-      { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
-      MR_STEP_SYNC();
+    } else {
+      float st[K][R], bprev[K];
+      uint32_t acc[K];
+  #pragma unroll
+      for (int k = 0; k < K; k++) {
+        const float v = (c * K + k == 0) ? 0.0f : INF;
+        bprev[k] = v;
+        acc[k] = 0;
+  #pragma unroll
+        for (int r = 0; r < R; r++) st[k][r] = v;
+      }
+      uint4* tbp = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid +
+                   (size_t)max(0, (tb_first - w - 1) >> 1) * nthreads;
+      int tb_next = tb_first;
+      __syncthreads();
+
+      // steps before this warp has live cells: keep pace with the CTA (barrier + C production)
+      s = 1;
+      for (; s < warp_lo && s <= nsteps; s++) {
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
+        MR_STEP_SYNC();
+      }
+      // parity of the exchange set written at step s: s & 1
+      uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
+      for (; s <= warp_hi; s++) {
+        // C(i, j) for my R rows: ring column j & 31 (columns <= 0 and > nB hold +inf)
+        float cv[R];
+        {
+          const uint32_t ca = a_c + (uint32_t)((s - w) & (MR_CRING - 1)) * c_row;
+          const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
+          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
+          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
+        }
+        // A(n, i_lo-1, j): the bottom row the tile above published last step
+        float bin[K];
+        {
+          const float4 v = mr_lds128(a_up + rd_off);
+          bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
+        }
+        // A(n_lo-1, i-1, j-1) for my lowest layer: what the lower-layer tile published last
+        // step = {its upper boundary, rows 0..6} of its top layer after column j-1
+        float dsh[R];
+        {
+          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
+          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
+        }
+  #pragma unroll
+        for (int k = K - 1; k >= 0; k--) {
+          float up = bin[k];
+  #pragma unroll
+          for (int r = 0; r < R; r++) {
+            const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
+            const float d = dg + cv[r];
+            const float left = st[k][r];
+            // two 2-input mins so the new value overwrites `left` in place (no register copy)
+            const float t = fminf(d, up);
+            const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
+            const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
+            const float best = fminf(t, left);
+            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+            st[k][r] = best;
+            up = best;
+          }
+        }
+        // publish: top layer shifted down one row (for the tile one chunk up, next column, next
+        // step) and bottom row (for the tile below, same column, next step)
+        mr_sts128(a_me + wr_off, bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
+        mr_sts128(a_me + wr_off + 16u, st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
+        mr_sts128(a_me + wr_off + 32u, st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
+  #pragma unroll
+        for (int k = 0; k < K; k++) bprev[k] = bin[k];
+        // traceback: the K words of this tile every second column (j = s - w even)
+        if (s == tb_next) {
+          *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+          tbp += nthreads;
+          tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
+        }
+        // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
+        if (s == cost_step) {
+  #pragma unroll
+          for (int k = 0; k < K; k++) {
+            const int n = c * K + k;
+            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
+          }
+        }
+        // n < n_min: the reference reports the corner of the layer's window,
+        // A(n, n+wA-1, n+wB-1) (dyn3d.cc:385, dyn3d.h:407-408): one layer per column
+        if (WINDOWED && has_tile) {
+          const int nq = s - w - P.wB + 1;
+          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
+            const int rho = nq + P.wA - 2 + pad;
+            if ((rho >> 3) == w) {
+              const int kq = nq & 3, rq = rho & 7;
+              float v = 0.0f;
+  #pragma unroll
+              for (int k = 0; k < K; k++)
+  #pragma unroll
+                for (int r = 0; r < R; r++)
+                  if (k == kq && r == rq) v = st[k][r];
+              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+            }
+          }
+        }
+        // every MR_CBATCH steps all threads produce the next MR_CBATCH columns of C
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
+        { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
+        MR_STEP_SYNC();
+      }
     }
     // steps after this warp's window
     for (; s <= nsteps; s++) {
@@ -381,6 +482,8 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
 }
 
 // ---------------------------------------------------------------------------------- host
+static inline int mr_dp_tiles_minb(int threads);
+static inline bool mr_dp_tiles_pp(int threads);
 static inline void mr_free_dp_tiled(MrTiledPlan* p) {
   if (p->d_tiles) cudaFree(p->d_tiles);
   if (p->d_tile_of) cudaFree(p->d_tile_of);
@@ -440,12 +543,14 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   if (threads > 1024) { p->why = "more than 1024 live tiles"; return; }
   for (int t = 0; t < ntiles; t++) index[(size_t)ts[t].w * CN + ts[t].c] = t;
   const int nslots = threads + 2;
+  const bool pp = mr_dp_tiles_pp(threads);
   std::vector<MrTile> tab((size_t)threads);
   int steps = 0;
   long long warp_steps = 0;
   for (int wp = 0; wp < threads / 32; wp++) {
     int lo = 1 << 30, hi = -1;
     for (int t = wp * 32; t < std::min(ntiles, wp * 32 + 32); t++) { lo = std::min(lo, ts[t].lo); hi = std::max(hi, ts[t].hi); }
+    if (pp && hi >= lo && ((hi - lo + 1) & 1)) { if (lo > 1) lo--; else hi++; }  // steps come in pairs
     warp_steps += hi - lo + 1;
     steps = std::max(steps, hi);
     for (int t = wp * 32; t < wp * 32 + 32; t++) {
@@ -468,10 +573,10 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   if (cudaMalloc(&p->d_tile_of, sizeof(int) * index.size()) != cudaSuccess) { p->why = "cudaMalloc"; return; }
   if (cudaMemcpy(p->d_tile_of, index.data(), sizeof(int) * index.size(), cudaMemcpyHostToDevice) != cudaSuccess) { p->why = "cudaMemcpy"; return; }
   p->K = K; p->R = R; p->W = W; p->CN = CN; p->nBe = nBe;
-  p->threads = threads; p->nslots = nslots; p->steps = steps;
+  p->threads = threads; p->nslots = nslots; p->steps = steps; p->pp = pp;
   p->smem = smem;
   const int by_smem = (int)(prop.sharedMemPerMultiprocessor / (smem + 1024));
-  int want = threads <= 384 ? 2 : 1;
+  int want = mr_dp_tiles_minb(threads);  // CTAs per SM the launch-bound bucket of this CTA size allows
 #ifdef MR_EXP_CTAS
   want = MR_EXP_CTAS;
 #endif
@@ -486,15 +591,15 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   p->why = "";
 }
 
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, bool PP>
 static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& P, const float* A,
                                        const float* B, const float* orient, const int* surv,
                                        const int* surv_count, uint32_t* tb, float* cost, int count,
                                        cudaStream_t stream) {
   typedef void (*kern_t)(MrDevParams, TbTiled, int, int, const MrTile*, const float*, const float*, const float*,
                          const int*, const int*, uint32_t*, float*);
-  static const kern_t kerns[4] = {k_dp_tiles<4, 8, MAXT, MINB, false, false>, k_dp_tiles<4, 8, MAXT, MINB, false, true>,
-                                  k_dp_tiles<4, 8, MAXT, MINB, true, false>, k_dp_tiles<4, 8, MAXT, MINB, true, true>};
+  static const kern_t kerns[4] = {k_dp_tiles<4, 8, MAXT, MINB, false, false, PP>, k_dp_tiles<4, 8, MAXT, MINB, false, true, PP>,
+                                  k_dp_tiles<4, 8, MAXT, MINB, true, false, PP>, k_dp_tiles<4, 8, MAXT, MINB, true, true, PP>};
   const kern_t kern = kerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
   // the opt-in shared-memory size is a per-device function attribute
   static size_t attr_set[64] = {0};
@@ -511,19 +616,33 @@ static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& 
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-// Launch-bound buckets: the register budget is 65536 / (MAXT * MINB); fewer threads per CTA
-// leave the 4x8 tile code more registers (no spills at <= 352 threads, 2 CTAs per SM).
+// Launch-bound buckets (CTA size, CTAs per SM, ping-pong form): the register budget is
+// 65536 / (MAXT * MINB).  The two-min form of the 4x8 tile update needs ~88 registers, the
+// ping-pong form (one FMNMX3 per cell) ~150.  Small pairs have few tiles: several CTAs
+// (orientations) per SM keep the pipes fed; from 320 threads on, one CTA per SM in the
+// ping-pong form is faster than two in the two-min form (config 2: 2.07 vs 2.01 TCUPS).
+#define MR_DP_BUCKETS(X) \
+  X(64, 10, false) X(128, 5, false) X(192, 3, false) X(256, 2, false) X(320, 1, true) X(352, 1, true) X(384, 1, true) X(512, 1, true)
+static inline int mr_dp_tiles_minb(int threads) {
+#define MR_X(MAXT, MINB, PP) if (threads <= MAXT) return MINB;
+  MR_DP_BUCKETS(MR_X)
+#undef MR_X
+  return 1;
+}
+static inline bool mr_dp_tiles_pp(int threads) {
+#define MR_X(MAXT, MINB, PP) if (threads <= MAXT) return PP;
+  MR_DP_BUCKETS(MR_X)
+#undef MR_X
+  return false;
+}
+
 static inline int mr_launch_dp_tiled(const MrTiledPlan& p, const MrDevParams& P, const float* A,
                                      const float* B, const float* orient, const int* surv,
                                      const int* surv_count, uint32_t* tb, float* cost, int count,
                                      cudaStream_t stream) {
-#define MR_TRY(MAXT, MINB) \
-  if (p.threads <= MAXT) return mr_launch_dp_tiles_t<MAXT, MINB>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream)
-  MR_TRY(256, 2);
-  MR_TRY(320, 2);
-  MR_TRY(352, 2);
-  MR_TRY(384, 2);
-  MR_TRY(512, 1);
-#undef MR_TRY
-  return mr_launch_dp_tiles_t<1024, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+#define MR_X(MAXT, MINB, PP) \
+  if (p.threads <= MAXT) return mr_launch_dp_tiles_t<MAXT, MINB, PP>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+  MR_DP_BUCKETS(MR_X)
+#undef MR_X
+  return mr_launch_dp_tiles_t<1024, 1, false>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
 }

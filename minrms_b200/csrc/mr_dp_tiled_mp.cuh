@@ -40,7 +40,7 @@ struct MrTileMp {
   int pad_;
 };
 
-template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED>
+template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, const MrPass* __restrict__ passes,
               const MrTileMp* __restrict__ tiles, const float* __restrict__ A, const float* __restrict__ B,
@@ -117,112 +117,222 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
       __syncthreads();
       mr_produce_c<NB1>(Cr, sA, sB, 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
 
-      float st[K][R], bprev[K];
-      uint32_t acc[K];
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        const float v = (c * K + k == 0) ? 0.0f : INF;
-        bprev[k] = v;
-        acc[k] = 0;
-#pragma unroll
-        for (int r = 0; r < R; r++) st[k][r] = v;
-      }
-      uint4* tbp = tb_o + (pass.gid_off + tid) + (size_t)max(0, (tb_first - wl - 1) >> 1) * L.T;
-      int tb_next = tb_first;
-      __syncthreads();
-
       int s = 1;
-      for (; s < warp_lo && s <= nsteps; s++) {
-        if ((s & (MR_CBATCH - 1)) == 0)
-          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+      if constexpr (PP) {
+        // ping-pong form of the tile update (see k_dp_tiles): best = min3(d, up, left) in one
+        // instruction, s2 = best - left from the untouched source copy of the state
+        float st[2][K][R], bprev[2][K];
+        uint32_t acc[K];
+  #pragma unroll
+        for (int k = 0; k < K; k++) {
+          const float v = (c * K + k == 0) ? 0.0f : INF;
+          bprev[0][k] = bprev[1][k] = v;
+          acc[k] = 0;
+  #pragma unroll
+          for (int r = 0; r < R; r++) st[0][k][r] = st[1][k][r] = v;
+        }
+        uint4* tbp = tb_o + (pass.gid_off + tid) + (size_t)max(0, (tb_first - wl - 1) >> 1) * L.T;
+        int tb_next = tb_first;
         __syncthreads();
-      }
-      uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
-      // upper boundary of the first strip: column j = s of the carry, fetched one step ahead
-      float4 gnext = make_float4(INF, INF, INF, INF);
-      if (from_carry) gnext = __ldcg(cme + (size_t)min(s, nBe + 1) * CN);
-      for (; s <= warp_hi; s++) {
-        float cv[R];
-        {
-          const uint32_t ca = a_c + (uint32_t)((s - wl) & (MR_CRING - 1)) * c_row;
-          const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
-          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
-          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
+        s = 1;
+        for (; s < warp_lo && s <= nsteps; s++) {
+          if ((s & (MR_CBATCH - 1)) == 0)
+            mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+          __syncthreads();
         }
-        float bin[K];
-        {
-          float4 v = mr_lds128(a_up + rd_off);
-          if (from_carry) {
-            v = ((unsigned)(s - me.s_lo) <= own_span) ? gnext : make_float4(c == 0 ? 0.0f : INF, INF, INF, INF);
-            gnext = __ldcg(cme + (size_t)min(s + 1, nBe + 1) * CN);
+        const uint32_t off_a = (s & 1) ? 0u : par_bytes, off_b = par_bytes - off_a;
+        float4 gnext = make_float4(INF, INF, INF, INF);
+        if (from_carry) gnext = __ldcg(cme + (size_t)min(s, nBe + 1) * CN);
+        auto step = [&](auto src_tag, const int s, const uint32_t rd_off, const uint32_t wr_off) {
+          constexpr int S = decltype(src_tag)::value, D = 1 - S;
+          float cv[R];
+          {
+            const uint32_t ca = a_c + (uint32_t)((s - wl) & (MR_CRING - 1)) * c_row;
+            const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
+            cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
+            cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
           }
-          bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
-        }
-        float dsh[R];
-        {
-          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
-          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-        }
-#pragma unroll
-        for (int k = K - 1; k >= 0; k--) {
-          float up = bin[k];
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
-            const float d = dg + cv[r];
-            const float left = st[k][r];
-            const float t = fminf(d, up);
-            const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
-            const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
-            const float best = fminf(t, left);
-            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
-            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
-            st[k][r] = best;
-            up = best;
+          {
+            float4 v = mr_lds128(a_up + rd_off);
+            if (from_carry) {
+              v = ((unsigned)(s - me.s_lo) <= own_span) ? gnext : make_float4(c == 0 ? 0.0f : INF, INF, INF, INF);
+              gnext = __ldcg(cme + (size_t)min(s + 1, nBe + 1) * CN);
+            }
+            bprev[D][0] = v.x; bprev[D][1] = v.y; bprev[D][2] = v.z; bprev[D][3] = v.w;
           }
-        }
-        mr_sts128(a_me + wr_off, bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
-        mr_sts128(a_me + wr_off + 16u, st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
-        mr_sts128(a_me + wr_off + 32u, st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
-#pragma unroll
-        for (int k = 0; k < K; k++) bprev[k] = bin[k];
-        // bottom row of the pass -> carry[column j = s - wl]
-        if ((unsigned)(s - out_lo) <= own_span)
-          __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]));
-        if (s == tb_next) {
-          *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-          tbp += L.T;
-          tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
-        }
-        if (s == cost_step) {
-#pragma unroll
-          for (int k = 0; k < K; k++) {
-            const int n = c * K + k;
-            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
+          float dsh[R];
+          {
+            const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
+            dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+            dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
           }
-        }
-        // n < n_min: corner of the layer's window (dyn3d.cc:385, dyn3d.h:407-408)
-        if (WINDOWED && has_tile) {
-          const int nq = s - wl - P.wB + 1;
-          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
-            const int rho = nq + P.wA - 2 + pad;
-            if ((rho >> 3) == w) {
-              const int kq = nq & 3, rq = rho & 7;
-              float v = 0.0f;
-#pragma unroll
-              for (int k = 0; k < K; k++)
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                  if (k == kq && r == rq) v = st[k][r];
-              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+  #pragma unroll
+          for (int k = K - 1; k >= 0; k--) {
+            float up = bprev[D][k];
+  #pragma unroll
+            for (int r = 0; r < R; r++) {
+              const float dg = (k > 0) ? ((r > 0) ? st[S][k - 1][r - 1] : bprev[S][k - 1]) : dsh[r];
+              const float d = dg + cv[r];
+              const float left = st[S][k][r];
+              const float best = fminf(fminf(d, up), left);
+              const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
+              const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
+              acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+              acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+              st[D][k][r] = best;
+              up = best;
             }
           }
+          mr_sts128(a_me + wr_off, bprev[D][K - 1], st[D][K - 1][0], st[D][K - 1][1], st[D][K - 1][2]);
+          mr_sts128(a_me + wr_off + 16u, st[D][K - 1][3], st[D][K - 1][4], st[D][K - 1][5], st[D][K - 1][6]);
+          mr_sts128(a_me + wr_off + 32u, st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1], st[D][3][R - 1]);
+          if ((unsigned)(s - out_lo) <= own_span)
+            __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1], st[D][3][R - 1]));
+          if (s == tb_next) {
+            *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            tbp += L.T;
+            tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
+          }
+          if (s == cost_step) {
+  #pragma unroll
+            for (int k = 0; k < K; k++) {
+              const int n = c * K + k;
+              if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[D][k][R - 1];
+            }
+          }
+          if (WINDOWED && has_tile) {
+            const int nq = s - wl - P.wB + 1;
+            if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
+              const int rho = nq + P.wA - 2 + pad;
+              if ((rho >> 3) == w) {
+                const int kq = nq & 3, rq = rho & 7;
+                float v = 0.0f;
+  #pragma unroll
+                for (int k = 0; k < K; k++)
+  #pragma unroll
+                  for (int r = 0; r < R; r++)
+                    if (k == kq && r == rq) v = st[D][k][r];
+                cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+              }
+            }
+          }
+          if ((s & (MR_CBATCH - 1)) == 0)
+            mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+          __syncthreads();
+        };
+        // the plan makes every warp window an even number of steps
+        for (; s < warp_hi; s += 2) {
+          step(std::integral_constant<int, 0>(), s, off_a, off_b);
+          step(std::integral_constant<int, 1>(), s + 1, off_b, off_a);
         }
-        if ((s & (MR_CBATCH - 1)) == 0)
-          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
-        { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
+      } else {
+        float st[K][R], bprev[K];
+        uint32_t acc[K];
+  #pragma unroll
+        for (int k = 0; k < K; k++) {
+          const float v = (c * K + k == 0) ? 0.0f : INF;
+          bprev[k] = v;
+          acc[k] = 0;
+  #pragma unroll
+          for (int r = 0; r < R; r++) st[k][r] = v;
+        }
+        uint4* tbp = tb_o + (pass.gid_off + tid) + (size_t)max(0, (tb_first - wl - 1) >> 1) * L.T;
+        int tb_next = tb_first;
         __syncthreads();
+
+        s = 1;
+        for (; s < warp_lo && s <= nsteps; s++) {
+          if ((s & (MR_CBATCH - 1)) == 0)
+            mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+          __syncthreads();
+        }
+        uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
+        // upper boundary of the first strip: column j = s of the carry, fetched one step ahead
+        float4 gnext = make_float4(INF, INF, INF, INF);
+        if (from_carry) gnext = __ldcg(cme + (size_t)min(s, nBe + 1) * CN);
+        for (; s <= warp_hi; s++) {
+          float cv[R];
+          {
+            const uint32_t ca = a_c + (uint32_t)((s - wl) & (MR_CRING - 1)) * c_row;
+            const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
+            cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
+            cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
+          }
+          float bin[K];
+          {
+            float4 v = mr_lds128(a_up + rd_off);
+            if (from_carry) {
+              v = ((unsigned)(s - me.s_lo) <= own_span) ? gnext : make_float4(c == 0 ? 0.0f : INF, INF, INF, INF);
+              gnext = __ldcg(cme + (size_t)min(s + 1, nBe + 1) * CN);
+            }
+            bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
+          }
+          float dsh[R];
+          {
+            const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
+            dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+            dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
+          }
+  #pragma unroll
+          for (int k = K - 1; k >= 0; k--) {
+            float up = bin[k];
+  #pragma unroll
+            for (int r = 0; r < R; r++) {
+              const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
+              const float d = dg + cv[r];
+              const float left = st[k][r];
+              const float t = fminf(d, up);
+              const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
+              const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
+              const float best = fminf(t, left);
+              acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+              acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+              st[k][r] = best;
+              up = best;
+            }
+          }
+          mr_sts128(a_me + wr_off, bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
+          mr_sts128(a_me + wr_off + 16u, st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
+          mr_sts128(a_me + wr_off + 32u, st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
+  #pragma unroll
+          for (int k = 0; k < K; k++) bprev[k] = bin[k];
+          // bottom row of the pass -> carry[column j = s - wl]
+          if ((unsigned)(s - out_lo) <= own_span)
+            __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]));
+          if (s == tb_next) {
+            *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            tbp += L.T;
+            tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
+          }
+          if (s == cost_step) {
+  #pragma unroll
+            for (int k = 0; k < K; k++) {
+              const int n = c * K + k;
+              if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
+            }
+          }
+          // n < n_min: corner of the layer's window (dyn3d.cc:385, dyn3d.h:407-408)
+          if (WINDOWED && has_tile) {
+            const int nq = s - wl - P.wB + 1;
+            if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
+              const int rho = nq + P.wA - 2 + pad;
+              if ((rho >> 3) == w) {
+                const int kq = nq & 3, rq = rho & 7;
+                float v = 0.0f;
+  #pragma unroll
+                for (int k = 0; k < K; k++)
+  #pragma unroll
+                  for (int r = 0; r < R; r++)
+                    if (k == kq && r == rq) v = st[k][r];
+                cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+              }
+            }
+          }
+          if ((s & (MR_CBATCH - 1)) == 0)
+            mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+          { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
+          __syncthreads();
+        }
       }
       for (; s <= nsteps; s++) {
         if ((s & (MR_CBATCH - 1)) == 0)
@@ -239,6 +349,7 @@ struct MrTiledMpPlan {
   const char* why = "not planned";
   int W = 0, CN = 0, nBe = 0;
   int threads = 0, minb = 1, nslots = 0, npasses = 0, wl_max = 0;
+  bool pp = false;
   size_t smem = 0;
   int grid_cap = 0;
   size_t tb_words = 0, carry_pitch = 0;
@@ -314,15 +425,25 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
   if (widest > 1024) { p->why = "more than 1024 live tiles in one row strip"; return; }
   // passes: consecutive strips while the tiles fit one CTA
   std::vector<MrPass> passes;
+  // as few passes as the CTA size allows, with the tiles spread evenly over them (a last pass
+  // with a handful of warps runs as long as a full one: it is latency-bound)
+  int remaining = 0;
+  for (int w = 0; w < W; w++) remaining += per_strip[w];
   for (int w0 = 0; w0 < W;) {
+    const int passes_left = (remaining + threads - 1) / threads;
+    const int target = (remaining + passes_left - 1) / passes_left;
     int w1 = w0, cnt = 0;
-    while (w1 < W && w1 - w0 < WL_MAX && cnt + per_strip[w1] <= threads) cnt += per_strip[w1++];
+    while (w1 < W && w1 - w0 < WL_MAX && cnt + per_strip[w1] <= threads &&
+           (w1 == w0 || cnt + per_strip[w1] / 2 <= target))
+      cnt += per_strip[w1++];
+    remaining -= cnt;
     MrPass ps;
     ps.w0 = w0; ps.nstrips = w1 - w0; ps.nsteps = nBe + (w1 - w0) - 1; ps.gid_off = 0;
     passes.push_back(ps);
     w0 = w1;
   }
   const int npasses = (int)passes.size();
+  const bool pp = threads == 512;  // ping-pong tile update: fits 128 registers only in the 512-thread bucket
   // a writer (last strip of a pass) covers the window of its reader (first strip of the next
   // pass, same chunk); bottom-up, so chains of one-strip passes are covered too
   for (int q = npasses - 2; q >= 0; q--) {
@@ -364,6 +485,8 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
     for (int wp = 0; wp < threads / 32; wp++) {
       int lo = 1 << 30, hi = -1;
       for (int t = wp * 32; t < std::min(ntiles, wp * 32 + 32); t++) { lo = std::min(lo, ts[t].lo); hi = std::max(hi, ts[t].hi); }
+      if (pp && hi >= lo && ((hi - lo + 1) & 1)) { if (lo > 1) lo--; else hi++; }  // steps come in pairs
+      if (pp) ps.nsteps = std::max(ps.nsteps, hi);
       if (hi >= lo) warp_steps += hi - lo + 1;
       for (int t = wp * 32; t < wp * 32 + 32; t++) {
         MrTileMp& e = tab[(size_t)q * threads + t];
@@ -398,6 +521,7 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
   if (cudaMalloc(&p->d_carry, sizeof(float4) * carry_pitch * grid_cap) != cudaSuccess) { cudaGetLastError(); return fail("cudaMalloc (carry buffer)"); }
   if (cudaMemset(p->d_carry, 0x7f, sizeof(float4) * carry_pitch * grid_cap) != cudaSuccess) return fail("cudaMemset");
   p->W = W; p->CN = CN; p->nBe = nBe;
+  p->pp = pp;
   p->threads = threads; p->minb = minb; p->nslots = nslots; p->npasses = npasses; p->wl_max = wl_max;
   p->smem = smem; p->grid_cap = grid_cap; p->carry_pitch = carry_pitch;
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
@@ -416,15 +540,15 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
   }
 }
 
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, bool PP>
 static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevParams& P, const float* A,
                                           const float* B, const float* orient, const int* surv,
                                           const int* surv_count, uint32_t* tb, float* cost, int count,
                                           cudaStream_t stream) {
   typedef void (*kern_t)(MrDevParams, TbTiled, int, int, int, const MrPass*, const MrTileMp*, const float*,
                          const float*, const float*, const int*, const int*, float4*, size_t, uint32_t*, float*);
-  static const kern_t kerns[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true>,
-                                  k_dp_tiles_mp<4, 8, MAXT, MINB, true, false>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true>};
+  static const kern_t kerns[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false, PP>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true, PP>,
+                                  k_dp_tiles_mp<4, 8, MAXT, MINB, true, false, PP>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true, PP>};
   const kern_t kern = kerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
   static size_t attr_set[64] = {0};
   int dev = 0;
@@ -444,14 +568,11 @@ static inline int mr_launch_dp_tiled_mp(const MrTiledMpPlan& p, const MrDevParam
                                         const float* B, const float* orient, const int* surv,
                                         const int* surv_count, uint32_t* tb, float* cost, int count,
                                         cudaStream_t stream) {
-#define MR_TRY(MAXT, MINB) \
-  if (p.threads == MAXT) return mr_launch_dp_tiles_mp_t<MAXT, MINB>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream)
-  MR_TRY(320, 2);
-  MR_TRY(352, 2);
-  MR_TRY(384, 2);
-  MR_TRY(512, 1);
-  MR_TRY(640, 1);
-  MR_TRY(768, 1);
+#define MR_TRY(MAXT, MINB, PP) \
+  if (p.threads == MAXT) return mr_launch_dp_tiles_mp_t<MAXT, MINB, PP>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream)
+  MR_TRY(512, 1, true);
+  MR_TRY(640, 1, false);
+  MR_TRY(768, 1, false);
 #undef MR_TRY
-  return mr_launch_dp_tiles_mp_t<1024, 1>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+  return mr_launch_dp_tiles_mp_t<1024, 1, false>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
 }
