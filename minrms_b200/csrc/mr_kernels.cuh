@@ -200,7 +200,6 @@ k_nw_filter_warp(MrDevParams P, const float* __restrict__ A, const float* __rest
   }
   float last = 0.0f, diag_in = (float)j0 * G;  // my last column at my current row; A[i-1][j0]
   int lastc = 0, diag_inc = 0;
-  int result = 0;
   for (int t = 1; t <= m + 31; t++) {
     // value / count to my left at the row I am about to process: lane-1 finished it last step
     float left = __shfl_up_sync(0xffffffffu, last, 1);
@@ -215,6 +214,8 @@ k_nw_filter_warp(MrDevParams P, const float* __restrict__ A, const float* __rest
       int diagc = diag_inc;
       diag_in = left;  // A[i][j0] is the diagonal input of my first column at the next row
       diag_inc = leftc;
+      // rows whose band covers all of my columns skip the per-cell border test
+      const bool inside = (j0 + 1 >= jlo) && (j0 + CPL <= jhi);
 #pragma unroll
       for (int c = 0; c < CPL; c++) {
         const int j = j0 + 1 + c;
@@ -225,18 +226,21 @@ k_nw_filter_warp(MrDevParams P, const float* __restrict__ A, const float* __rest
         int bc = upc[c];
         if (c_j < best) { best = c_j; bc = leftc; }
         if (c_match < best) { best = c_match; bc = diagc + 1; }
-        if (j < jlo || j > jhi) { best = (float)(i + j) * G; bc = 0; }
+        if (!inside && (j < jlo || j > jhi)) { best = (float)(i + j) * G; bc = 0; }
         diag = up[c]; diagc = upc[c];
         up[c] = best; upc[c] = bc;
         left = best; leftc = bc;
-        if (i == m && j == nB) result = bc;
       }
       last = left;
       lastc = leftc;
     }
   }
-  // the lane that owns column nB holds the count at (m, nB)
+  // the lane that owns column nB holds the count at (m, nB): its row-m value of that column
   const int owner = (nB - 1) / CPL;
+  int result = 0;
+#pragma unroll
+  for (int c = 0; c < CPL; c++)
+    if (c == (nB - 1) - owner * CPL) result = upc[c];
   result = __shfl_sync(0xffffffffu, result, owner);
   if (lane == 0) {
     nw_matches[o] = result;
@@ -284,7 +288,6 @@ k_nw_filter_cta(MrDevParams P, const float* __restrict__ A, const float* __restr
     }
     float last = 0.0f, diag_in = (float)j0 * G;
     int lastc = 0, diag_inc = 0;
-    int result = 0;
     for (int g = 0; g < nblk; g++) {
       const int beta = g - 2 * warp;
       if (beta >= 0 && beta < nblk_local) {
@@ -308,6 +311,7 @@ k_nw_filter_cta(MrDevParams P, const float* __restrict__ A, const float* __restr
             int diagc = diag_inc;
             diag_in = left;
             diag_inc = leftc;
+            const bool inside = (j0 + 1 >= jlo) && (j0 + CPL <= jhi);
 #pragma unroll
             for (int c = 0; c < CPL; c++) {
               const int j = j0 + 1 + c;
@@ -318,11 +322,10 @@ k_nw_filter_cta(MrDevParams P, const float* __restrict__ A, const float* __restr
               int bc = upc[c];
               if (c_j < best) { best = c_j; bc = leftc; }
               if (c_match < best) { best = c_match; bc = diagc + 1; }
-              if (j < jlo || j > jhi) { best = (float)(i + j) * G; bc = 0; }
+              if (!inside && (j < jlo || j > jhi)) { best = (float)(i + j) * G; bc = 0; }
               diag = up[c]; diagc = upc[c];
               up[c] = best; upc[c] = bc;
               left = best; leftc = bc;
-              if (i == m && j == nB) result = bc;
             }
             last = left;
             lastc = leftc;
@@ -332,8 +335,12 @@ k_nw_filter_cta(MrDevParams P, const float* __restrict__ A, const float* __restr
       }
       __syncthreads();
     }
-    // the thread that owns column nB holds the count at (m, nB)
+    // the thread that owns column nB holds the count at (m, nB): its row-m value of that column
     if (warp * 32 + lane == (nB - 1) / CPL) {
+      int result = 0;
+#pragma unroll
+      for (int c = 0; c < CPL; c++)
+        if (c == (nB - 1) - ((nB - 1) / CPL) * CPL) result = upc[c];
       nw_matches[o] = result;
       if (result >= P.of_min) surv[atomicAdd(surv_count, 1)] = o;
     }
