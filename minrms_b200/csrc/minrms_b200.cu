@@ -263,7 +263,7 @@ int ensure_chunk(mr_ctx* c, int64_t want) {
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
       // our arena and the parked one are given back before a larger one is made
       const size_t held = c->arena.size + arena_cached_bytes(c);
-      budget = std::max(budget, std::min(per_o * (size_t)wave, (size_t)(0.8 * (double)(free_b + held))));
+      budget = std::max(budget, std::min(per_o * (size_t)wave + ((size_t)64 << 20), (size_t)(0.8 * (double)(free_b + held))));
     }
   }
   // (64 MB of the budget cover alignment and rounding of the sub-buffers, so that a chunk at
