@@ -23,12 +23,18 @@
 //   * tiles are packed into warps sorted by the step at which they become live (cells with
 //     j < n are dead): a warp skips the steps outside the window of its lanes, which removes
 //     most of the triangular waste of the (n <= i, n <= j) pyramid;
-//   * C(i,j) = |A_i - B'_j|^2 is produced one column ahead by the first threads of the CTA
+//   * C(i,j) = |A_i - B'_j|^2 is produced 8 columns at a time by all threads of the CTA
 //     into a 32-column shared-memory ring (+inf outside the matrix, so pipeline fill and
 //     drain steps leave the state untouched);
-//   * the two tie-break predicates are the sign bits of (d - up) and (best - left) (exact
-//     for IEEE floats), funnel-shifted into a per-layer accumulator:
-//     3 FADD (FMA pipes) + FMNMX3 + 2 SHF (ALU pipe) per cell.
+//   * the two tie-break predicates NOT(up <= d) and NOT(left <= min(d, up)) are the sign bits
+//     of float differences (exact for IEEE floats), funnel-shifted into a per-layer
+//     accumulator.  Two forms of the cell update (template parameter PP):
+//       ping-pong (CTAs of 320+ threads, ~150 registers, 1 CTA per SM): the state is kept
+//         twice, read from one copy and written to the other, so that
+//         best = min3(d, up, left) is one FMNMX3 and s2 = best - left still sees the old
+//         value: 3 FADD (FMA pipes) + FMNMX3 + 2 SHF (ALU pipe) per cell;
+//       two-min (smaller CTAs, 88 registers, 2-10 CTAs per SM): t = min(d, up),
+//         s2 = t - left, best = min(t, left) updated in place: one more FMNMX.
 #pragma once
 #include <algorithm>
 #include <type_traits>
