@@ -161,8 +161,9 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
       for (int q = 0; q < 4; q++) Cr[((jn + q) & (MR_CRING - 1)) * WRp + rho] = cc[q];
     }
   } else {
-    for (int e = tid; e < MR_CBATCH * WR; e += nthreads) {
-      const int dj = e / WR, rho = e - dj * WR;
+    // flat loop over (column, row) items; the indices advance without a division per item
+    int dj = tid / WR, rho = tid - dj * WR;
+    while (dj < MR_CBATCH) {
       const int jn = j0 + dj, i = rho0 + rho - pad + 1;
       float cc = INF;
       if (i >= 1 && jn <= nB) {
@@ -175,6 +176,8 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
         if (cc > cutoff) cc = MR_UB;
       }
       Cr[(jn & (MR_CRING - 1)) * WRp + rho] = cc;
+      rho += nthreads;
+      while (rho >= WR) { rho -= WR; dj++; }
     }
   }
 }
