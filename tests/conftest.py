@@ -26,3 +26,10 @@ def golden_c1():
 @pytest.fixture(scope="session")
 def golden_c2():
     return _load("ref_c2.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_mid():
+    """230 x 250 synthetic pair, `-fm 4,0.6 -HS -ir -r` (887 orientations): run of the
+    unmodified reference on a problem that needs the multi-pass DP kernel"""
+    return _load("ref_mid.npz")

@@ -20,29 +20,37 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_ctypes as oc  # noqa: E402
 
+PAIR = ("hemoglobin.pdb,*.A", "myoglobin.pdb")
+SYNTH = ("synth_a.pdb", "synth_b.pdb")       # tests/golden/make_synth_pdbs.py: 230 x 250 residues
+# name: (detail stride, sample size, flags, molecules, fragment RMSD cut-off)
 CONFIGS = {
-    "c1": (50, 32, ["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.5", "-ir", "-r"]),
-    "c2": (200, 16, ["-fm", "4", "-HS", "-ir", "-r"]),
+    "c1": (50, 32, ["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.5", "-ir", "-r"], PAIR, -1.0),
+    "c2": (200, 16, ["-fm", "4", "-HS", "-ir", "-r"], PAIR, -1.0),
+    # a pair beyond the single-pass DP kernel; "-fm 4,0.6" keeps only fragment pairs that
+    # superimpose within 0.6 A (a few hundred orientations: the reference needs ~40 s)
+    "mid": (5, 12, ["-fm", "4,0.6", "-HS", "-ir", "-r"], SYNTH, 0.6),
 }
 TMP = os.environ.get("GOLDEN_TMP", "/tmp/dumps")
 
 
-def run_dump(flavour, cfg, stride, args):
+def run_dump(flavour, cfg, stride, args, mols):
     out = os.path.join(TMP, "%s_%s.bin" % (cfg, flavour))
     if not os.path.exists(out):
         os.makedirs(TMP, exist_ok=True)
-        for f in ("hemoglobin.pdb", "myoglobin.pdb"):
-            subprocess.check_call(["cp", os.path.join(HERE, f), TMP])
+        for f in mols:
+            subprocess.check_call(["cp", os.path.join(HERE, f.split(",")[0]), TMP])
         exe = os.path.join(ROOT, "oracle", "_ref", flavour, "ref_dump")
-        subprocess.check_call([exe, out, str(stride)] + args + ["hemoglobin.pdb,*.A", "myoglobin.pdb"],
-                              cwd=TMP, stdout=subprocess.DEVNULL)
+        subprocess.check_call([exe, out, str(stride)] + args + list(mols), cwd=TMP, stdout=subprocess.DEVNULL)
     return oc.read_ref_dump(out)
 
 
 def main():
-    for cfg, (stride, nsample, args) in CONFIGS.items():
-        ds = run_dump("strict", cfg, stride, args)
-        df = run_dump("fast", cfg, -1, args)
+    only = sys.argv[1:]
+    for cfg, (stride, nsample, args, mols, fm_cutoff) in CONFIGS.items():
+        if only and cfg not in only:
+            continue
+        ds = run_dump("strict", cfg, stride, args, mols)
+        df = run_dump("fast", cfg, -1, args, mols)
         assert np.array_equal(ds["orient"], df["orient"]) or True
         # sample: detail orientations, preferring ones that reach the DP, plus a few rejected
         det = sorted(ds["detail"].keys())
@@ -55,6 +63,7 @@ def main():
             m=ds["m"], nB=ds["nB"], nb=ds["nb"], n_min=ds["n_min"], n_max=ds["n_max"],
             max_dist=ds["max_dist"], max_rmsd=ds["max_rmsd"], use_filter=ds["use_filter"],
             of_dist=ds["of_dist"], of_min=ds["of_min"], ir=ds["ir"], frag=ds["frag"],
+            fm_cutoff=np.float32(fm_cutoff),
             count=ds["count"], A=ds["A"], B=ds["B"],
             orient_sha256=np.frombuffer(hashlib.sha256(ds["orient"].tobytes()).digest(), np.uint8),
             orient_fast_sha256=np.frombuffer(hashlib.sha256(df["orient"].tobytes()).digest(), np.uint8),

@@ -1,0 +1,33 @@
+#!/usr/bin/env python3
+"""CA-only PDB files of a synthetic mid-size pair (230 and 250 residues, seeded random walk
++ a rigidly moved noisy copy with indels; tests/helpers.py) so that the UNMODIFIED reference
+can be run on a problem that needs the multi-pass DP kernel.  Outputs are committed."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from helpers import random_chain, related_chain  # noqa: E402
+
+
+def write_pdb(path, pts):
+    with open(path, "w") as f:
+        for k, (x, y, z) in enumerate(pts, 1):
+            f.write("ATOM  %5d  %-3s %3s %1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n"
+                    % (k, "CA", "GLY", "A", k, x, y, z, 1.00, 0.00))
+        f.write("END\n")
+
+
+def main():
+    rng = np.random.default_rng(230250)
+    A = random_chain(rng, 230)
+    B = related_chain(rng, A, 250, noise=0.9)
+    write_pdb(os.path.join(HERE, "synth_a.pdb"), A)
+    write_pdb(os.path.join(HERE, "synth_b.pdb"), B)
+    print("wrote synth_a.pdb (230 CA), synth_b.pdb (250 CA)")
+
+
+if __name__ == "__main__":
+    main()

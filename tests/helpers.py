@@ -27,7 +27,8 @@ def settings_from_golden(g):
                     orientation_filter_nw=bool(g["use_filter"]),
                     orientation_filter_nw_max_dist=float(g["of_dist"]),
                     orientation_filter_nw_min_num_matches=int(g["of_min"]),
-                    refine_while_searching=bool(g["ir"]), fm_fragment_size=int(g["frag"]))
+                    refine_while_searching=bool(g["ir"]), fm_fragment_size=int(g["frag"]),
+                    fm_cutoff_rmsd=float(g["fm_cutoff"]) if "fm_cutoff" in g else -1.0)
 
 
 def settings_from_params(p, frag=4):

@@ -9,17 +9,22 @@ import oracle_ctypes as oc
 from helpers import (assert_eval_equal, assert_table_equal, bits, params_from_golden, sha)
 
 
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2"])
+def _orientations(g):
+    return oc.gen_orientations(g["A"], g["B"], int(g["nb"]), int(g["frag"]), int(g["n_min"]),
+                               cutoff_rmsd=float(g["fm_cutoff"]) if "fm_cutoff" in g else -1.0)
+
+
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid"])
 def test_orientation_list_matches_reference(cfg, request):
     g = request.getfixturevalue(cfg)
-    og = oc.gen_orientations(g["A"], g["B"], int(g["nb"]), int(g["frag"]), int(g["n_min"]))
+    og = _orientations(g)
     assert og.shape[0] == int(g["count"])
     assert np.array_equal(bits(og[:8]), bits(g["orient_head"]))
     assert np.array_equal(sha(og), g["orient_sha256"])          # includes the shuffle order
     assert np.array_equal(og[g["sample_ids"]], g["sample_orient"])
 
 
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid"])
 def test_per_orientation_values_match_reference(cfg, request):
     g = request.getfixturevalue(cfg)
     ws = oc.Workspace(g["A"], g["B"], params_from_golden(g))
@@ -35,6 +40,20 @@ def test_config1_search_and_refine_bit_exact(golden_c1):
     g = golden_c1
     ws = oc.Workspace(g["A"], g["B"], params_from_golden(g))
     og = oc.gen_orientations(g["A"], g["B"], int(g["nb"]), int(g["frag"]), int(g["n_min"]))
+    best = ws.search(og)
+    assert_table_equal(best["ssd"], best["T"], best["pairs"], g["strict_search_ssd"],
+                       g["strict_search_T"], g["strict_search_pairs"], int(g["n_min"]), "search")
+    ws.refine(best)
+    assert_table_equal(best["ssd"], best["T"], best["pairs"], g["strict_refine_ssd"],
+                       g["strict_refine_T"], g["strict_refine_pairs"], int(g["n_min"]), "refine")
+
+
+def test_mid_size_search_and_refine_bit_exact(golden_mid):
+    """230 x 250 synthetic pair with a fragment RMSD cut-off (-fm 4,0.6): 887 orientations"""
+    g = golden_mid
+    ws = oc.Workspace(g["A"], g["B"], params_from_golden(g))
+    og = _orientations(g)
+    assert og.shape[0] == int(g["count"]) == 887
     best = ws.search(og)
     assert_table_equal(best["ssd"], best["T"], best["pairs"], g["strict_search_ssd"],
                        g["strict_search_T"], g["strict_search_pairs"], int(g["n_min"]), "search")
