@@ -33,3 +33,10 @@ def golden_mid():
     """230 x 250 synthetic pair, `-fm 4,0.6 -HS -ir -r` (887 orientations): run of the
     unmodified reference on a problem that needs the multi-pass DP kernel"""
     return _load("ref_mid.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_long():
+    """280 x 300 synthetic pair, `-fm 4,0.6 -of 8.0,0.33 -HS -minN 0.33 -max-rmsd 4.0 -ir -r`:
+    the flags of config 1 on a pair whose second molecule is longer than 256 residues"""
+    return _load("ref_long.npz")

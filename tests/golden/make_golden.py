@@ -29,6 +29,10 @@ CONFIGS = {
     # a pair beyond the single-pass DP kernel; "-fm 4,0.6" keeps only fragment pairs that
     # superimpose within 0.6 A (a few hundred orientations: the reference needs ~40 s)
     "mid": (5, 12, ["-fm", "4,0.6", "-HS", "-ir", "-r"], SYNTH, 0.6),
+    # 280 x 300 residues with the flags of config 1: molecule 2 is longer than 256 residues
+    # (CTA-per-orientation NW filter), banded DP windows, max-rmsd cut-off, multi-pass DP
+    "long": (5, 12, ["-fm", "4,0.6", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "4.0", "-ir", "-r"],
+             ("synth_c.pdb", "synth_d.pdb"), 0.6),
 }
 TMP = os.environ.get("GOLDEN_TMP", "/tmp/dumps")
 

@@ -27,6 +27,13 @@ def main():
     write_pdb(os.path.join(HERE, "synth_a.pdb"), A)
     write_pdb(os.path.join(HERE, "synth_b.pdb"), B)
     print("wrote synth_a.pdb (230 CA), synth_b.pdb (250 CA)")
+    # a longer pair (molecule 2 beyond 256 residues: CTA-per-orientation NW filter)
+    rng = np.random.default_rng(280300)
+    A = random_chain(rng, 280)
+    B = related_chain(rng, A, 300, noise=0.8)
+    write_pdb(os.path.join(HERE, "synth_c.pdb"), A)
+    write_pdb(os.path.join(HERE, "synth_d.pdb"), B)
+    print("wrote synth_c.pdb (280 CA), synth_d.pdb (300 CA)")
 
 
 if __name__ == "__main__":
