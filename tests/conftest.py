@@ -40,3 +40,15 @@ def golden_long():
     """280 x 300 synthetic pair, `-fm 4,0.6 -of 8.0,0.33 -HS -minN 0.33 -max-rmsd 4.0 -ir -r`:
     the flags of config 1 on a pair whose second molecule is longer than 256 residues"""
     return _load("ref_long.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_bb():
+    """60 x 66 residues with four backbone atoms each (atoms_used.txt = N, C, CA, O), unconstrained"""
+    return _load("ref_bb.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_bb_of():
+    """the same pair under `-of 8.0,0.33 -minN 0.33 -max-rmsd 3.0`"""
+    return _load("ref_bb_of.npz")

@@ -33,6 +33,10 @@ CONFIGS = {
     # (CTA-per-orientation NW filter), banded DP windows, max-rmsd cut-off, multi-pass DP
     "long": (5, 12, ["-fm", "4,0.6", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "4.0", "-ir", "-r"],
              ("synth_c.pdb", "synth_d.pdb"), 0.6),
+    # four backbone atoms per residue (atoms_used.txt = N, C, CA, O; share/README.md), 60 x 66
+    "bb": (50, 12, ["-fm", "4", "-HS", "-ir", "-r"], ("synth_bb1.pdb", "synth_bb2.pdb"), -1.0),
+    "bb_of": (20, 12, ["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.0", "-ir", "-r"],
+              ("synth_bb1.pdb", "synth_bb2.pdb"), -1.0),
 }
 TMP = os.environ.get("GOLDEN_TMP", "/tmp/dumps")
 
@@ -43,6 +47,11 @@ def run_dump(flavour, cfg, stride, args, mols):
         os.makedirs(TMP, exist_ok=True)
         for f in mols:
             subprocess.check_call(["cp", os.path.join(HERE, f.split(",")[0]), TMP])
+        au = os.path.join(TMP, "atoms_used.txt")       # read by the reference from its cwd
+        if cfg.startswith("bb"):
+            subprocess.check_call(["cp", os.path.join(HERE, "atoms_used_backbone.txt"), au])
+        elif os.path.exists(au):
+            os.remove(au)
         exe = os.path.join(ROOT, "oracle", "_ref", flavour, "ref_dump")
         subprocess.check_call([exe, out, str(stride)] + args + list(mols), cwd=TMP, stdout=subprocess.DEVNULL)
     return oc.read_ref_dump(out)

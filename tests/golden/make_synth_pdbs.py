@@ -20,7 +20,26 @@ def write_pdb(path, pts):
         f.write("END\n")
 
 
+def write_backbone_pdb(path, pts, names=("N", "CA", "C", "O")):
+    """four backbone atoms per residue (pts: [residues * 4, 3])"""
+    with open(path, "w") as f:
+        for k, (x, y, z) in enumerate(pts):
+            res, a = k // len(names) + 1, names[k % len(names)]
+            f.write("ATOM  %5d  %-3s %3s %1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n"
+                    % (k + 1, a, "GLY", "A", res, x, y, z, 1.00, 0.00))
+        f.write("END\n")
+
+
 def main():
+    # a short pair with the four backbone atoms of share/README.md's atoms_used.txt example
+    rng = np.random.default_rng(6066)
+    A = random_chain(rng, 60, 4)
+    B = related_chain(rng, A, 66, 4, noise=0.6)
+    write_backbone_pdb(os.path.join(HERE, "synth_bb1.pdb"), A)
+    write_backbone_pdb(os.path.join(HERE, "synth_bb2.pdb"), B)
+    with open(os.path.join(HERE, "atoms_used_backbone.txt"), "w") as f:
+        f.write(" N\n C\n CA\n O\n")
+    print("wrote synth_bb1.pdb (60 x 4 atoms), synth_bb2.pdb (66 x 4 atoms), atoms_used_backbone.txt")
     rng = np.random.default_rng(230250)
     A = random_chain(rng, 230)
     B = related_chain(rng, A, 250, noise=0.9)

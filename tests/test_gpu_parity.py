@@ -25,7 +25,7 @@ def make_search(A, B, settings, kernel=None):
     return s
 
 
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of"])
 def test_orientation_generation_matches_reference(cfg, request):
     from minrms_b200 import OrientationGenerator
     g = request.getfixturevalue(cfg)
@@ -37,7 +37,7 @@ def test_orientation_generation_matches_reference(cfg, request):
 
 
 @pytest.mark.parametrize("kernel", [1, 0, 3])
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of"])
 def test_single_orientation_values_match_reference(cfg, kernel, request):
     g = request.getfixturevalue(cfg)
     s = make_search(g["A"], g["B"], settings_from_golden(g), kernel)
@@ -48,7 +48,7 @@ def test_single_orientation_values_match_reference(cfg, kernel, request):
 
 
 @pytest.mark.parametrize("kernel", [1, 0, 3])
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of"])
 def test_full_search_and_refine_match_reference(cfg, kernel, request):
     """configs 1 and 2 (and the 230 x 250 pair of the multi-pass kernel) end to end:
     orientation generation, FirstPass, Refine; the per-size tables must equal the strict
@@ -69,7 +69,7 @@ def test_full_search_and_refine_match_reference(cfg, kernel, request):
     t = s.best_table()
     assert_table_equal(t["ssd"], t["T"], t["pairs"], g["strict_refine_ssd"], g["strict_refine_T"],
                        g["strict_refine_pairs"], int(g["n_min"]), "refine")
-    if cfg in ("golden_mid", "golden_long"):
+    if cfg not in ("golden_c1", "golden_c2"):
         return   # strict build only: with -ffast-math the reference itself moves by 1e-3 A here
     # and the shipped-flags reference within the stated tolerance (RMSD >= 0.01 A: 1.5e-4 A)
     n = int(g["n_min"]) + np.arange(t["ssd"].shape[0])
