@@ -52,3 +52,9 @@ def golden_bb():
 def golden_bb_of():
     """the same pair under `-of 8.0,0.33 -minN 0.33 -max-rmsd 3.0`"""
     return _load("ref_bb_of.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_ir_off():
+    """CA atoms of the 60 x 66 pair, `-IR -max-dist 7.0 -minN 0.25 -r`"""
+    return _load("ref_ir_off.npz")

@@ -37,6 +37,10 @@ CONFIGS = {
     "bb": (50, 12, ["-fm", "4", "-HS", "-ir", "-r"], ("synth_bb1.pdb", "synth_bb2.pdb"), -1.0),
     "bb_of": (20, 12, ["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.0", "-ir", "-r"],
               ("synth_bb1.pdb", "synth_bb2.pdb"), -1.0),
+    # CA atoms of the same files, -IR (the DP cost is the score, no Kabsch per size) and the
+    # -max-dist cut-off with its early exit
+    "ir_off": (50, 12, ["-fm", "4", "-HS", "-IR", "-max-dist", "7.0", "-minN", "0.25", "-r"],
+               ("synth_bb1.pdb", "synth_bb2.pdb"), -1.0),
 }
 TMP = os.environ.get("GOLDEN_TMP", "/tmp/dumps")
 
