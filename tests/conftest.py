@@ -58,3 +58,9 @@ def golden_bb_of():
 def golden_ir_off():
     """CA atoms of the 60 x 66 pair, `-IR -max-dist 7.0 -minN 0.25 -r`"""
     return _load("ref_ir_off.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_iv():
+    """CA atoms of the 60 x 66 pair, two `-fm-interval` pairs restricting the fragment starts"""
+    return _load("ref_iv.npz")

@@ -41,7 +41,12 @@ CONFIGS = {
     # -max-dist cut-off with its early exit
     "ir_off": (50, 12, ["-fm", "4", "-HS", "-IR", "-max-dist", "7.0", "-minN", "0.25", "-r"],
                ("synth_bb1.pdb", "synth_bb2.pdb"), -1.0),
+    # explicit fragment-matching interval pairs (residue numbers 5-30 x 10-40 and 35-55 x 30-60:
+    # 0-based index intervals [4,29]x[9,39], [34,54]x[29,59]; or_gen.cc:345-493)
+    "iv": (20, 12, ["-fm", "4", "-HS", "-fm-interval", "5-30.A,10-40.A", "-fm-interval", "35-55.A,30-60.A",
+                    "-ir", "-r"], ("synth_bb1.pdb", "synth_bb2.pdb"), -1.0),
 }
+INTERVALS = {"iv": np.array([[4, 29, 9, 39], [34, 54, 29, 59]], np.int32)}
 TMP = os.environ.get("GOLDEN_TMP", "/tmp/dumps")
 
 
@@ -81,6 +86,7 @@ def main():
             max_dist=ds["max_dist"], max_rmsd=ds["max_rmsd"], use_filter=ds["use_filter"],
             of_dist=ds["of_dist"], of_min=ds["of_min"], ir=ds["ir"], frag=ds["frag"],
             fm_cutoff=np.float32(fm_cutoff),
+            **({"intervals": INTERVALS[cfg]} if cfg in INTERVALS else {}),
             count=ds["count"], A=ds["A"], B=ds["B"],
             orient_sha256=np.frombuffer(hashlib.sha256(ds["orient"].tobytes()).digest(), np.uint8),
             orient_fast_sha256=np.frombuffer(hashlib.sha256(df["orient"].tobytes()).digest(), np.uint8),

@@ -25,19 +25,19 @@ def make_search(A, B, settings, kernel=None):
     return s
 
 
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv"])
 def test_orientation_generation_matches_reference(cfg, request):
     from minrms_b200 import OrientationGenerator
     g = request.getfixturevalue(cfg)
     s = make_search(g["A"], g["B"], settings_from_golden(g))
-    og = OrientationGenerator(s)
+    og = OrientationGenerator(s, intervals=g["intervals"] if "intervals" in g else None)
     assert og.size() == int(g["count"])
     assert np.array_equal(bits(og.orientations[:8]), bits(g["orient_head"]))
     assert np.array_equal(sha(og.orientations), g["orient_sha256"])
 
 
 @pytest.mark.parametrize("kernel", [1, 0, 3])
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv"])
 def test_single_orientation_values_match_reference(cfg, kernel, request):
     g = request.getfixturevalue(cfg)
     s = make_search(g["A"], g["B"], settings_from_golden(g), kernel)
@@ -48,7 +48,7 @@ def test_single_orientation_values_match_reference(cfg, kernel, request):
 
 
 @pytest.mark.parametrize("kernel", [1, 0, 3])
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv"])
 def test_full_search_and_refine_match_reference(cfg, kernel, request):
     """configs 1 and 2 (and the 230 x 250 pair of the multi-pass kernel) end to end:
     orientation generation, FirstPass, Refine; the per-size tables must equal the strict
@@ -56,7 +56,7 @@ def test_full_search_and_refine_match_reference(cfg, kernel, request):
     from minrms_b200 import OrientationGenerator
     g = request.getfixturevalue(cfg)
     s = make_search(g["A"], g["B"], settings_from_golden(g), kernel)
-    og = OrientationGenerator(s)
+    og = OrientationGenerator(s, intervals=g["intervals"] if "intervals" in g else None)
     s.Search(og, 0, og.size())
     s.check_solutions()
     t = s.best_table()
