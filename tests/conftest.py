@@ -64,3 +64,9 @@ def golden_ir_off():
 def golden_iv():
     """CA atoms of the 60 x 66 pair, two `-fm-interval` pairs restricting the fragment starts"""
     return _load("ref_iv.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_maxn():
+    """CA atoms of the 60 x 66 pair, `-fm 5 -minN 10 -maxN 40`"""
+    return _load("ref_maxn.npz")

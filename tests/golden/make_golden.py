@@ -45,6 +45,9 @@ CONFIGS = {
     # 0-based index intervals [4,29]x[9,39], [34,54]x[29,59]; or_gen.cc:345-493)
     "iv": (20, 12, ["-fm", "4", "-HS", "-fm-interval", "5-30.A,10-40.A", "-fm-interval", "35-55.A,30-60.A",
                     "-ir", "-r"], ("synth_bb1.pdb", "synth_bb2.pdb"), -1.0),
+    # -minN / -maxN as counts: only sizes 10..40 of the 60 x 66 pair
+    "maxn": (50, 12, ["-fm", "5", "-HS", "-minN", "10", "-maxN", "40", "-ir", "-r"],
+             ("synth_bb1.pdb", "synth_bb2.pdb"), -1.0),
 }
 INTERVALS = {"iv": np.array([[4, 29, 9, 39], [34, 54, 29, 59]], np.int32)}
 TMP = os.environ.get("GOLDEN_TMP", "/tmp/dumps")

@@ -25,7 +25,7 @@ def make_search(A, B, settings, kernel=None):
     return s
 
 
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv", "golden_maxn"])
 def test_orientation_generation_matches_reference(cfg, request):
     from minrms_b200 import OrientationGenerator
     g = request.getfixturevalue(cfg)
@@ -37,7 +37,7 @@ def test_orientation_generation_matches_reference(cfg, request):
 
 
 @pytest.mark.parametrize("kernel", [1, 0, 3])
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv", "golden_maxn"])
 def test_single_orientation_values_match_reference(cfg, kernel, request):
     g = request.getfixturevalue(cfg)
     s = make_search(g["A"], g["B"], settings_from_golden(g), kernel)
@@ -48,7 +48,7 @@ def test_single_orientation_values_match_reference(cfg, kernel, request):
 
 
 @pytest.mark.parametrize("kernel", [1, 0, 3])
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv", "golden_maxn"])
 def test_full_search_and_refine_match_reference(cfg, kernel, request):
     """configs 1 and 2 (and the 230 x 250 pair of the multi-pass kernel) end to end:
     orientation generation, FirstPass, Refine; the per-size tables must equal the strict

@@ -15,7 +15,7 @@ def _orientations(g):
                                intervals=g["intervals"] if "intervals" in g else None)
 
 
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv", "golden_maxn"])
 def test_orientation_list_matches_reference(cfg, request):
     g = request.getfixturevalue(cfg)
     og = _orientations(g)
@@ -25,7 +25,7 @@ def test_orientation_list_matches_reference(cfg, request):
     assert np.array_equal(og[g["sample_ids"]], g["sample_orient"])
 
 
-@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv"])
+@pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv", "golden_maxn"])
 def test_per_orientation_values_match_reference(cfg, request):
     g = request.getfixturevalue(cfg)
     ws = oc.Workspace(g["A"], g["B"], params_from_golden(g))
@@ -49,7 +49,7 @@ def test_config1_search_and_refine_bit_exact(golden_c1):
                        g["strict_refine_T"], g["strict_refine_pairs"], int(g["n_min"]), "refine")
 
 
-@pytest.mark.parametrize("cfg", ["golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv"])
+@pytest.mark.parametrize("cfg", ["golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv", "golden_maxn"])
 def test_synthetic_search_and_refine_bit_exact(cfg, request):
     """synthetic pairs run through the unmodified reference: 230 x 250 unconstrained and
     280 x 300 under the flags of config 1 (fragment RMSD cut-off -fm 4,0.6), and a 60 x 66 pair
