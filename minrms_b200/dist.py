@@ -1,9 +1,9 @@
 """Multi-GPU reduction of per-size best tables: orientations are
-partitioned across ranks (one process per GPU); after the local FirstPass one small
-all-reduce(MIN) of the 64-bit keys (float_bits(ssd) << 32 | orientation id) picks, per
-size, the lowest score with the lowest id winning ties -- the reference's sequential
-rule (bin/minrms/search_or_dyn3d.cc:1825-1835).  The payload (transform + alignment) of
-each size is then taken from the rank whose local key equals the reduced key.
+partitioned across ranks (one process per GPU); after the local FirstPass the per-size
+records are exchanged once and the minimum of the 64-bit keys (float_bits(ssd) << 32 |
+orientation id) picks, per size, the lowest score with the lowest id winning ties -- the
+reference's sequential rule (bin/minrms/search_or_dyn3d.cc:1825-1835).  The payload
+(transform + alignment) of each size is the row of the rank that holds that key.
 
 torch.distributed is plumbing only (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
 import numpy as np
@@ -34,27 +34,31 @@ def partition(count, rank, world):
 
 def allreduce_best(table, device=None, group=None):
     """table: dict(ssd[R] f32, T[R,12] f32, pairs[R,N,2] i16, o_id[R] i64) of this rank.
-    Returns the merged table (identical on every rank)."""
+    Returns the merged table (identical on every rank).
+
+    One collective: every rank contributes its R records {key, transform, alignment} as int32
+    rows (all_gather, 166 KB per rank for config 2); each rank then takes, per size, the row of
+    the rank holding the minimum key -- the keys are unique per orientation id, so the minimum
+    identifies exactly one owner."""
     R = table["ssd"].shape[0]
     dev = device if device is not None else torch.device("cpu")
-    keys = torch.from_numpy(keys_from_table(table["ssd"], table["o_id"])).to(dev)
-    red = keys.clone()
-    dist.all_reduce(red, op=dist.ReduceOp.MIN, group=group)
-    mine = (keys == red) & (red != KEY_NONE)
-    # payload: rows this rank owns, zero elsewhere; the keys are unique per id so exactly
-    # one rank owns each size -> a SUM all-reduce is a gather of the owners' rows.
-    payload = np.concatenate([table["T"].reshape(R, -1).view(np.int32),
-                              table["pairs"].reshape(R, -1).astype(np.int32)], axis=1)
-    pt = torch.from_numpy(np.ascontiguousarray(payload)).to(dev)
-    pt = pt * mine.to(pt.dtype).unsqueeze(1)
-    dist.all_reduce(pt, op=dist.ReduceOp.SUM, group=group)
+    world = dist.get_world_size(group)
+    keys = keys_from_table(table["ssd"], table["o_id"])
+    rows = np.concatenate([keys.view(np.int32).reshape(R, 2), table["T"].reshape(R, -1).view(np.int32),
+                           table["pairs"].reshape(R, -1).astype(np.int32)], axis=1)
+    mine = torch.from_numpy(np.ascontiguousarray(rows)).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    allrows = torch.stack(parts)                                        # [world, R, C]
+    allkeys = allrows[:, :, :2].contiguous().view(torch.int64).squeeze(-1)   # [world, R]
+    red, owner = allkeys.min(dim=0)
+    pay = allrows[owner, torch.arange(R, device=allrows.device)].cpu().numpy()
     red_np = red.cpu().numpy()
-    pay = pt.cpu().numpy()
     none = red_np == KEY_NONE
     ssd = (red_np >> 32).astype(np.uint32).view(np.float32).copy()
     o_id = (red_np & 0xFFFFFFFF).astype(np.int64)
-    T = pay[:, :12].astype(np.int32).view(np.float32).copy()
-    pairs = pay[:, 12:].astype(np.int16).reshape(table["pairs"].shape)
+    T = np.ascontiguousarray(pay[:, 2:14]).view(np.float32).copy()
+    pairs = pay[:, 14:].astype(np.int16).reshape(table["pairs"].shape)
     ssd[none] = np.float32(1.0e26)
     o_id[none] = -1
     T[none] = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
