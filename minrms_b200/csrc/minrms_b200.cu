@@ -937,18 +937,23 @@ static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* b
     hn[b] = n;
     memcpy(hp + (size_t)b * N, best->pairs + (size_t)rs[b] * 2 * N, sizeof(short2) * (size_t)n);
   }
+  static const bool dbg = getenv("MR_DEBUG_REFINE") != nullptr;
+  static cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const auto w0 = std::chrono::steady_clock::now();
+  if (dbg) { if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); } cudaEventRecord(e0, c->stream); }
   CU(c, cudaMemcpyAsync(c->d_ref_pairs_in, hp, sizeof(short2) * (size_t)N * k, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(c->d_ref_n, hn, sizeof(int) * (size_t)k, cudaMemcpyHostToDevice, c->stream));
   c->st.h2d_bytes += (int64_t)k * (4 * N + 4);
   // orientation that optimally superimposes each alignment (:2401-2407)
-  k_superimpose_pairs_batch<<<k, 32, 0, c->stream>>>(c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N, c->d_ref_orient);
+  k_superimpose_pairs_batch<<<k, 128, 4 * 3 * (size_t)(c->m + c->nB) * c->hp.nb + 4 * (size_t)N, c->stream>>>(
+      c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N, c->d_ref_orient);
   CU(c, cudaGetLastError());
   c->st.kernel_launches++;
-  if (launch_filter(c, c->d_ref_orient, k, false)) return 1;
-  CU(c, cudaMemsetAsync(c->d_valid, 0, (size_t)NP * k, c->stream));
-  CU(c, cudaMemsetAsync(c->d_cost, 0, (size_t)NP * 4 * k, c->stream));
-  CU(c, cudaMemsetAsync(c->d_ssd, 0, (size_t)NP * 4 * k, c->stream));
-  CU(c, cudaMemsetAsync(c->d_nlast, 0, 4 * (size_t)k, c->stream));
+  c->surv = c->d_surv;
+  k_refine_prep<<<(k * NP + 255) / 256, 256, 0, c->stream>>>(c->d_surv, c->d_surv_count, k, NP, c->d_cost, c->d_ssd,
+                                                            c->d_valid, c->d_nlast);
+  CU(c, cudaGetLastError());
+  c->st.kernel_launches++;
   if (launch_dp(c, c->d_ref_orient, k)) return 1;
   if (launch_tb<true>(c, c->d_ref_orient, k, nullptr, 0, c->d_ref_T, c->d_ref_pairs)) return 1;
   k_select<<<(k + 31) / 32, 32, 0, c->stream>>>(c->P, NP, c->d_surv, c->d_surv_count, c->d_cost, c->d_ssd, 0ll,
@@ -958,7 +963,20 @@ static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* b
   CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_ssd, c->d_ssd, 4 * (size_t)NP * k, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_valid, c->d_valid, (size_t)NP * k, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_nlast, c->d_nlast, 4 * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  if (dbg) cudaEventRecord(e1, c->stream);
   CU(c, cudaStreamSynchronize(c->stream));
+  if (dbg) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    float dp = 0.f, tb = 0.f;
+    for (size_t q = 0; q < c->events_used; q++) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, c->events[q].a, c->events[q].b);
+      (c->events[q].kind == 0 ? dp : tb) += t;
+    }
+    fprintf(stderr, "[mr] refine batch: %3d items, device %.3f ms (dp %.3f, traceback %.3f), wall %.3f ms\n", k, ms, dp, tb,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
+  }
   c->st.d2h_bytes += (int64_t)k * (5 * NP + 4);
   c->events_used = 0;  // Refine evaluations are not part of the search throughput stats
   c->st.refine_batches++;

@@ -28,7 +28,7 @@ struct TbColumns {
   __device__ __forceinline__ void load_table(int*, int, int) const {}
   // Dyn3d::ExportSolution (dyn3d.cc:391-431): from (n, m, nB) follow the codes; emit(k, i0, j0)
   // for the k-th (0-based) matched pair with 0-based residue indices
-  template <class Emit>
+  template <bool GROUP, class Emit>
   __device__ __forceinline__ void walk(const int*, const uint32_t* __restrict__ tbo, int n, int m, int nB, Emit emit) const {
     int cn = n, ci = m, cj = nB;
     while (cn > 0) {
@@ -349,6 +349,17 @@ k_nw_filter_cta(MrDevParams P, const float* __restrict__ A, const float* __restr
 
 __global__ void k_set_int(int* __restrict__ p, int v) { *p = v; }
 
+// Refine batch set-up in one launch: identity survivor list of `count` items and zeroed
+// per-size outputs (what k_iota + four memsets did)
+__global__ void k_refine_prep(int* __restrict__ surv, int* __restrict__ surv_count, int count, int NP,
+                              float* __restrict__ cost, float* __restrict__ ssd,
+                              unsigned char* __restrict__ valid, int* __restrict__ n_last) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) *surv_count = count;
+  if (t < count) { surv[t] = t; n_last[t] = 0; }
+  if (t < count * NP) { cost[t] = 0.0f; ssd[t] = 0.0f; valid[t] = 0; }
+}
+
 // identity survivor list when the filter is off
 __global__ void k_iota(int* __restrict__ surv, int* __restrict__ surv_count, int count) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -492,7 +503,7 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
   short2* my = scratch + (size_t)(tid >> 5) * 32 * P.N + (tid & 31);
 #define MY(k) my[(size_t)(k) * 32]
   const uint32_t* tbo = tb + (size_t)s * L.words(P.nB);
-  L.walk(tab, tbo, n, P.m, P.nB, [&](int k, int i0, int j0) { MY(k) = make_short2((short)i0, (short)j0); });
+  L.template walk<EMIT>(tab, tbo, n, P.m, P.nB, [&](int k, int i0, int j0) { MY(k) = make_short2((short)i0, (short)j0); });
   float T[12];
   float ssd;
   if (P.refine_while_searching) {
@@ -551,15 +562,25 @@ __global__ void k_gather_orient(const float* __restrict__ orient, const int* __r
 __global__ void k_superimpose_pairs_batch(MrDevParams P, const float* __restrict__ A,
                                           const float* __restrict__ B, const short2* __restrict__ pairs,
                                           const int* __restrict__ n_of, int N, float* __restrict__ T_out) {
-  if (threadIdx.x != 0) return;
+  // the block stages both molecules and the pair list in shared memory (coalesced); thread 0
+  // then runs the sequential sums from there instead of chasing ~2n dependent global loads
+  extern __shared__ float sp_smem[];
   const int nb = P.nb, b = blockIdx.x, n = n_of[b];
+  float* sA = sp_smem;                    // m*nb*3
+  float* sB = sA + P.m * nb * 3;          // nB*nb*3
+  short2* sp = reinterpret_cast<short2*>(sB + P.nB * nb * 3);  // n pairs
+  for (int k = threadIdx.x; k < P.m * nb * 3; k += blockDim.x) sA[k] = A[k];
+  for (int k = threadIdx.x; k < P.nB * nb * 3; k += blockDim.x) sB[k] = B[k];
   const short2* mine = pairs + (size_t)b * N;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) sp[k] = mine[k];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   float T[12];
   mr_superimpose(n * nb, [&](int a, float* pf, float* pm) {
     const int k = a / nb, q = a - k * nb;
-    const short2 pr = mine[k];
-    const float* f = A + 3 * ((size_t)pr.x * nb + q);
-    const float* mv = B + 3 * ((size_t)pr.y * nb + q);
+    const short2 pr = sp[k];
+    const float* f = sA + 3 * (pr.x * nb + q);
+    const float* mv = sB + 3 * (pr.y * nb + q);
     pf[0] = f[0]; pf[1] = f[1]; pf[2] = f[2];
     pm[0] = mv[0]; pm[1] = mv[1]; pm[2] = mv[2];
   }, T);
