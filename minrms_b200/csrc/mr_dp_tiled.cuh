@@ -645,8 +645,13 @@ static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& 
 // ping-pong form (one FMNMX3 per cell) ~150.  Small pairs have few tiles: several CTAs
 // (orientations) per SM keep the pipes fed; from 320 threads on, one CTA per SM in the
 // ping-pong form is faster than two in the two-min form (config 2: 2.07 vs 2.01 TCUPS).
+#ifdef MR_EXP_PP2
+#define MR_DP_BIG_BUCKETS(X) X(320, 2, true) X(352, 2, true) X(384, 2, true)  // experiment: ping-pong at 2 CTAs/SM (spills)
+#else
+#define MR_DP_BIG_BUCKETS(X) X(320, 1, true) X(352, 1, true) X(384, 1, true)
+#endif
 #define MR_DP_BUCKETS(X) \
-  X(64, 10, false) X(128, 5, false) X(192, 3, false) X(256, 2, false) X(320, 1, true) X(352, 1, true) X(384, 1, true) X(512, 1, true)
+  X(64, 10, false) X(128, 5, false) X(192, 3, false) X(256, 2, false) MR_DP_BIG_BUCKETS(X) X(512, 1, true)
 static inline int mr_dp_tiles_minb(int threads) {
 #define MR_X(MAXT, MINB, PP) if (threads <= MAXT) return MINB;
   MR_DP_BUCKETS(MR_X)
