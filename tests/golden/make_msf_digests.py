@@ -16,7 +16,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CONFIGS = {
     "c1": ["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.5", "-ir", "-r"],
     "c2": ["-fm", "4", "-HS", "-ir", "-r"],
+    # synthetic pairs of make_synth_pdbs.py: 280 x 300 under config-1 flags with a fragment RMSD
+    # cut-off (multi-pass DP, CTA NW filter), and 60 x 66 with four backbone atoms per residue
+    "long": ["-fm", "4,0.6", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "4.0", "-ir", "-r"],
+    "bb": ["-fm", "4", "-HS", "-ir", "-r"],
 }
+MOLS = {"long": ("synth_c.pdb", "synth_d.pdb"), "bb": ("synth_bb1.pdb", "synth_bb2.pdb")}
+PAIR = ("hemoglobin.pdb,*.A", "myoglobin.pdb")
 
 
 def digest_dir(d):
@@ -28,10 +34,13 @@ def digest_dir(d):
     return out
 
 
-def run(exe, args, workdir):
-    for f in ("hemoglobin.pdb", "myoglobin.pdb"):
-        subprocess.check_call(["cp", os.path.join(HERE, f), workdir])
-    subprocess.check_call([exe] + args + ["hemoglobin.pdb,*.A", "myoglobin.pdb"], cwd=workdir,
+def run(exe, args, workdir, cfg=None):
+    mols = MOLS.get(cfg, PAIR)
+    for f in mols:
+        subprocess.check_call(["cp", os.path.join(HERE, f.split(",")[0]), workdir])
+    if cfg == "bb":   # the reference reads the atom names from atoms_used.txt in its cwd
+        subprocess.check_call(["cp", os.path.join(HERE, "atoms_used_backbone.txt"), os.path.join(workdir, "atoms_used.txt")])
+    subprocess.check_call([exe] + args + list(mols), cwd=workdir,
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return digest_dir(workdir)
 
@@ -45,7 +54,7 @@ def main():
             res[cfg] = digest_dir(pre)
         else:
             with tempfile.TemporaryDirectory() as d:
-                res[cfg] = run(exe, args, d)
+                res[cfg] = run(exe, args, d, cfg)
         print(cfg, len(res[cfg]), "files")
     json.dump(res, open(os.path.join(HERE, "msf_digests.json"), "w"), indent=0, sort_keys=True)
 
