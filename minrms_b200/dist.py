@@ -44,16 +44,24 @@ def allreduce_best(table, device=None, group=None):
     dev = device if device is not None else torch.device("cpu")
     world = dist.get_world_size(group)
     keys = keys_from_table(table["ssd"], table["o_id"])
-    rows = np.concatenate([keys.view(np.int32).reshape(R, 2), table["T"].reshape(R, -1).view(np.int32),
-                           table["pairs"].reshape(R, -1).astype(np.int32)], axis=1)
-    mine = torch.from_numpy(np.ascontiguousarray(rows)).to(dev)
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine, group=group)
-    allrows = torch.stack(parts)                                        # [world, R, C]
+    C = 2 + 12 + table["pairs"][0].size
+    rows = np.empty((R, C), np.int32)
+    rows[:, :2] = keys.view(np.int32).reshape(R, 2)
+    rows[:, 2:14] = table["T"].reshape(R, 12).view(np.int32)
+    rows[:, 14:] = table["pairs"].reshape(R, -1)
+    mine = torch.from_numpy(rows).to(dev, non_blocking=True)
+    allrows = torch.empty((world, R, C), dtype=torch.int32, device=dev)
+    try:
+        dist.all_gather_into_tensor(allrows, mine, group=group)
+    except (RuntimeError, NotImplementedError):      # backend without the single-tensor form
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        allrows = torch.stack(parts)
     allkeys = allrows[:, :, :2].contiguous().view(torch.int64).squeeze(-1)   # [world, R]
-    red, owner = allkeys.min(dim=0)
-    pay = allrows[owner, torch.arange(R, device=allrows.device)].cpu().numpy()
-    red_np = red.cpu().numpy()
+    owner = allkeys.argmin(dim=0)                                       # first rank on (impossible) ties
+    sel = allrows[owner, torch.arange(R, device=allrows.device)]        # [R, C]: the owners' rows
+    pay = sel.cpu().numpy()
+    red_np = np.ascontiguousarray(pay[:, :2]).view(np.int64).reshape(R)
     none = red_np == KEY_NONE
     ssd = (red_np >> 32).astype(np.uint32).view(np.float32).copy()
     o_id = (red_np & 0xFFFFFFFF).astype(np.int64)
