@@ -81,6 +81,7 @@ struct mr_ctx {
   char* h_ref = nullptr;             // pinned staging
   size_t ref_off_n = 0, ref_off_ssd = 0, ref_off_valid = 0, ref_off_nlast = 0, ref_off_T = 0, ref_off_pairs = 0;
   int64_t opt_refine_batch = 0;      // 0: all flagged sizes per batch; k > 0: at most k (1 = sequential)
+  int ref_host_item = -1;            // batch item whose transforms / alignments sit in the pinned buffer
   int* h_pinned = nullptr;      // surv counts per chunk
   int h_pinned_cap = 0;
   long long id_offset = 0;
@@ -928,7 +929,7 @@ static int refine_alloc(mr_ctx* c) {
 }
 
 // evaluate the stored alignments of the sizes n_min + r, r in `rs`, as one batch
-static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* best) {
+static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* best, int first_item) {
   const int N = c->N, NP = c->NP, n_min = c->hp.n_min, k = (int)rs.size();
   short2* hp = reinterpret_cast<short2*>(c->h_ref);
   int* hn = reinterpret_cast<int*>(c->h_ref + c->ref_off_n);
@@ -963,6 +964,14 @@ static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* b
   CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_ssd, c->d_ssd, 4 * (size_t)NP * k, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_valid, c->d_valid, (size_t)NP * k, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_nlast, c->d_nlast, 4 * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  // the item consumed first (the median that triggered the batch) usually improves something:
+  // its transforms and alignments ride along instead of costing a round trip later
+  CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_T, c->d_ref_T + 12 * (size_t)NP * first_item, 48 * (size_t)NP,
+                        cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_pairs, c->d_ref_pairs + 2 * (size_t)N * NP * first_item,
+                        4 * (size_t)N * NP, cudaMemcpyDeviceToHost, c->stream));
+  c->ref_host_item = first_item;
+  c->st.d2h_bytes += (int64_t)NP * (48 + 4 * N);
   if (dbg) cudaEventRecord(e1, c->stream);
   CU(c, cudaStreamSynchronize(c->stream));
   if (dbg) {
@@ -1019,7 +1028,7 @@ int mr_refine(mr_ctx* c, mr_best* best, int32_t max_iters, int32_t* n_evals) {
       int lo = std::max(0, pos - kmax / 2);
       lo = std::min(lo, std::max(0, (int)flagged.size() - kmax));
       rs.assign(flagged.begin() + lo, flagged.begin() + std::min<int>((int)flagged.size(), lo + kmax));
-      if (refine_launch(c, rs, best)) return 1;
+      if (refine_launch(c, rs, best, pos - lo)) return 1;
       std::fill(item_of.begin(), item_of.end(), -1);
       for (int b = 0; b < (int)rs.size(); b++) item_of[rs[b]] = b;
     }
@@ -1034,12 +1043,15 @@ int mr_refine(mr_ctx* c, mr_best* best, int32_t max_iters, int32_t* n_evals) {
       const size_t slot = (size_t)b * NP + (m2 - 1);
       if (m2 > n_max || !h_valid[slot] || !(h_ssd[slot] < best->ssd[m2 - n_min])) continue;  // strict <, :2515
       if (!fetched) {  // transforms and alignments of this item, once
-        CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_T, c->d_ref_T + 12 * (size_t)NP * b, 48 * (size_t)NP,
-                              cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_pairs, c->d_ref_pairs + 2 * (size_t)N * NP * b,
-                              4 * (size_t)N * NP, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        c->st.d2h_bytes += (int64_t)NP * (48 + 4 * N);
+        if (c->ref_host_item != b) {
+          CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_T, c->d_ref_T + 12 * (size_t)NP * b, 48 * (size_t)NP,
+                                cudaMemcpyDeviceToHost, c->stream));
+          CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_pairs, c->d_ref_pairs + 2 * (size_t)N * NP * b,
+                                4 * (size_t)N * NP, cudaMemcpyDeviceToHost, c->stream));
+          CU(c, cudaStreamSynchronize(c->stream));
+          c->st.d2h_bytes += (int64_t)NP * (48 + 4 * N);
+          c->ref_host_item = b;
+        }
         fetched = true;
       }
       const int r = m2 - n_min;
