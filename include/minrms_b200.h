@@ -128,6 +128,17 @@ int mr_gen_orientations(mr_ctx *ctx, int32_t frag_len, float cutoff_rmsd,
 int mr_superimpose_batch(mr_ctx *ctx, int32_t batch, int32_t np, const float *fixed,
                          const float *moveable, float *T, float *rmsd);
 
+/* Replaces the per-size loop of SearchOrDyn3d::WritePlotFile
+ * (bin/minrms/search_or_dyn3d.cc:2703-2760), i.e. the rows of align_chimera.plot: for every
+ * size of `best`, PairwiseAlignment::FindFurthestResPair and LevittGerstein98::Sstr_Score
+ * (lib/pair_alignment/pair_alignment.cc:2351-2379, 2690-2790) run on the GPU at the stored
+ * transform; the closed form of Sstr_Probability (2798-2925) is evaluated per size on the host
+ * in the reference's long double arithmetic.  ca_index = position of the " CA" atom among
+ * the nb atoms used per residue (Biopolymer::Residue::LookupBackboneAtomSymbol).
+ * rows: R x 9 doubles {has solution, rmsd, longest distance, S_str, mu_str, delta_str, Z,
+ * probability, -log10(probability)}; the reference prints columns n, 1, 2 and 8. */
+int mr_plot_stats(mr_ctx *ctx, const mr_best *best, int32_t ca_index, double *rows);
+
 /* Counters for the benchmark (reset by mr_reset_stats). */
 typedef struct mr_stats {
   int64_t kernel_launches;   /* kernels of this library launched */

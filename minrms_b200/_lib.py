@@ -31,7 +31,7 @@ class MrStats(C.Structure):
 EXPORTS = ["mr_create", "mr_destroy", "mr_last_error", "mr_best_init", "mr_search",
            "mr_upload_orientations", "mr_search_resident", "mr_reset_best", "mr_fetch_best",
            "mr_fetch_keys", "mr_eval_one", "mr_refine", "mr_gen_orientations",
-           "mr_superimpose_batch", "mr_get_stats", "mr_reset_stats", "mr_set_option",
+           "mr_superimpose_batch", "mr_plot_stats", "mr_get_stats", "mr_reset_stats", "mr_set_option",
            "mr_dp_cells_per_orientation", "mr_event_record", "mr_event_elapsed_ms"]
 
 _lib = None
@@ -66,6 +66,7 @@ def load():
     L.mr_gen_orientations.argtypes = [vp, C.c_int32, C.c_float, C.POINTER(C.c_int32), C.c_int32,
                                       C.c_int32, fp, C.c_int64, C.POINTER(C.c_int64)]
     L.mr_superimpose_batch.argtypes = [vp, C.c_int32, C.c_int32, fp, fp, fp, fp]
+    L.mr_plot_stats.argtypes = [vp, C.POINTER(MrBest), C.c_int32, C.POINTER(C.c_double)]
     L.mr_get_stats.argtypes = [vp, C.POINTER(MrStats)]
     L.mr_reset_stats.argtypes = [vp]
     L.mr_event_record.argtypes = [vp, C.c_int32]

@@ -1089,6 +1089,96 @@ int mr_superimpose_batch(mr_ctx* c, int32_t batch, int32_t np, const float* fixe
   return 0;
 }
 
+// The probability of LevittGerstein98::Sstr_Probability (lib/pair_alignment/
+// pair_alignment.cc:2798-2925) from the score the GPU produced: a closed form per size in the
+// reference's long double arithmetic (its constants are double literals; log of a float and
+// of doubles are the float / double functions, exp of a long double is expl).
+static void sstr_probability(float S_str, int n, float out4[4]) {
+  const long double c = 18.411424, d = -4.501719, e = 2.637163, f = 21.351857, g = -37.521269;
+  const long double ln120 = log(120.0);
+  const long double a = 2.0 * ln120 * c + d;
+  const long double b = ln120 * ln120 * c + ln120 * d + e - a * ln120;
+  const long double lnN = logf((float)n);
+  const long double S = S_str;
+  long double mu, delta;
+  if (n < 120) {
+    mu = c * (lnN * lnN);
+    mu += d * lnN;
+    mu += e;
+    delta = f * lnN;
+    delta += g;
+  } else {
+    mu = a * lnN;
+    mu += b;
+    delta = f * ln120 + g;
+  }
+  const long double Z = (S - mu) / delta;
+  const long double result = (Z < log(10000.0 / 2)) ? 1.0f - expl(-expl(-Z)) : expl(-Z);
+  out4[0] = (float)mu;
+  out4[1] = (float)delta;
+  out4[2] = (float)Z;
+  out4[3] = (float)result;
+}
+
+int mr_plot_stats(mr_ctx* c, const mr_best* best, int32_t ca_index, double* rows) {
+  if (!c) return 1;
+  if (!best || !best->ssd || !best->T || !best->pairs || !rows) MR_FAIL(c, "mr_plot_stats: null argument");
+  const int nb = c->hp.nb, R = c->R, N = c->N;
+  if (ca_index < 0 || ca_index >= nb)
+    MR_FAIL(c, "mr_plot_stats: the C-alpha atom must be one of the %d atoms used per residue (index %d)", nb, ca_index);
+  CU(c, cudaSetDevice(c->device));
+  for (int r = 0; r < R; r++) {
+    if (!(best->ssd[r] < MR_UPPER_BOUND)) continue;
+    int pi = -1, pj = -1;
+    for (int k = 0; k < c->hp.n_min + r; k++) {
+      const int i = best->pairs[(size_t)r * 2 * N + 2 * k], j = best->pairs[(size_t)r * 2 * N + 2 * k + 1];
+      if (i <= pi || j <= pj || i >= c->m || j >= c->nB)
+        MR_FAIL(c, "mr_plot_stats: size %d: pair %d = (%d,%d) is not an ascending alignment", c->hp.n_min + r, k, i, j);
+      pi = i; pj = j;
+    }
+  }
+  const size_t b_ssd = (size_t)R * 4, b_T = (size_t)R * 48, b_pairs = (size_t)R * 2 * N * 2;
+  char* d = nullptr;
+  const size_t off_T = (b_ssd + 15) & ~(size_t)15, off_pairs = off_T + b_T, off_far = (off_pairs + b_pairs + 15) & ~(size_t)15,
+               off_s = off_far + b_ssd, off_has = off_s + b_ssd, total = off_has + b_ssd;
+  CU(c, cudaMalloc(&d, total));
+  std::vector<float> far(R), sstr(R);
+  std::vector<int> has(R);
+  cudaError_t e = cudaMemcpyAsync(d, best->ssd, b_ssd, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_T, best->T, b_T, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + off_pairs, best->pairs, b_pairs, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    k_plot_stats<<<R, 32, 2 * (size_t)N * sizeof(float), c->stream>>>(
+        nb, ca_index, c->hp.n_min, N, c->dA, c->dB, (const float*)d, (const float*)(d + off_T),
+        (const short*)(d + off_pairs), (float*)(d + off_far), (float*)(d + off_s), (int*)(d + off_has));
+    e = cudaGetLastError();
+    c->st.kernel_launches++;
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(far.data(), d + off_far, b_ssd, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sstr.data(), d + off_s, b_ssd, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(has.data(), d + off_has, b_ssd, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  CU(c, e);
+  c->st.h2d_bytes += (int64_t)(b_ssd + b_T + b_pairs);
+  c->st.d2h_bytes += (int64_t)(3 * b_ssd);
+  for (int r = 0; r < R; r++) {
+    double* o = rows + 9 * (size_t)r;
+    for (int k = 0; k < 9; k++) o[k] = 0.0;
+    if (!has[r]) continue;
+    const int n = c->hp.n_min + r;
+    float s4[4];
+    sstr_probability(sstr[r], n, s4);
+    o[0] = 1.0;
+    o[1] = sqrtf(best->ssd[r] / (n * nb));  // search_or_dyn3d.cc:2719-2721
+    o[2] = far[r];
+    o[3] = sstr[r];
+    o[4] = s4[0]; o[5] = s4[1]; o[6] = s4[2]; o[7] = s4[3];
+    o[8] = (s4[3] == 0.0) ? 0.0 : -log10f(s4[3]);  // :2755
+  }
+  return 0;
+}
+
 // glibc rand() in its never-seeded state (TYPE_3 additive feedback generator, seed 1):
 // std::random_shuffle in lib/or_gen/or_gen.cc:179 is driven by it.
 namespace {

@@ -621,3 +621,64 @@ __global__ void k_select(MrDevParams P, int NP, const int* __restrict__ surv,
   }
   if (n_last_out) n_last_out[s] = n_last;
 }
+
+// ---------------------------------------------------------------------------
+// K8: per-size statistics of align_chimera.plot (SearchOrDyn3d::WritePlotFile,
+// bin/minrms/search_or_dyn3d.cc:2703-2760): one warp per size r of a best table.
+//   furthest[r] = FindFurthestResPair (lib/pair_alignment/pair_alignment.cc:2351-2379,
+//                 84-105): sqrt of the largest per-pair sum over the nb atoms of squared
+//                 distances between A_i and T.B_j -- a max, so lanes take pairs k, k+32, ...
+//   sstr[r]     = LevittGerstein98::Sstr_Score (pair_alignment.cc:2690-2790): sum over the
+//                 pairs, in order, of 20 / (1 + d_CA^2 / 25) minus 10 per gap.  The terms
+//                 (transform, distance, division) are produced by all lanes into shared
+//                 memory; lane 0 then adds them in the reference's order (float addition
+//                 is not associative).
+// Transform = ApplyTransformBackbone (lib/biopolymer/apply_trans.cc:72-108) of the two
+// atoms involved only.  Sizes without a solution are skipped (has[r] = 0).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_plot_stats(int nb, int ca, int n_min, int N, const float* __restrict__ A, const float* __restrict__ B,
+             const float* __restrict__ ssd, const float* __restrict__ T12, const short* __restrict__ pairs,
+             float* __restrict__ furthest, float* __restrict__ sstr, int* __restrict__ has) {
+  extern __shared__ float plot_terms[];  // [N] S_str terms, then [N] gap flags (as float 0 / 1)
+  const int r = blockIdx.x, lane = threadIdx.x, n = n_min + r;
+  if (!(ssd[r] < MR_UB)) {
+    if (lane == 0) { has[r] = 0; furthest[r] = 0.0f; sstr[r] = 0.0f; }
+    return;
+  }
+  const float* T = T12 + 12 * (size_t)r;
+  const short* pr = pairs + (size_t)r * 2 * N;
+  float* term = plot_terms;
+  float* gap = plot_terms + N;
+  float far = 0.0f;
+  for (int k = lane; k < n; k += 32) {
+    const int i = pr[2 * k], j = pr[2 * k + 1];
+    float c = 0.0f, dca = 0.0f;
+    for (int q = 0; q < nb; q++) {
+      const float* a = A + 3 * ((size_t)i * nb + q);
+      const float* b = B + 3 * ((size_t)j * nb + q);
+      float x, y, z;
+      mr_xform(T, b[0], b[1], b[2], x, y, z);
+      const float d = mr_d2(a[0], a[1], a[2], x, y, z);
+      c += d;
+      if (q == ca) dca = d;
+    }
+    far = fmaxf(far, c);
+    term[k] = 20.0f / (1 + (dca / 25.0f));
+    const int pi = (k > 0) ? pr[2 * k - 2] : -1, pj = (k > 0) ? pr[2 * k - 1] : -1;
+    gap[k] = (k > 0 && (i - pi - 1) + (j - pj - 1) > 0) ? 1.0f : 0.0f;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) far = fmaxf(far, __shfl_xor_sync(0xffffffffu, far, off));
+  __syncwarp();
+  if (lane == 0) {
+    float total = 0.0f;
+    for (int k = 0; k < n; k++) {
+      total += term[k];
+      if (gap[k] != 0.0f) total -= 10.0f;
+    }
+    has[r] = 1;
+    furthest[r] = sqrtf(far);
+    sstr[r] = total;
+  }
+}

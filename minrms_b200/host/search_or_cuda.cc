@@ -4,6 +4,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <thread>
 
@@ -143,6 +144,60 @@ void SearchOrCuda::Refine()
   Check(ctx[0], mr_refine(ctx[0], &mine, (int32_t)iters, &evals));
   TableFromHost(mine);
   cout << "(During refinement, " << evals + 1 << " new orientations were tested on the GPU.)" << endl;
+}
+
+// search_or_dyn3d.cc:2942-2996.  The rows of the plot (WritePlotFile, 2662-2760: longest
+// matched distance, Levitt-Gerstein probability) come from mr_plot_stats; the streaming and
+// number formatting are the reference's (default ostream precision, same value types).
+void SearchOrCuda::WriteChimeraInfo() const
+{
+  const int nb = Biopolymer::Residue::NumBackboneAtoms();
+  int ca = -1;
+  for (int q = 0; q < nb; ++q)
+    if (strcmp(Biopolymer::Residue::LookupBackboneAtomSymbol(q), " CA") == 0) ca = q;
+  if (ca < 0) {  // S_str needs C-alpha atoms that the search never moved: the reference's own path
+    SearchOrDyn3d::WriteChimeraInfo();
+    return;
+  }
+  WritePlotFileCuda(ca);
+  string info_name = string(SearchOrDyn3d::BASE_FILE_NAME) + "_chimera.info";
+  ofstream info_file(info_name.c_str(), ios::out);
+  if (!info_file) ERR_INTERNAL("Cannot open file \"" << info_name << "\" for writing.  Exiting...");
+  info_file << "fixed pdb:" << settings.vPdbFileNames[0] << "\n";
+  info_file << "moveable pdb:" << settings.vPdbFileNames[1] << "\n";
+  info_file << "rmsd:" << SearchOrDyn3d::BASE_FILE_NAME << "_chimera.plot\n";
+  info_file << "base:" << SearchOrDyn3d::BASE_FILE_NAME << "\n";
+  info_file << "number of atoms used:" << nb << "\n";
+  for (int q = 0; q < nb; ++q) info_file << Biopolymer::Residue::LookupBackboneAtomSymbol(q) << "\n";
+}
+
+void SearchOrCuda::WritePlotFileCuda(int ca_index) const
+{
+  vector<float> vs(R), vT(12 * R);
+  vector<int16_t> vp((size_t)2 * N * R, 0);
+  for (int r = 0; r < R; ++r) {
+    vs[r] = aaSumSqdDists[0][r];
+    memcpy(&vT[12 * r], &aaTransforms[0][r][0][0], 12 * sizeof(float));
+    if (!(vs[r] < DistanceMetric::UPPER_BOUND)) continue;
+    for (int k = 0; k < n_min + r; ++k) {
+      vp[(size_t)2 * N * r + 2 * k] = aaAlignments[0][r][k][0];
+      vp[(size_t)2 * N * r + 2 * k + 1] = aaAlignments[0][r][k][1];
+    }
+  }
+  mr_best t;
+  t.ssd = &vs[0]; t.T = &vT[0]; t.pairs = &vp[0]; t.o_id = NULL;
+  vector<double> rows((size_t)9 * R);
+  Check(ctx[0], mr_plot_stats(ctx[0], &t, ca_index, &rows[0]));
+  string plot_name = string(SearchOrDyn3d::BASE_FILE_NAME) + "_chimera.plot";
+  ofstream plot_file(plot_name.c_str(), ios::out);
+  if (!plot_file) ERR_INTERNAL("WritePlotFile() cannot create file \"" << plot_name << "\" for writing.");
+  plot_file << "# Matches,RMSD,Longest Distance" << ",-log(probability)\n";
+  for (int r = 0; r < R; ++r) {
+    const double* o = &rows[(size_t)9 * r];
+    if (o[0] == 0.0) continue;
+    // rmsd and distance are Real in the reference, the last column a double (2719-2755)
+    plot_file << n_min + r << " " << (float)o[1] << " " << (float)o[2] << " " << o[8] << "\n";
+  }
 }
 
 }  // namespace minrms

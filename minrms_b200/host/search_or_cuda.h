@@ -28,12 +28,16 @@ class SearchOrCuda : public SearchOrDyn3d {
   // SearchOr interface (bin/minrms/search_or.h:87-114)
   void Search(OrientationGenerator const& og, long start, long stop);
   void Refine();
+  // SearchOr::WriteChimeraInfo (search_or.h:125-129): align_chimera.info as the reference
+  // writes it and align_chimera.plot with its per-size statistics computed on the GPU
+  void WriteChimeraInfo() const;
 
  private:
   SearchOrCuda(SearchOrCuda const&);
   SearchOrCuda& operator=(SearchOrCuda const&);
   void TableToHost(mr_best& t);   // reference tables -> flat C-ABI table
   void TableFromHost(mr_best const& t);
+  void WritePlotFileCuda(int ca_index) const;
   std::vector<mr_ctx*> ctx;       // one per GPU ($MINRMS_CUDA_GPUS, default 1)
   std::vector<float> ssd, T;
   std::vector<int16_t> pairs;

@@ -27,6 +27,7 @@ def _fp(a):
 @dataclass
 class Settings:
     nb: int = 1                                   # atoms per residue (" CA" by default)
+    ca_index: int = 0                             # position of " CA" among those atoms (atoms_used.txt order)
     n_min: int = 1                                # -minN
     n_max: int = 0                                # -maxN (0 = min(m, n))
     dyn3d_max_dist: float = -1.0                  # -max-dist (NO_MAX_PHYS_DISTANCE = -1)
@@ -213,6 +214,33 @@ class SearchOrCuda:
     def best_table(self):
         return dict(ssd=self.aSumSqdDists[:self.R].copy(), T=self.aTransforms[:self.R].copy(),
                     pairs=self.aAlignments[:self.R].copy(), o_id=self.aOrientationIds[:self.R].copy())
+
+    # -- output statistics -----------------------------------
+    def plot_stats(self, table=None):
+        """Rows of align_chimera.plot for the stored table (or `table` = dict(ssd, T, pairs)):
+        float64 [R, 9] = {has solution, rmsd, longest distance, S_str, mu_str, delta_str, Z,
+        probability, -log10(probability)} (SearchOrDyn3d::WritePlotFile,
+        search_or_dyn3d.cc:2703-2760)."""
+        best = self._best
+        if table is not None:
+            keep = [np.ascontiguousarray(table["ssd"], np.float32), np.ascontiguousarray(table["T"], np.float32),
+                    np.ascontiguousarray(table["pairs"], np.int16)]
+            best = _lib.MrBest(_fp(keep[0]), _fp(keep[1]), keep[2].ctypes.data_as(C.POINTER(C.c_int16)), None)
+        rows = np.zeros((max(self.R, 1), 9), np.float64)
+        self._check(self.lib.mr_plot_stats(self.ctx, C.byref(best), self.settings.ca_index,
+                                           rows.ctypes.data_as(C.POINTER(C.c_double))))
+        return rows[:self.R]
+
+    def WritePlotFile(self, path="align_chimera.plot"):
+        """The file SearchOr::WriteChimeraInfo -> WritePlotFile writes (search_or_dyn3d.cc:2662-2760);
+        numbers are formatted like the reference's ostream (6 significant digits)."""
+        rows = self.plot_stats()
+        with open(path, "w") as f:
+            f.write("# Matches,RMSD,Longest Distance,-log(probability)\n")
+            for r in range(self.R):
+                if rows[r, 0] == 0.0:
+                    continue
+                f.write("%d %g %g %g\n" % (self.n_min + r, rows[r, 1], rows[r, 2], rows[r, 8]))
 
     def rmsd(self, n):
         """RMSD of the stored size-n alignment as WriteMSF prints it (search_or_dyn3d.cc:2878)."""

@@ -9,7 +9,7 @@
 #   flavour "strict" = no fast-math, no FMA contraction                 -> Oracle-S
 #
 # Outputs per flavour: libminrms_ref.a (all lib/* objects), minrms (the CLI), and the
-# drivers ref_dump / ref_bench (oracle/*.cc linked against the reference objects).
+# drivers ref_dump / ref_bench / ref_plot (oracle/*.cc linked against the reference objects).
 set -e
 REF=${REF:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -60,7 +60,7 @@ build_flavour() {
   rm -f $O/libminrms_bin.a
   ar rcs $O/libminrms_bin.a $binobjs
   g++ -o $O/minrms $O/obj/bin_main.o $O/libminrms_bin.a $O/libminrms_ref.a
-  for drv in ref_dump ref_bench; do
+  for drv in ref_dump ref_bench ref_plot; do
     if [ -f $HERE/$drv.cc ]; then
       g++ -std=c++11 $FLAGS -w $INC $HERE/$drv.cc $O/libminrms_bin.a $O/libminrms_ref.a -o $O/$drv
     fi

@@ -756,3 +756,119 @@ int orc_refine(orc_ws *w, const float *A, const float *B, orc_best *best, int ma
   free(old);
   return evals;
 }
+
+/* ------------------------------------------------------------------------------------
+ * Per-size statistics of align_chimera.plot.
+ * bin/minrms/search_or_dyn3d.cc:2703-2760 (WritePlotFile) */
+
+/* lib/pair_alignment/pair_alignment.cc:84-105 (SumSqdDistBetweenResidues) with
+ * lib/vect_3d/vect_3d.h:268-276: every atom's dot product is summed left to right and
+ * accumulated into a float that starts at 0. */
+static float sum_sqd_dist_residues(const float *A, int i, const float *Bp, int j, int nb)
+{
+  float out = 0.0f;
+  int q;
+  for (q = 0; q < nb; q++) {
+    const float *a = A + 3 * ((size_t)i * nb + q), *b = Bp + 3 * ((size_t)j * nb + q);
+    float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    out += dx * dx + dy * dy + dz * dz;
+  }
+  return out;
+}
+
+/* lib/pair_alignment/pair_alignment.cc:2351-2379 (FindFurthestResPair) */
+static float furthest_res_pair(const float *A, const float *Bp, int nb, const int16_t *pairs, int n)
+{
+  float furthest = 0.0f;
+  int k;
+  for (k = 0; k < n; k++) {
+    float c = sum_sqd_dist_residues(A, pairs[2 * k], Bp, pairs[2 * k + 1], nb);
+    if (c > furthest || k == 0) furthest = c;
+  }
+  return sqrtf(furthest);
+}
+
+/* lib/pair_alignment/pair_alignment.cc:2690-2790 (LevittGerstein98::Sstr_Score):
+ * M = 20, d_o = 5, gap opening 10, gap extension 0; C-alpha atoms only. */
+static float sstr_score(const float *A, const float *Bp, int nb, int ca, const int16_t *pairs, int n)
+{
+  const float M = 20.0f, d_o_sqrd = 5.0f * 5.0f;
+  float total = 0.0f;
+  int prev_i = -1, prev_j = -1, k;
+  for (k = 0; k < n; k++) {
+    const int i = pairs[2 * k], j = pairs[2 * k + 1];
+    const float *a = A + 3 * ((size_t)i * nb + ca), *b = Bp + 3 * ((size_t)j * nb + ca);
+    float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    float d2 = dx * dx + dy * dy + dz * dz;
+    int gap;
+    total += M / (1 + (d2 / d_o_sqrd));
+    gap = (i - prev_i - 1) + (j - prev_j - 1);
+    if (gap > 0 && prev_i != -1) total -= (10.0f + (gap - 1) * 0.0f);
+    prev_i = i;
+    prev_j = j;
+  }
+  return total;
+}
+
+/* lib/pair_alignment/pair_alignment.cc:2798-2925 (LevittGerstein98::Sstr_Probability):
+ * long double arithmetic on constants that are double literals; log() of a float and of
+ * doubles resolve to the float / double overloads, exp() of a long double to expl. */
+void orc_sstr_probability(float S_str_f, int n, float out4[4] /* mu, delta, Z, probability */)
+{
+  const long double c = 18.411424, d = -4.501719, e = 2.637163, f = 21.351857, g = -37.521269;
+  const long double ln120 = log(120.0);
+  const long double a = 2.0 * ln120 * c + d;
+  const long double b = ln120 * ln120 * c + ln120 * d + e - a * ln120;
+  long double mu, delta, Z, result;
+  const long double lnN = logf((float)n);
+  const long double S = S_str_f;
+  if (n < 120) {
+    mu = c * (lnN * lnN);
+    mu += d * lnN;
+    mu += e;
+    delta = f * lnN;
+    delta += g;
+  } else {
+    mu = a * lnN;
+    mu += b;
+    delta = f * ln120 + g;
+  }
+  Z = (S - mu) / delta;
+  if (Z < log(10000.0 / 2))
+    result = 1.0f - expl(-expl(-Z));
+  else
+    result = expl(-Z);
+  out4[0] = (float)mu;
+  out4[1] = (float)delta;
+  out4[2] = (float)Z;
+  out4[3] = (float)result;
+}
+
+/* One row of the plot per size of a best table: out[9 r ..] = {has solution, rmsd,
+ * furthest distance, S_str, mu_str, delta_str, Z, probability, -log10(probability)} as
+ * WritePlotFile evaluates them (search_or_dyn3d.cc:2703-2760).  ca = index of the " CA"
+ * atom among the nb atoms used per residue. */
+void orc_plot_stats(const float *A, int m, const float *B, int nB, int nb, int ca, int n_min,
+                    int R, int N, const orc_best *best, double *out)
+{
+  float *Bp = (float *)malloc(sizeof(float) * 3 * (size_t)nB * nb);
+  int r;
+  (void)m;
+  for (r = 0; r < R; r++) {
+    const int n = n_min + r;
+    double *o = out + 9 * (size_t)r;
+    const int16_t *pairs = best->pairs + (size_t)r * 2 * N;
+    float s4[4], S;
+    memset(o, 0, 9 * sizeof(double));
+    if (!(best->ssd[r] < ORC_UPPER_BOUND)) continue;
+    o[0] = 1.0;
+    o[1] = sqrtf(best->ssd[r] / (n * nb));
+    orc_apply_transform(best->T + 12 * (size_t)r, B, nB * nb, Bp);
+    o[2] = furthest_res_pair(A, Bp, nb, pairs, n);
+    S = sstr_score(A, Bp, nb, ca, pairs, n);
+    orc_sstr_probability(S, n, s4);
+    o[3] = S; o[4] = s4[0]; o[5] = s4[1]; o[6] = s4[2]; o[7] = s4[3];
+    o[8] = (s4[3] == 0.0) ? 0.0 : -log10f(s4[3]);
+  }
+  free(Bp);
+}

@@ -112,6 +112,14 @@ int64_t orc_search(orc_ws *ws, const float *A, const float *B, const float *orie
  * max_iters < 0 = iterate until convergence.  Returns number of evaluations done. */
 int orc_refine(orc_ws *ws, const float *A, const float *B, orc_best *best, int max_iters);
 
+/* Statistics of align_chimera.plot for every size of a best table
+ * (bin/minrms/search_or_dyn3d.cc:2703-2760; lib/pair_alignment/pair_alignment.cc:84-105,
+ * 2351-2379, 2690-2925).  out: R x 9 doubles {has, rmsd, furthest distance, S_str, mu_str,
+ * delta_str, Z, probability, -log10(probability)}; ca = index of " CA" among the nb atoms. */
+void orc_plot_stats(const float *A, int m, const float *B, int nB, int nb, int ca, int n_min,
+                    int R, int N, const orc_best *best, double *out);
+void orc_sstr_probability(float S_str, int n, float out4[4] /* mu, delta, Z, probability */);
+
 /* closed-form / counted number of Dyn3d cells for all layers 1..n_max */
 int64_t orc_dp_cells(int m, int nB, int n_min, int n_max);
 

@@ -66,6 +66,9 @@ def lib():
         L.orc_search.argtypes = [C.c_void_p, fp, fp, fp, C.c_int64, C.c_int64, C.POINTER(OrcBest)]
         L.orc_refine.restype = C.c_int
         L.orc_refine.argtypes = [C.c_void_p, fp, fp, C.POINTER(OrcBest), C.c_int]
+        L.orc_plot_stats.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(OrcBest), C.POINTER(C.c_double)]
+        L.orc_sstr_probability.argtypes = [C.c_float, C.c_int, fp]
         L.orc_dp_cells.restype = C.c_int64
         L.orc_dp_cells.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         _lib = L
@@ -188,6 +191,21 @@ class Workspace:
     def refine(self, best, max_iters=-1):
         return lib().orc_refine(self.ws, _fp(self.A), _fp(self.B),
                                 C.byref(self._best_struct(best)), max_iters)
+
+
+def plot_stats(A, B, nb, ca, n_min, ssd, T, pairs):
+    """Rows of align_chimera.plot for a best table: [R][9] float64 (see orc_plot_stats)."""
+    A = np.ascontiguousarray(A, np.float32)
+    B = np.ascontiguousarray(B, np.float32)
+    ssd = np.ascontiguousarray(ssd, np.float32)
+    T = np.ascontiguousarray(T, np.float32)
+    pairs = np.ascontiguousarray(pairs, np.int16)
+    R, N = pairs.shape[0], pairs.shape[1]
+    b = OrcBest(_fp(ssd), _fp(T), pairs.ctypes.data_as(C.POINTER(C.c_int16)), None)
+    out = np.zeros((R, 9), np.float64)
+    lib().orc_plot_stats(_fp(A), A.size // (3 * nb), _fp(B), B.size // (3 * nb), nb, ca, n_min, R, N,
+                         C.byref(b), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
 
 
 def dp_cells(m, nB, n_min, n_max):

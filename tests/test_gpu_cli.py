@@ -37,6 +37,9 @@ def test_cli_config1_side_by_side(tmp_path):
     got = run(EXE, CONFIGS["c1"], str(a))
     ref = run(REF, CONFIGS["c1"], str(b))
     assert got == ref and len(ref) == 96      # align47..141.msf + align_chimera.plot
+    # SearchOrCuda::WriteChimeraInfo writes the plot from mr_plot_stats and the info file itself
+    assert (a / "align_chimera.info").read_bytes() == (b / "align_chimera.info").read_bytes()
+    assert (a / "align_chimera.plot").read_bytes() == (b / "align_chimera.plot").read_bytes()
 
 
 @pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref not built")
