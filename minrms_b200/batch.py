@@ -17,7 +17,7 @@ from dataclasses import dataclass, replace
 import numpy as np
 
 from .search import (OrientationGenerator, SearchOrCuda, Settings, dp_cells_per_orientation,
-                     interpret_num_matches, load_ca_pdb, MinrmsError, UPPER_BOUND)
+                     interpret_num_matches, load_ca_pdb, NoOrientationsError, UPPER_BOUND)
 
 
 def pair_cost(m, n, settings):
@@ -82,10 +82,13 @@ def pair_settings(settings, m, n, min_n=None, max_n=None, of_min=None):
     return s
 
 
-def search_pair(A, B, settings, device=0, refine=True):
-    """One `minrms A B` run: FirstPass over every orientation, then Refine."""
+def search_pair(A, B, settings, device=0, refine=True, budget_mb=None):
+    """One `minrms A B` run: FirstPass over every orientation, then Refine.
+    budget_mb: cap of the chunk work space of this context (several contexts share a GPU)."""
     s = SearchOrCuda(A, B, settings, device=device)
     try:
+        if budget_mb:
+            s.set_option("budget_mb", budget_mb)
         og = OrientationGenerator(s)
         s.Search(og, 0, og.size())
         evals = 0
@@ -100,24 +103,46 @@ def search_pair(A, B, settings, device=0, refine=True):
 
 
 def all_vs_all(chains, settings=None, rank=0, world=1, device=0, refine=True, min_n=None,
-               max_n=None, of_min=None, on_result=None):
+               max_n=None, of_min=None, on_result=None, workers=1):
     """Search this rank's share of all unordered pairs of `chains` (list of float32 [len*nb, 3]
     arrays).  Pairs too short for the fragment size are skipped like the reference refuses them
     (lib/or_gen/or_gen.cc:548-580).  Returns {(i, j): PairResult}; `on_result(i, j, result)` is
-    called as each pair finishes (e.g. to write it out)."""
+    called as each pair finishes (e.g. to write it out).
+
+    workers > 1: that many host threads take pairs from the rank's list, each with its own
+    context (own stream and work space) on the same GPU, so that the set-up, the latency-bound
+    Refine batches and the copies of one pair overlap the DP kernels of another.  The result
+    of a pair does not depend on which thread ran it."""
     settings = settings or Settings()
     nb = settings.nb
     lengths = [c.shape[0] // nb for c in chains]
+    mine = schedule(lengths, world, settings)[rank]
     out = {}
-    for (i, j) in schedule(lengths, world, settings)[rank]:
+    # several contexts on one GPU share its memory: 140 GB of chunk work space between them
+    budget_mb = None if workers <= 1 else min(32768, 140000 // workers)
+
+    def run(p):
+        i, j = p
         ps = pair_settings(settings, lengths[i], lengths[j], min_n, max_n, of_min)
         try:
-            res = search_pair(chains[i], chains[j], ps, device=device, refine=refine)
-        except MinrmsError:
+            return p, search_pair(chains[i], chains[j], ps, device=device, refine=refine, budget_mb=budget_mb)
+        except NoOrientationsError:
+            return p, None     # the reference refuses such a pair; every other failure propagates
+
+    if workers <= 1:
+        done = map(run, mine)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=workers)
+        done = pool.map(run, mine)     # results in list order, pairs run `workers` at a time
+    for (i, j), res in done:
+        if res is None:
             continue
         out[(i, j)] = res
         if on_result is not None:
             on_result(i, j, res)
+    if workers > 1:
+        pool.shutdown()
     return out
 
 
@@ -132,13 +157,14 @@ def main(argv=None):
     ap.add_argument("--fm", type=int, default=4)
     ap.add_argument("--minN", type=float, default=None)
     ap.add_argument("--no-refine", action="store_true")
+    ap.add_argument("--workers", type=int, default=2, help="host threads (contexts) per GPU")
     a = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     device = int(os.environ.get("LOCAL_RANK", 0))
     files = sorted(glob.glob(os.path.join(a.dir, "*.pdb")))
     chains = [load_ca_pdb(f) for f in files]
     res = all_vs_all(chains, Settings(fm_fragment_size=a.fm), rank, world, device,
-                     refine=not a.no_refine, min_n=a.minN,
+                     refine=not a.no_refine, min_n=a.minN, workers=a.workers,
                      on_result=lambda i, j, r: print("%s %s: %d sizes, rmsd(N=%d) %.4f" % (
                          os.path.basename(files[i]), os.path.basename(files[j]), len(r.sizes()),
                          r.sizes()[-1] if r.sizes() else 0, r.rmsd(r.sizes()[-1]) if r.sizes() else 0.0),

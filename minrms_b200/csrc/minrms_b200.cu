@@ -206,19 +206,25 @@ const TbTiled& tiled_layout(const mr_ctx* c) { return dp_path(c) == 2 ? c->tiled
 // and the next context on that device picks it up: in an all-vs-all run cudaMalloc +
 // cudaFree of 32 GB cost ~0.5 s per pair, as much as the search itself.
 static std::mutex g_arena_mu;
-static Arena g_arena_cache[64];
+constexpr int kArenaSlots = 4;  // per device: contexts of concurrent host threads (all-vs-all workers) each park one
+static Arena g_arena_cache[64][kArenaSlots];
 
 static void arena_release(mr_ctx* c) {  // stream must be idle
   if (!c->arena.base) return;
   std::lock_guard<std::mutex> lk(g_arena_mu);
-  Arena& slot = g_arena_cache[c->device & 63];
-  if (slot.size < c->arena.size) std::swap(slot, c->arena);
+  Arena* slots = g_arena_cache[c->device & 63];
+  Arena* smallest = &slots[0];
+  for (int k = 1; k < kArenaSlots; k++)
+    if (slots[k].size < smallest->size) smallest = &slots[k];
+  if (smallest->size < c->arena.size) std::swap(*smallest, c->arena);
   if (c->arena.base) cudaFree(c->arena.base);
   c->arena = Arena();
 }
 static size_t arena_cached_bytes(const mr_ctx* c) {
   std::lock_guard<std::mutex> lk(g_arena_mu);
-  return g_arena_cache[c->device & 63].size;
+  size_t sum = 0;  // all of it is given back when a larger arena has to be made
+  for (int k = 0; k < kArenaSlots; k++) sum += g_arena_cache[c->device & 63][k].size;
+  return sum;
 }
 // make c->arena at least `bytes` large (contents are lost)
 static int arena_reserve(mr_ctx* c, size_t bytes) {
@@ -226,13 +232,18 @@ static int arena_reserve(mr_ctx* c, size_t bytes) {
   cudaStreamSynchronize(c->stream);
   {
     std::lock_guard<std::mutex> lk(g_arena_mu);
-    Arena& slot = g_arena_cache[c->device & 63];
-    if (slot.size >= bytes) {
-      std::swap(slot, c->arena);  // ours (smaller or none) is parked instead
-      if (slot.base) { cudaFree(slot.base); slot = Arena(); }
+    Arena* slots = g_arena_cache[c->device & 63];
+    Arena* fit = nullptr;  // smallest parked arena that is large enough
+    for (int k = 0; k < kArenaSlots; k++)
+      if (slots[k].size >= bytes && (!fit || slots[k].size < fit->size)) fit = &slots[k];
+    if (fit) {
+      std::swap(*fit, c->arena);  // ours (smaller or none) is parked instead
+      if (fit->base) { cudaFree(fit->base); *fit = Arena(); }
       return 0;
     }
-    if (slot.base) { cudaFree(slot.base); slot = Arena(); }
+    // nothing fits: parked arenas are only in the way of the allocation below
+    for (int k = 0; k < kArenaSlots; k++)
+      if (slots[k].base) { cudaFree(slots[k].base); slots[k] = Arena(); }
   }
   if (c->arena.base) cudaFree(c->arena.base);
   c->arena = Arena();
@@ -262,7 +273,7 @@ int ensure_chunk(mr_ctx* c, int64_t want) {
   if (c->budget_is_default && budget < per_o * (size_t)wave && want > (int64_t)(budget / per_o)) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      // our arena and the parked one are given back before a larger one is made
+      // our arena and the parked ones are given back before a larger one is made
       const size_t held = c->arena.size + arena_cached_bytes(c);
       budget = std::max(budget, std::min(per_o * (size_t)wave + ((size_t)64 << 20), (size_t)(0.8 * (double)(free_b + held))));
     }

@@ -408,6 +408,10 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
       }
       // parity of the exchange set written at step s: s & 1
       uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
+#ifdef MR_EXP_UNROLL
+      constexpr int kUnroll = MR_EXP_UNROLL;
+#pragma unroll kUnroll
+#endif
       for (; s <= warp_hi; s++) {
         // C(i, j) for my R rows: ring column j & 31 (columns <= 0 and > nB hold +inf)
         float cv[R];
@@ -439,11 +443,19 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
             const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
             const float d = dg + cv[r];
             const float left = st[k][r];
+#ifdef MR_EXP_MIN3IP
+            // experiment: one FMNMX3 with the state updated in place (register renaming + copies
+            // at the loop back-edge are left to ptxas)
+            const float best = fminf(fminf(d, up), left);
+            const float s1 = __fsub_rn(d, up);
+            const float s2 = __fsub_rn(best, left);
+#else
             // two 2-input mins so the new value overwrites `left` in place (no register copy)
             const float t = fminf(d, up);
             const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
             const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
             const float best = fminf(t, left);
+#endif
             acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
             acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
             st[k][r] = best;
@@ -647,6 +659,8 @@ static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& 
 // ping-pong form is faster than two in the two-min form (config 2: 2.07 vs 2.01 TCUPS).
 #ifdef MR_EXP_PP2
 #define MR_DP_BIG_BUCKETS(X) X(320, 2, true) X(352, 2, true) X(384, 2, true)  // experiment: ping-pong at 2 CTAs/SM (spills)
+#elif defined(MR_EXP_BIG2)
+#define MR_DP_BIG_BUCKETS(X) X(320, 2, false) X(352, 2, false) X(384, 2, false)  // experiment: in-place forms at 2 CTAs/SM
 #else
 #define MR_DP_BIG_BUCKETS(X) X(320, 1, true) X(352, 1, true) X(384, 1, true)
 #endif

@@ -20,6 +20,10 @@ class MinrmsError(RuntimeError):
     """Raised where the reference would ERR(...) -> exit(-1) (lib/global_utils/ERR.h:20-21)."""
 
 
+class NoOrientationsError(MinrmsError):
+    """the orientation generator has no fragment pair to fit (lib/or_gen/or_gen.cc:548-580)"""
+
+
 def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
@@ -262,7 +266,7 @@ class OrientationGenerator:
         search._check(lib.mr_gen_orientations(search.ctx, s.fm_fragment_size, s.fm_cutoff_rmsd, iv, niv,
                                               int(shuffle), None, 0, C.byref(cnt)))
         if cnt.value == 0:
-            raise MinrmsError("Error: there are no valid regions from which to draw the "
+            raise NoOrientationsError("Error: there are no valid regions from which to draw the "
                               "%d residue blocks (lib/or_gen/or_gen.cc:548-580)" % s.fm_fragment_size)
         self.orientations = np.zeros((cnt.value, 12), np.float32)
         search._check(lib.mr_gen_orientations(search.ctx, s.fm_fragment_size, s.fm_cutoff_rmsd, iv, niv,

@@ -16,7 +16,8 @@ t0 = time.perf_counter()
 last=[time.perf_counter()]
 def show(i,j,r):
     now=time.perf_counter(); print('pair %d-%d (%dx%d) %d orientations: %.1f ms' % (i,j,lens[i],lens[j],r.orientations,(now-last[0])*1e3), flush=True); last[0]=now
-res = all_vs_all(chains, st, refine=False, on_result=show if len(sys.argv)>2 else None)
+import os
+res = all_vs_all(chains, st, refine=bool(int(os.environ.get('C5_REFINE','1'))), on_result=show if len(sys.argv)>2 else None, workers=int(os.environ.get('C5_WORKERS','1')))
 t1 = time.perf_counter()
 ori = sum(r.orientations for r in res.values())
 print('%d chains (%d..%d residues), %d pairs, %d orientations, %.3e DP cells: %.2f s -> %.2f pairs/s, %.0f orientations/s, %.0f GCUPS end to end' % (

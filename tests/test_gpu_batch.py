@@ -15,13 +15,15 @@ def _chains():
     return [base] + [related_chain(rng, base, n, noise=0.7) for n in lens[1:]]
 
 
-def test_all_vs_all_matches_oracle_pair_by_pair():
+@pytest.mark.parametrize("workers", [1, 3])
+def test_all_vs_all_matches_oracle_pair_by_pair(workers):
+    """workers = 3: three host threads, each with its own context on the GPU, share the list"""
     from minrms_b200 import Settings
     from minrms_b200.batch import all_vs_all
     chains = _chains()
     st = Settings(fm_fragment_size=4)
     seen = []
-    res = all_vs_all(chains, st, on_result=lambda i, j, r: seen.append((i, j)))
+    res = all_vs_all(chains, st, on_result=lambda i, j, r: seen.append((i, j)), workers=workers)
     # every pair of the four long chains; pairs with the 3-residue chain are refused
     # (no 4-residue fragment, lib/or_gen/or_gen.cc:548-580)
     want = {(i, j) for i in range(4) for j in range(i + 1, 4)}
