@@ -263,8 +263,9 @@ class OrientationGenerator:
             self._iv = np.ascontiguousarray(intervals, np.int32).reshape(-1, 4)
             iv, niv = self._iv.ctypes.data_as(C.POINTER(C.c_int32)), self._iv.shape[0]
         cnt = C.c_int64(0)
-        search._check(lib.mr_gen_orientations(search.ctx, s.fm_fragment_size, s.fm_cutoff_rmsd, iv, niv,
-                                              int(shuffle), None, 0, C.byref(cnt)))
+        if s.fm_fragment_size <= search.N:   # a longer fragment fits nowhere: count stays 0
+            search._check(lib.mr_gen_orientations(search.ctx, s.fm_fragment_size, s.fm_cutoff_rmsd, iv, niv,
+                                                  int(shuffle), None, 0, C.byref(cnt)))
         if cnt.value == 0:
             raise NoOrientationsError("Error: there are no valid regions from which to draw the "
                               "%d residue blocks (lib/or_gen/or_gen.cc:548-580)" % s.fm_fragment_size)
