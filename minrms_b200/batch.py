@@ -148,8 +148,10 @@ def all_vs_all(chains, settings=None, rank=0, world=1, device=0, refine=True, mi
 
 def main(argv=None):
     """python -m minrms_b200.batch DIR [--out results.npz] [--fm L] [--minN x] [--no-refine]
+    [--workers k] [--msf-dir OUT]
     One rank per GPU under torchrun (RANK / WORLD_SIZE / LOCAL_RANK); each rank writes its own
-    file (results.rank<k>.npz) -- there is nothing to reduce."""
+    file (results.rank<k>.npz) -- there is nothing to reduce.  --msf-dir: also write, per pair,
+    OUT/<a>__<b>/align<n>.msf in the reference's format (minrms_b200/msf.py)."""
     import argparse
     ap = argparse.ArgumentParser(description=main.__doc__)
     ap.add_argument("dir")
@@ -157,18 +159,36 @@ def main(argv=None):
     ap.add_argument("--fm", type=int, default=4)
     ap.add_argument("--minN", type=float, default=None)
     ap.add_argument("--no-refine", action="store_true")
-    ap.add_argument("--workers", type=int, default=2, help="host threads (contexts) per GPU")
+    ap.add_argument("--workers", type=int, default=None,
+                    help="host threads (contexts) per GPU; default 4 with Refine, 1 without")
+    ap.add_argument("--msf-dir", default=None)
     a = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     device = int(os.environ.get("LOCAL_RANK", 0))
     files = sorted(glob.glob(os.path.join(a.dir, "*.pdb")))
     chains = [load_ca_pdb(f) for f in files]
+    names = [os.path.basename(f) for f in files]
+    seqs = None
+    if a.msf_dir:
+        from .msf import pdb_sequence, write_msf_files
+        seqs = [pdb_sequence(f) for f in files]
+        for f, c, q in zip(files, chains, seqs):   # the search and the sequence must index the same residues
+            if c.shape[0] != len(q):
+                raise SystemExit("%s: %d residues but %d with a CA atom; MSF output needs the index map "
+                                 "(write_msf_files(index_a=..., index_b=...))" % (f, len(q), c.shape[0]))
+
+    def report(i, j, r):
+        sizes = r.sizes()
+        print("%s %s: %d sizes, rmsd(N=%d) %.4f" % (names[i], names[j], len(sizes), sizes[-1] if sizes else 0,
+                                                  r.rmsd(sizes[-1]) if sizes else 0.0), flush=True)
+        if seqs is not None:
+            d = os.path.join(a.msf_dir, "%s__%s" % (os.path.splitext(names[i])[0], os.path.splitext(names[j])[0]))
+            os.makedirs(d, exist_ok=True)
+            write_msf_files(d, r, seqs[i], seqs[j], names[i], names[j])
+
+    workers = a.workers if a.workers else (1 if a.no_refine else 4)
     res = all_vs_all(chains, Settings(fm_fragment_size=a.fm), rank, world, device,
-                     refine=not a.no_refine, min_n=a.minN, workers=a.workers,
-                     on_result=lambda i, j, r: print("%s %s: %d sizes, rmsd(N=%d) %.4f" % (
-                         os.path.basename(files[i]), os.path.basename(files[j]), len(r.sizes()),
-                         r.sizes()[-1] if r.sizes() else 0, r.rmsd(r.sizes()[-1]) if r.sizes() else 0.0),
-                         flush=True))
+                     refine=not a.no_refine, min_n=a.minN, workers=workers, on_result=report)
     out = a.out if world == 1 else a.out.replace(".npz", ".rank%d.npz" % rank)
     np.savez_compressed(out, files=np.array(files), **{
         "%d_%d_%s" % (i, j, k): getattr(r, k) for (i, j), r in res.items() for k in ("ssd", "T", "pairs")})

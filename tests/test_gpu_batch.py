@@ -54,3 +54,26 @@ def test_all_vs_all_ranks_partition_the_pairs():
             w = whole[key]
             assert r.n_min == w.n_min == max(1, int(np.floor(0.5 * min(chains[key[0]].shape[0], chains[key[1]].shape[0]) + 0.5)))
             assert np.array_equal(r.ssd.view(np.uint32), w.ssd.view(np.uint32)) and np.array_equal(r.pairs, w.pairs)
+
+
+def test_batch_cli_writes_the_reference_s_msf_files(tmp_path):
+    """`python -m minrms_b200.batch DIR --msf-dir OUT` on the reference's test pair = config 2
+    (-fm 4 -HS -ir -r): the 140 align<n>.msf files must hash to the digests of the files the
+    unmodified reference binary wrote (tests/golden/msf_digests.json)"""
+    import json
+    import os
+    import shutil
+    import sys
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    from make_msf_digests import digest_dir
+    from minrms_b200.batch import main
+    src = tmp_path / "pdb"
+    src.mkdir()
+    for f in ("hemoglobin.pdb", "myoglobin.pdb"):
+        shutil.copy(os.path.join(gold, f), str(src))
+    assert main([str(src), "--out", str(tmp_path / "r.npz"), "--msf-dir", str(tmp_path / "msf"), "--workers", "2"]) == 0
+    want = {k: v for k, v in json.load(open(os.path.join(gold, "msf_digests.json")))["c2"].items() if k.endswith(".msf")}
+    got = digest_dir(str(tmp_path / "msf" / "hemoglobin__myoglobin"))
+    assert sorted(got) == sorted(want) and len(got) == 140
+    assert not [f for f in want if got[f] != want[f]]
