@@ -165,7 +165,9 @@ int mr_event_elapsed_ms(mr_ctx *ctx, int32_t slot_a, int32_t slot_b, float *ms);
 /* Tuning knobs (by name): "dp_kernel" = 0 auto / 1 general / 2 tiled single-pass /
  * 3 tiled multi-pass; "budget_mb", "chunk" (work space per chunk of orientations);
  * "refine_batch" = 0 all flagged sizes per Refine batch / k at most k (1 = sequential);
- * "nw_kernel" = 1 thread-per-orientation filter; "mp_threads" (tests). */
+ * "refine_split" = 0 keeps one CTA per orientation in the DP of Refine batches (default 1: the
+ * passes of the multi-pass kernel run on a cluster of CTAs); "nw_kernel" = 1
+ * thread-per-orientation filter; "mp_threads" (tests). */
 int mr_set_option(mr_ctx *ctx, const char *name, int64_t value);
 
 /* number of Dyn3d cells per orientation for all layers 1..n_max */

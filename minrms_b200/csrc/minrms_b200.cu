@@ -77,10 +77,11 @@ struct mr_ctx {
   int* d_ref_n = nullptr;            // [kcap]
   float* d_ref_orient = nullptr;     // [kcap][12]
   float* d_ref_T = nullptr;          // [kcap][NP][12]
-  short* d_ref_pairs = nullptr;      // [kcap][NP][2N]
+  int ref_slice_warps = 0;           // warps of traceback threads that can cover one item's sizes
   char* h_ref = nullptr;             // pinned staging
   size_t ref_off_n = 0, ref_off_ssd = 0, ref_off_valid = 0, ref_off_nlast = 0, ref_off_T = 0, ref_off_pairs = 0;
   int64_t opt_refine_batch = 0;      // 0: all flagged sizes per batch; k > 0: at most k (1 = sequential)
+  int64_t opt_refine_split = 1;      // Refine batches of the multi-pass DP: passes of an orientation on a cluster of CTAs
   int ref_host_item = -1;            // batch item whose transforms / alignments sit in the pinned buffer
   int* h_pinned = nullptr;      // surv counts per chunk
   int h_pinned_cap = 0;
@@ -323,7 +324,9 @@ int ensure_chunk(mr_ctx* c, int64_t want) {
 }
 
 // launch the 3-D DP for the survivors of the current chunk
-int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count) {
+// latency: a few orientations whose result the host waits for (Refine batches): the multi-pass
+// kernel then spreads the passes of an orientation over a cluster of CTAs (split mode)
+int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count, bool latency = false) {
   EventPair* ev = next_events(c, 0);
   if (!ev) MR_FAIL(c, "cudaEventCreate failed");
   CU(c, cudaEventRecord(ev->a, c->stream));
@@ -334,7 +337,8 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count) {
       MR_FAIL(c, "tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else if (path == 2) {
     if (mr_launch_dp_tiled_mp(c->tiled_mp, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
-                              c->d_tb, c->d_cost, count, c->stream) != 0)
+                              c->d_tb, c->d_cost, count, c->stream,
+                              latency && c->opt_refine_split && count <= c->tiled_mp.split_cap) != 0)
       MR_FAIL(c, "multi-pass tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else {
     if (c->use_gcol && !c->d_gcol) CU(c, cudaMalloc(&c->d_gcol, c->gcol_bytes));
@@ -351,9 +355,10 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count) {
 
 template <bool EMIT>
 int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* items, int n_items,
-              float* d_T = nullptr, short* d_pairs = nullptr) {
+              float* d_T = nullptr, short* d_pairs = nullptr, bool pairs_in_scratch = false) {
   if (!d_T) d_T = c->d_Tout;
   if (!d_pairs) d_pairs = c->d_pairs_out;
+  if (pairs_in_scratch) d_pairs = nullptr;  // the pair lists stay in the per-thread scratch slices
   const int n_lo = std::max(2, c->hp.n_min);
   const int per = c->hp.n_max - n_lo + 1;
   const int64_t threads = items ? n_items : (int64_t)count * std::max(per, 0);
@@ -711,7 +716,7 @@ void mr_destroy(mr_ctx* c) {
   cudaFree(c->d_surv_all); cudaFree(c->d_nw_all);
   cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w);
   cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
-  cudaFree(c->d_ref_pairs_in); cudaFree(c->d_ref_n); cudaFree(c->d_ref_orient); cudaFree(c->d_ref_T); cudaFree(c->d_ref_pairs);
+  cudaFree(c->d_ref_pairs_in); cudaFree(c->d_ref_n); cudaFree(c->d_ref_orient); cudaFree(c->d_ref_T);
   if (c->h_ref) cudaFreeHost(c->h_ref);
   mr_free_dp_tiled(&c->tiled);
   mr_free_dp_tiled_mp(&c->tiled_mp);
@@ -734,6 +739,7 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
   else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);
   else if (!strcmp(name, "refine_batch")) c->opt_refine_batch = std::max<int64_t>(0, value);
+  else if (!strcmp(name, "refine_split")) c->opt_refine_split = value != 0;
   else if (!strcmp(name, "mp_threads")) {
     if (value != 0 && (value < 32 || value > 1024 || value % 32)) MR_FAIL(c, "mr_set_option: mp_threads must be a multiple of 32 in [32, 1024]");
     c->opt_mp_threads = value;
@@ -920,23 +926,53 @@ static int find_median(const std::vector<char>& in_set, int n_min, int n_max) {
 static int refine_alloc(mr_ctx* c) {
   if (c->ref_kcap > 0) return 0;
   const size_t N = (size_t)c->N, NP = (size_t)c->NP;
-  const size_t per_item = NP * (48 + 4 * N);
+  const size_t per_item = NP * 48 + 4 * N;
   int kcap = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->R, ((size_t)1 << 30) / per_item));
   CU(c, cudaMalloc(&c->d_ref_pairs_in, sizeof(short2) * N * kcap));
   CU(c, cudaMalloc(&c->d_ref_n, sizeof(int) * kcap));
   CU(c, cudaMalloc(&c->d_ref_orient, 48 * (size_t)kcap));
   CU(c, cudaMalloc(&c->d_ref_T, 48 * NP * kcap));
-  CU(c, cudaMalloc(&c->d_ref_pairs, 4 * N * NP * kcap));
-  // pinned staging: pairs_in | n | ssd | valid | n_last | T (one item) | pairs (one item)
+  // The alignments of a batch are NOT written out per (item, size): the traceback threads'
+  // scratch slices (warp-interleaved, [warp][pair][lane]) hold them already, and only the few
+  // items the replay consumes are fetched -- as the raw slices of the warps that cover the
+  // item's sizes -- and de-interleaved on the host.
+  const int per = std::max(1, c->hp.n_max - std::max(2, c->hp.n_min) + 1);
+  c->ref_slice_warps = (per + 31) / 32 + 1;
+  // pinned staging: pairs_in | n | ssd | valid | n_last | T (one item) | raw pair slices (one item)
   c->ref_off_n = sizeof(short2) * N * kcap;
   c->ref_off_ssd = c->ref_off_n + sizeof(int) * kcap;
   c->ref_off_valid = c->ref_off_ssd + 4 * NP * kcap;
   c->ref_off_nlast = (c->ref_off_valid + NP * kcap + 15) & ~(size_t)15;
   c->ref_off_T = c->ref_off_nlast + sizeof(int) * kcap;
   c->ref_off_pairs = (c->ref_off_T + 48 * NP + 15) & ~(size_t)15;
-  CU(c, cudaMallocHost(&c->h_ref, c->ref_off_pairs + 4 * N * NP));
+  CU(c, cudaMallocHost(&c->h_ref, c->ref_off_pairs + sizeof(short2) * 32 * N * (size_t)c->ref_slice_warps));
   c->ref_kcap = kcap;
   return 0;
+}
+
+// Refine batch item b = traceback threads [b * per, (b + 1) * per): copy the scratch slices of
+// the warps that cover them to the pinned buffer (asynchronous).
+static int refine_fetch_slices(mr_ctx* c, int b) {
+  const int per = std::max(1, c->hp.n_max - std::max(2, c->hp.n_min) + 1);
+  const size_t w_lo = ((size_t)b * per) >> 5, w_hi = ((size_t)(b + 1) * per - 1) >> 5;
+  const size_t bytes = sizeof(short2) * 32 * (size_t)c->N * (w_hi - w_lo + 1);
+  CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_pairs, c->d_scratch + w_lo * 32 * (size_t)c->N, bytes,
+                        cudaMemcpyDeviceToHost, c->stream));
+  c->st.d2h_bytes += (int64_t)bytes;
+  return 0;
+}
+// pair list of (item b, size m2) from the fetched slices -> dst[2 * m2]
+static void refine_unpack_pairs(const mr_ctx* c, int b, int m2, int16_t* dst) {
+  const int n_lo = std::max(2, c->hp.n_min);
+  const int per = std::max(1, c->hp.n_max - n_lo + 1);
+  const size_t tid = (size_t)b * per + (size_t)(m2 - n_lo);
+  const size_t w_lo = ((size_t)b * per) >> 5;
+  const short2* raw = reinterpret_cast<const short2*>(c->h_ref + c->ref_off_pairs) +
+                      ((tid >> 5) - w_lo) * 32 * (size_t)c->N + (tid & 31);
+  for (int k = 0; k < m2; k++) {
+    dst[2 * k] = raw[(size_t)k * 32].x;
+    dst[2 * k + 1] = raw[(size_t)k * 32].y;
+  }
 }
 
 // evaluate the stored alignments of the sizes n_min + r, r in `rs`, as one batch
@@ -966,8 +1002,8 @@ static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* b
                                                             c->d_valid, c->d_nlast);
   CU(c, cudaGetLastError());
   c->st.kernel_launches++;
-  if (launch_dp(c, c->d_ref_orient, k)) return 1;
-  if (launch_tb<true>(c, c->d_ref_orient, k, nullptr, 0, c->d_ref_T, c->d_ref_pairs)) return 1;
+  if (launch_dp(c, c->d_ref_orient, k, true)) return 1;
+  if (launch_tb<true>(c, c->d_ref_orient, k, nullptr, 0, c->d_ref_T, nullptr, true)) return 1;
   k_select<<<(k + 31) / 32, 32, 0, c->stream>>>(c->P, NP, c->d_surv, c->d_surv_count, c->d_cost, c->d_ssd, 0ll,
                                               nullptr, c->d_valid, c->d_nlast);
   CU(c, cudaGetLastError());
@@ -979,10 +1015,9 @@ static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* b
   // its transforms and alignments ride along instead of costing a round trip later
   CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_T, c->d_ref_T + 12 * (size_t)NP * first_item, 48 * (size_t)NP,
                         cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_pairs, c->d_ref_pairs + 2 * (size_t)N * NP * first_item,
-                        4 * (size_t)N * NP, cudaMemcpyDeviceToHost, c->stream));
+  if (refine_fetch_slices(c, first_item)) return 1;
   c->ref_host_item = first_item;
-  c->st.d2h_bytes += (int64_t)NP * (48 + 4 * N);
+  c->st.d2h_bytes += (int64_t)NP * 48;
   if (dbg) cudaEventRecord(e1, c->stream);
   CU(c, cudaStreamSynchronize(c->stream));
   if (dbg) {
@@ -1018,7 +1053,6 @@ int mr_refine(mr_ctx* c, mr_best* best, int32_t max_iters, int32_t* n_evals) {
   const uint8_t* h_valid = reinterpret_cast<const uint8_t*>(c->h_ref + c->ref_off_valid);
   const int* h_nlast = reinterpret_cast<const int*>(c->h_ref + c->ref_off_nlast);
   const float* h_T = reinterpret_cast<const float*>(c->h_ref + c->ref_off_T);
-  const int16_t* h_pairs = reinterpret_cast<const int16_t*>(c->h_ref + c->ref_off_pairs);
   int evals = 0;
   for (int it = 1; it <= max_iters || max_iters < 0; it++) {
     const int n = find_median(need, n_min, n_max);
@@ -1031,6 +1065,8 @@ int mr_refine(mr_ctx* c, mr_best* best, int32_t max_iters, int32_t* n_evals) {
       const int path = dp_path(c);
       const int wave = path == 2 ? c->tiled_mp.grid_cap : path == 1 ? c->tiled.grid_cap : c->dp_grid_cap;
       int kmax = std::min(std::min(c->ref_kcap, c->chunk_cap), std::max(wave, 1));
+      // split mode of the multi-pass kernel: one cluster of CTAs per item, fewer items per wave
+      if (path == 2 && c->opt_refine_split && c->tiled_mp.split_cap > 0) kmax = std::min(kmax, c->tiled_mp.split_cap);
       if (c->opt_refine_batch > 0) kmax = std::min<int>(kmax, (int)c->opt_refine_batch);
       std::vector<int> flagged;
       int pos = 0;
@@ -1057,10 +1093,9 @@ int mr_refine(mr_ctx* c, mr_best* best, int32_t max_iters, int32_t* n_evals) {
         if (c->ref_host_item != b) {
           CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_T, c->d_ref_T + 12 * (size_t)NP * b, 48 * (size_t)NP,
                                 cudaMemcpyDeviceToHost, c->stream));
-          CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_pairs, c->d_ref_pairs + 2 * (size_t)N * NP * b,
-                                4 * (size_t)N * NP, cudaMemcpyDeviceToHost, c->stream));
+          if (refine_fetch_slices(c, b)) return 1;
           CU(c, cudaStreamSynchronize(c->stream));
-          c->st.d2h_bytes += (int64_t)NP * (48 + 4 * N);
+          c->st.d2h_bytes += (int64_t)NP * 48;
           c->ref_host_item = b;
         }
         fetched = true;
@@ -1068,7 +1103,7 @@ int mr_refine(mr_ctx* c, mr_best* best, int32_t max_iters, int32_t* n_evals) {
       const int r = m2 - n_min;
       best->ssd[r] = h_ssd[slot];
       memcpy(best->T + 12 * r, h_T + 12 * (size_t)(m2 - 1), 48);
-      memcpy(best->pairs + (size_t)r * 2 * N, h_pairs + (size_t)(m2 - 1) * 2 * N, sizeof(int16_t) * 2 * (size_t)m2);
+      refine_unpack_pairs(c, b, m2, best->pairs + (size_t)r * 2 * N);
       if (best->o_id) best->o_id[r] = -2;
       if (m2 != n) need[r] = 1;  // :2546
       item_of[r] = -1;           // its alignment changed: a result computed from the old one is void

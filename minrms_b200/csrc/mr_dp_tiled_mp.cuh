@@ -29,7 +29,29 @@ struct MrPass {
   int w0, nstrips;   // first strip and number of strips of the pass
   int nsteps;        // columns (even) + strips - 1
   int gid_off;       // global id of thread 0's tile
+  int lag;           // split mode: step s of this pass runs at tick lag + s
+  int ticks;         // split mode: ticks of the whole orientation (max over passes of lag + nsteps)
 };
+
+// Split mode (template parameter SPLIT): the passes of ONE orientation run concurrently on the
+// CTAs of a thread-block cluster (CTA rank = pass), pipelined through the carry buffer: pass p
+// runs lag_p = sum over the passes above it of (strips + MR_SPLIT_GROUP) steps behind pass 0, and
+// every MR_SPLIT_GROUP-th per-step barrier is a cluster barrier (release / acquire, which also
+// orders the L2 carry traffic): a carry column is written at least one cluster barrier before
+// the pass below prefetches it.  The sweep of
+// an orientation then takes columns + all strips (+ passes) ticks instead of passes x (columns
+// + strips): the latency of a single evaluation, which is what Refine batches wait for.
+// Throughput per SM is lower (cluster barriers, idle head and tail ticks): FirstPass keeps one
+// CTA per orientation.
+#define MR_SPLIT_GROUP 8  // ticks between cluster barriers (a cluster barrier costs ~0.8 us, a CTA barrier ~0.1)
+__device__ __forceinline__ void mr_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned mr_cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 
 struct MrTileMp {
   int w, c;              // global row strip, layer chunk (-1: idle thread)
@@ -40,7 +62,7 @@ struct MrTileMp {
   int pad_;
 };
 
-template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP>
+template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP, bool SPLIT = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, const MrPass* __restrict__ passes,
               const MrTileMp* __restrict__ tiles, const float* __restrict__ A, const float* __restrict__ B,
@@ -61,7 +83,12 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
   float* sA = sB + 3 * nBp;
   const float INF = __int_as_float(0x7f800000);
   const int nsurv = *surv_count;
-  float4* carry = carry_all + (size_t)blockIdx.x * carry_pitch;
+  // split mode: the cluster (npasses CTAs) owns the orientation slot, the CTA rank is the pass
+  const int slot = SPLIT ? (int)blockIdx.x / npasses : (int)blockIdx.x;
+  const int nslots_grid = SPLIT ? (int)gridDim.x / npasses : (int)gridDim.x;
+  const int ps_first = SPLIT ? (int)mr_cluster_ctarank() : 0;
+  const int ps_end = SPLIT ? ps_first + 1 : npasses;
+  float4* carry = carry_all + (size_t)slot * carry_pitch;
 
   const uint32_t exch0 = (uint32_t)__cvta_generic_to_shared(exch);
   const uint32_t par_bytes = (uint32_t)nslots * 48u;
@@ -70,7 +97,9 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
   const uint32_t cr0 = (uint32_t)__cvta_generic_to_shared(Cr);
   for (int k = tid; k < m * nb * 3; k += nthreads) sA[k] = A[k];
 
-  for (int sv = blockIdx.x; sv < nsurv; sv += gridDim.x) {
+// split mode: a cluster barrier every MR_SPLIT_GROUP ticks (tick = lag + step), CTA barriers in between
+#define MR_MP_SYNC(S) do { if (SPLIT && ((tick0 + (S)) & (MR_SPLIT_GROUP - 1)) == 0) mr_cluster_sync(); else __syncthreads(); } while (0)
+  for (int sv = slot; sv < nsurv; sv += nslots_grid) {
     const float* T = orient + 12 * (size_t)surv[sv];
     __syncthreads();
     for (int k = tid; k < nBp; k += nthreads) {
@@ -84,7 +113,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
     }
     uint4* const tb_o = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB));
 
-    for (int ps = 0; ps < npasses; ps++) {
+    for (int ps = ps_first; ps < ps_end; ps++) {
       const MrPass pass = passes[ps];
       const MrTileMp* ptiles = tiles + (size_t)ps * nthreads;
       const MrTileMp me = ptiles[tid];
@@ -116,6 +145,12 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
       for (int k = tid; k < MR_CRING * WRp; k += nthreads) Cr[k] = INF;
       __syncthreads();
       mr_produce_c<NB1>(Cr, sA, sB, 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+      const int tick0 = pass.lag;
+      if constexpr (SPLIT) {
+        __syncthreads();
+        for (int t = 1; t <= pass.lag; t++)  // the passes above are that far ahead
+          if ((t & (MR_SPLIT_GROUP - 1)) == 0) mr_cluster_sync();
+      }
 
       int s = 1;
       if constexpr (PP) {
@@ -138,7 +173,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
         for (; s < warp_lo && s <= nsteps; s++) {
           if ((s & (MR_CBATCH - 1)) == 0)
             mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
-          __syncthreads();
+          MR_MP_SYNC(s);
         }
         const uint32_t off_a = (s & 1) ? 0u : par_bytes, off_b = par_bytes - off_a;
         float4 gnext = make_float4(INF, INF, INF, INF);
@@ -218,7 +253,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
           }
           if ((s & (MR_CBATCH - 1)) == 0)
             mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
-          __syncthreads();
+          MR_MP_SYNC(s);
         };
         // the plan makes every warp window an even number of steps
         for (; s < warp_hi; s += 2) {
@@ -244,7 +279,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
         for (; s < warp_lo && s <= nsteps; s++) {
           if ((s & (MR_CBATCH - 1)) == 0)
             mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
-          __syncthreads();
+          MR_MP_SYNC(s);
         }
         uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
         // upper boundary of the first strip: column j = s of the carry, fetched one step ahead
@@ -331,16 +366,20 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
           if ((s & (MR_CBATCH - 1)) == 0)
             mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
           { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
-          __syncthreads();
+          MR_MP_SYNC(s);
         }
       }
       for (; s <= nsteps; s++) {
         if ((s & (MR_CBATCH - 1)) == 0)
           mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
-        __syncthreads();
+        MR_MP_SYNC(s);
       }
+      if constexpr (SPLIT)
+        for (int t = pass.lag + nsteps + 1; t <= pass.ticks; t++)  // the passes below finish
+          if ((t & (MR_SPLIT_GROUP - 1)) == 0) mr_cluster_sync();
     }
   }
+#undef MR_MP_SYNC
 }
 
 // ---------------------------------------------------------------------------------- host
@@ -354,6 +393,8 @@ struct MrTiledMpPlan {
   int grid_cap = 0;
   size_t tb_words = 0, carry_pitch = 0;
   double lane_efficiency = 0.0;
+  int split_ticks = 0;   // split mode: ticks per orientation
+  int split_cap = 0;     // split mode: orientations (clusters of npasses CTAs) resident at once; 0 = not available
   TbTiled layout;
   MrPass* d_passes = nullptr;
   MrTileMp* d_tiles = nullptr;
@@ -438,7 +479,7 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
       cnt += per_strip[w1++];
     remaining -= cnt;
     MrPass ps;
-    ps.w0 = w0; ps.nstrips = w1 - w0; ps.nsteps = nBe + (w1 - w0) - 1; ps.gid_off = 0;
+    ps.w0 = w0; ps.nstrips = w1 - w0; ps.nsteps = nBe + (w1 - w0) - 1; ps.gid_off = 0; ps.lag = 0; ps.ticks = 0;
     passes.push_back(ps);
     w0 = w1;
   }
@@ -503,6 +544,19 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
     }
   }
   const int T_total = gid;
+  // split mode: pass q runs lag_q steps behind pass 0: per pass above it, its strips (a column
+  // leaves the pass that many steps after it entered) + the ticks between two cluster barriers
+  int split_ticks = 0;
+  {
+    int lag = 0;
+    for (int q = 0; q < npasses; q++) {
+      passes[q].lag = lag;
+      split_ticks = std::max(split_ticks, lag + passes[q].nsteps);
+      lag += passes[q].nstrips + MR_SPLIT_GROUP;
+    }
+    split_ticks = (split_ticks + MR_SPLIT_GROUP - 1) & ~(MR_SPLIT_GROUP - 1);  // ends on a cluster barrier
+    for (int q = 0; q < npasses; q++) passes[q].ticks = split_ticks;
+  }
   const size_t smem = 16 * (size_t)(6 * nslots) +
                       4 * (size_t)(MR_CRING * mr_ring_stride(wl_max * R) + 3 * ((nB * P.nb + 11) & ~3) + ((m * P.nb * 3 + 3) & ~3));
   if (smem > prop.sharedMemPerBlockOptin) { p->why = "work space does not fit shared memory"; return; }
@@ -524,6 +578,10 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
   p->pp = pp;
   p->threads = threads; p->minb = minb; p->nslots = nslots; p->npasses = npasses; p->wl_max = wl_max;
   p->smem = smem; p->grid_cap = grid_cap; p->carry_pitch = carry_pitch;
+  p->split_ticks = split_ticks;
+  // clusters of up to 8 CTAs are portable; one CTA per SM; GPCs of a B200 hold 16-20 SMs, so a
+  // conservative count of co-resident clusters is enough (more would only queue)
+  p->split_cap = (threads == 512 && npasses >= 2 && npasses <= 8) ? std::max(1, (grid_cap * 3 / 4) / npasses) : 0;
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
   p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = T_total;
   p->layout.tile_of = p->d_tile_of;
@@ -544,9 +602,41 @@ template <int MAXT, int MINB, bool PP>
 static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevParams& P, const float* A,
                                           const float* B, const float* orient, const int* surv,
                                           const int* surv_count, uint32_t* tb, float* cost, int count,
-                                          cudaStream_t stream) {
+                                          cudaStream_t stream, bool split = false) {
   typedef void (*kern_t)(MrDevParams, TbTiled, int, int, int, const MrPass*, const MrTileMp*, const float*,
                          const float*, const float*, const int*, const int*, float4*, size_t, uint32_t*, float*);
+  if constexpr (MAXT == 512 && PP) {
+    if (split && p.split_cap > 0) {
+      // one cluster of npasses CTAs per orientation (see the comment on split mode above)
+      static const kern_t skerns[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false, PP, true>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true, PP, true>,
+                                       k_dp_tiles_mp<4, 8, MAXT, MINB, true, false, PP, true>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true, PP, true>};
+      const kern_t kern = skerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
+      static size_t sattr_set[64] = {0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (sattr_set[dev & 63] < p.smem) {
+        for (int q = 0; q < 4; q++)
+          if (cudaFuncSetAttribute(skerns[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
+        sattr_set[dev & 63] = p.smem;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(std::min(count, p.split_cap) * p.npasses));
+      cfg.blockDim = dim3((unsigned)p.threads);
+      cfg.dynamicSmemBytes = p.smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)p.npasses;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P, p.layout, p.nslots, p.npasses, p.wl_max, (const MrPass*)p.d_passes,
+                                               (const MrTileMp*)p.d_tiles, A, B, orient, surv, surv_count, p.d_carry,
+                                               p.carry_pitch, tb, cost);
+      return e == cudaSuccess ? 0 : 1;
+    }
+  }
   static const kern_t kerns[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false, PP>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true, PP>,
                                   k_dp_tiles_mp<4, 8, MAXT, MINB, true, false, PP>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true, PP>};
   const kern_t kern = kerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
@@ -567,9 +657,9 @@ static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevPar
 static inline int mr_launch_dp_tiled_mp(const MrTiledMpPlan& p, const MrDevParams& P, const float* A,
                                         const float* B, const float* orient, const int* surv,
                                         const int* surv_count, uint32_t* tb, float* cost, int count,
-                                        cudaStream_t stream) {
+                                        cudaStream_t stream, bool split = false) {
 #define MR_TRY(MAXT, MINB, PP) \
-  if (p.threads == MAXT) return mr_launch_dp_tiles_mp_t<MAXT, MINB, PP>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream)
+  if (p.threads == MAXT) return mr_launch_dp_tiles_mp_t<MAXT, MINB, PP>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream, split)
   MR_TRY(512, 1, true);
   MR_TRY(640, 1, false);
   MR_TRY(768, 1, false);

@@ -540,10 +540,14 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
     const size_t e = items ? (size_t)tid : slot;
 #pragma unroll
     for (int k = 0; k < 12; k++) T_out[12 * e + k] = T[k];
-    short* po = pairs_out + e * 2 * P.N;
-    for (int k = 0; k < n; k++) {
-      po[2 * k] = MY(k).x;
-      po[2 * k + 1] = MY(k).y;
+    // pairs_out == NULL: the caller reads the pair lists from the scratch slices themselves
+    // (Refine batches: only a few of the items are ever consumed)
+    if (pairs_out) {
+      short* po = pairs_out + e * 2 * P.N;
+      for (int k = 0; k < n; k++) {
+        po[2 * k] = MY(k).x;
+        po[2 * k + 1] = MY(k).y;
+      }
     }
   }
 }
