@@ -607,19 +607,35 @@ __global__ void k_select(MrDevParams P, int NP, const int* __restrict__ surv,
   if (s >= *surv_count) return;
   const unsigned long long oid = (unsigned long long)(id_base + surv[s]);
   int n_last = min(1, P.n_max);
-  for (int n = 2; n <= P.n_max; n++) {
-    const size_t slot = (size_t)s * NP + (n - 1);
-    n_last = n;
-    if (cost[slot] >= MR_UB) break;
-    if (n >= P.n_min) {
-      const float v = ssd[slot];
-      if (P.max_rmsd >= 0.0f && v > (float)(n * P.nb) * (P.max_rmsd * P.max_rmsd)) break;
-      if (valid) valid[slot] = 1;
-      if (keys && v < MR_UB) {
-        const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | oid;
-        // most candidates lose: a plain (possibly stale, only ever too large) read first
-        // keeps the 64-bit atomics on the ~140 hot addresses rare
-        if (key < *(volatile unsigned long long*)&keys[n - P.n_min]) atomicMin(&keys[n - P.n_min], key);
+  // the loop exits on loaded values, so its loads are fetched eight sizes ahead (rows are padded
+  // to NP, a multiple of 32): one memory latency per eight sizes instead of one per size --
+  // what a Refine batch (a few dozen threads, the host waiting) is bound by
+  bool done = false;
+  for (int n0 = 2; n0 <= P.n_max && !done; n0 += 8) {
+    float cv[8], sv8[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int n = min(n0 + q, NP);
+      cv[q] = cost[(size_t)s * NP + (n - 1)];
+      sv8[q] = ssd[(size_t)s * NP + (n - 1)];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int n = n0 + q;
+      if (done || n > P.n_max) continue;
+      const size_t slot = (size_t)s * NP + (n - 1);
+      n_last = n;
+      if (cv[q] >= MR_UB) { done = true; continue; }
+      if (n >= P.n_min) {
+        const float v = sv8[q];
+        if (P.max_rmsd >= 0.0f && v > (float)(n * P.nb) * (P.max_rmsd * P.max_rmsd)) { done = true; continue; }
+        if (valid) valid[slot] = 1;
+        if (keys && v < MR_UB) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | oid;
+          // most candidates lose: a plain (possibly stale, only ever too large) read first
+          // keeps the 64-bit atomics on the ~140 hot addresses rare
+          if (key < *(volatile unsigned long long*)&keys[n - P.n_min]) atomicMin(&keys[n - P.n_min], key);
+        }
       }
     }
   }
