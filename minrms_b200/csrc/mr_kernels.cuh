@@ -467,8 +467,13 @@ k_dp_columns(MrDevParams P, TbColumns L, const float* __restrict__ A, const floa
 #ifndef MR_TB_MINB
 #define MR_TB_MINB 12
 #endif
+// The emit variant runs a few hundred threads whose result the host waits for (winners'
+// payload, Refine batches): no occupancy target, so no register cap and no spills.
+#ifndef MR_TB_EMIT_MINB
+#define MR_TB_EMIT_MINB 4
+#endif
 template <class Layout, bool EMIT>
-__global__ void __launch_bounds__(128, MR_TB_MINB)
+__global__ void __launch_bounds__(128, EMIT ? MR_TB_EMIT_MINB : MR_TB_MINB)
 k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const float* __restrict__ B,
                    const float* __restrict__ orient, const int* __restrict__ surv,
                    const int* __restrict__ surv_count, const uint32_t* __restrict__ tb,
