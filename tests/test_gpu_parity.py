@@ -416,3 +416,39 @@ def test_single_residue_molecule_has_no_sizes():
     s.Search(IDENT.reshape(1, 12))
     with pytest.raises(MinrmsError):
         s.check_solutions()
+
+
+@pytest.mark.parametrize("case", [
+    # m, nB, nb, n_min, max_dist, max_rmsd
+    (210, 200, 2, 1, -1.0, -1.0),      # two atoms per residue, 2 passes
+    (260, 240, 1, 80, 9.0, 5.0),       # banded windows and both cut-offs
+    (400, 380, 1, 1, -1.0, -1.0),      # 5+ passes on one cluster
+    (640, 600, 1, 1, -1.0, -1.0),      # more passes than a cluster holds: one CTA per orientation
+])
+def test_refine_with_cluster_split_dp_matches_oracle(case):
+    """Refine() on chains beyond one CTA: the DP of its batches runs the passes of an orientation
+    on a cluster of CTAs (split mode of k_dp_tiles_mp).  A bounded number of iterations against
+    the oracle's sequential loop, and against the same library with split mode off."""
+    m, nB, nb, n_min, max_dist, max_rmsd = case
+    rng = np.random.default_rng(17 * m + nB)
+    A = random_chain(rng, m, nb)
+    B, idx = related_chain(rng, A, nB, nb, noise=0.9, return_idx=True)
+    p = oc.make_params(nb=nb, n_min=n_min, n_max=min(m, nB), max_dist=max_dist, max_rmsd=max_rmsd)
+    Ar, Br = A.reshape(m, nb, 3), B.reshape(nB, nb, 3)
+    r, Tgood = oc.superimpose(Ar[idx].reshape(-1, 3), Br[:len(idx)].reshape(-1, 3))
+    ws = oc.Workspace(A, B, p)
+    iters = 8 if m < 600 else 4
+    tables = []
+    for split in (1, 0):
+        s = make_search(A, B, settings_from_params(p, 4))
+        s.set_option("refine_split", split)
+        s.Search(Tgood[None])
+        ev = s.Refine(max_iters=iters)
+        tables.append((ev, s.best_table()))
+        s.close()
+    best = ws.search(Tgood[None])
+    ev = ws.refine(best, max_iters=iters)
+    for got_ev, t in tables:
+        assert got_ev == ev
+        assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "refine")
+    assert np.any(best["ssd"] < 1e26)
