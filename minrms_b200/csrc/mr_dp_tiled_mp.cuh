@@ -581,7 +581,9 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
   p->split_ticks = split_ticks;
   // clusters of up to 8 CTAs are portable; one CTA per SM; GPCs of a B200 hold 16-20 SMs, so a
   // conservative count of co-resident clusters is enough (more would only queue)
-  p->split_cap = (threads == 512 && npasses >= 2 && npasses <= 8) ? std::max(1, (grid_cap * 3 / 4) / npasses) : 0;
+  // (9..16 passes: non-portable cluster size, opt-in per kernel; fewer such clusters fit a GPC)
+  p->split_cap = (threads == 512 && npasses >= 2 && npasses <= 16)
+                     ? std::max(1, (npasses <= 8 ? grid_cap * 3 / 4 : grid_cap / 2) / npasses) : 0;
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
   p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = T_total;
   p->layout.tile_of = p->d_tile_of;
@@ -615,8 +617,10 @@ static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevPar
       int dev = 0;
       cudaGetDevice(&dev);
       if (sattr_set[dev & 63] < p.smem) {
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < 4; q++) {
           if (cudaFuncSetAttribute(skerns[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
+          if (cudaFuncSetAttribute(skerns[q], cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return 1;
+        }
         sattr_set[dev & 63] = p.smem;
       }
       cudaLaunchConfig_t cfg = {};

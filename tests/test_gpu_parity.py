@@ -423,7 +423,8 @@ def test_single_residue_molecule_has_no_sizes():
     (210, 200, 2, 1, -1.0, -1.0),      # two atoms per residue, 2 passes
     (260, 240, 1, 80, 9.0, 5.0),       # banded windows and both cut-offs
     (400, 380, 1, 1, -1.0, -1.0),      # 5+ passes on one cluster
-    (640, 600, 1, 1, -1.0, -1.0),      # more passes than a cluster holds: one CTA per orientation
+    (640, 600, 1, 1, -1.0, -1.0),      # 15 passes: a non-portable cluster of 15 CTAs
+    (900, 860, 1, 1, -1.0, -1.0),      # more passes than a cluster holds: one CTA per orientation
 ])
 def test_refine_with_cluster_split_dp_matches_oracle(case):
     """Refine() on chains beyond one CTA: the DP of its batches runs the passes of an orientation
@@ -437,7 +438,7 @@ def test_refine_with_cluster_split_dp_matches_oracle(case):
     Ar, Br = A.reshape(m, nb, 3), B.reshape(nB, nb, 3)
     r, Tgood = oc.superimpose(Ar[idx].reshape(-1, 3), Br[:len(idx)].reshape(-1, 3))
     ws = oc.Workspace(A, B, p)
-    iters = 8 if m < 600 else 4
+    iters = 8 if m < 600 else (4 if m < 800 else 2)
     tables = []
     for split in (1, 0):
         s = make_search(A, B, settings_from_params(p, 4))
