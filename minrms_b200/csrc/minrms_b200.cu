@@ -368,14 +368,28 @@ int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* ite
   CU(c, cudaEventRecord(ev->a, c->stream));
   const int grid = (int)((threads + 127) / 128);
   const size_t coords = 4 * 3 * (size_t)(c->m + c->nB) * c->hp.nb;
-  if (use_tiled(c))
-    k_traceback_kabsch<TbTiled, EMIT><<<grid, 128, 4 * tiled_layout(c).table_ints() + coords, c->stream>>>(
+  const size_t base = coords + (use_tiled(c) ? 4 * (size_t)tiled_layout(c).table_ints() : 0);
+  // emit mode: the pair lists also in shared memory (N pairs x 128 threads) when that fits
+  size_t pairs_smem = 0;
+  if (EMIT) {
+    const size_t want = sizeof(short2) * 128 * (size_t)c->N;
+    if (base + want <= (size_t)c->prop.sharedMemPerBlockOptin) pairs_smem = want;
+  }
+  if (use_tiled(c)) {
+    auto kern = k_traceback_kabsch<TbTiled, EMIT>;
+    if (EMIT && base + pairs_smem > 48 * 1024)
+      CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + pairs_smem)));
+    kern<<<grid, 128, base + pairs_smem, c->stream>>>(
         c->P, tiled_layout(c), c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb,
-        c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs);
-  else
-    k_traceback_kabsch<TbColumns, EMIT><<<grid, 128, coords, c->stream>>>(
+        c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs, pairs_smem ? 1 : 0);
+  } else {
+    auto kern = k_traceback_kabsch<TbColumns, EMIT>;
+    if (EMIT && base + pairs_smem > 48 * 1024)
+      CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + pairs_smem)));
+    kern<<<grid, 128, base + pairs_smem, c->stream>>>(
         c->P, c->Lc, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb, c->d_cost,
-        items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs);
+        items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs, pairs_smem ? 1 : 0);
+  }
   CU(c, cudaGetLastError());
   CU(c, cudaEventRecord(ev->b, c->stream));
   c->st.kernel_launches++;
@@ -993,8 +1007,18 @@ static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* b
   CU(c, cudaMemcpyAsync(c->d_ref_n, hn, sizeof(int) * (size_t)k, cudaMemcpyHostToDevice, c->stream));
   c->st.h2d_bytes += (int64_t)k * (4 * N + 4);
   // orientation that optimally superimposes each alignment (:2401-2407)
-  k_superimpose_pairs_batch<<<k, 128, 4 * 3 * (size_t)(c->m + c->nB) * c->hp.nb + 4 * (size_t)N, c->stream>>>(
-      c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N, c->d_ref_orient);
+  {
+    const size_t team = 4 * 15 * (size_t)N * c->hp.nb;
+    if (team <= (size_t)c->prop.sharedMemPerBlockOptin) {
+      if (team > 48 * 1024)
+        CU(c, cudaFuncSetAttribute(k_superimpose_pairs_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team));
+      k_superimpose_pairs_batch<<<k, 128, team, c->stream>>>(c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N,
+                                                            c->d_ref_orient);
+    } else {
+      k_superimpose_pairs_batch_seq<<<k, 128, 4 * 3 * (size_t)(c->m + c->nB) * c->hp.nb + 4 * (size_t)N, c->stream>>>(
+          c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N, c->d_ref_orient);
+    }
+  }
   CU(c, cudaGetLastError());
   c->st.kernel_launches++;
   c->surv = c->d_surv;

@@ -113,6 +113,9 @@ __device__ __forceinline__ void mr_jacobi4(float (&a)[4][4], float (&d)[4], floa
 // Fetch(a, f, mv) must load the a-th fixed and moveable points, a = 0..np-1; sums are
 // accumulated sequentially in that order (the reference's order).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float mr_superimpose_finish(int np, float cf0, float cf1, float cf2, float cm0, float cm1,
+                                                       float cm2, const float (&M)[3][3], float E0, float (&T)[12]);
+
 template <class Fetch>
 __device__ __forceinline__ float mr_superimpose(int np, Fetch fetch, float (&T)[12]) {
   float cf0 = 0.f, cf1 = 0.f, cf2 = 0.f, cm0 = 0.f, cm1 = 0.f, cm2 = 0.f;
@@ -142,6 +145,13 @@ __device__ __forceinline__ float mr_superimpose(int np, Fetch fetch, float (&T)[
       E0 += df * df;
     }
   }
+  return mr_superimpose_finish(np, cf0, cf1, cf2, cm0, cm1, cm2, M, E0, T);
+}
+
+// second half of mr_superimpose: from the centroids, the 3x3 covariance sums and E0 to the
+// transform and the RMSD (superimpose.cc:120-287)
+__device__ __forceinline__ float mr_superimpose_finish(int np, float cf0, float cf1, float cf2, float cm0, float cm1,
+                                                       float cm2, const float (&M)[3][3], float E0, float (&T)[12]) {
   const float tr = M[0][0] + M[1][1] + M[2][2];
   float P[4][4], d[4], ev[4][4];
 #pragma unroll

@@ -479,12 +479,16 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
                    const int* __restrict__ surv_count, const uint32_t* __restrict__ tb,
                    const float* __restrict__ cost, const int2* __restrict__ items, int n_items,
                    int n_lo, short2* __restrict__ scratch, float* __restrict__ ssd_out,
-                   float* __restrict__ T_out, short* __restrict__ pairs_out) {
+                   float* __restrict__ T_out, short* __restrict__ pairs_out, int pairs_in_smem) {
   extern __shared__ int tb_smem[];
   const int nb = P.nb;
   int* tab = tb_smem;                                              // layout table
   float* sA = reinterpret_cast<float*>(tab + L.table_ints());      // m*nb*3
   float* sB = sA + P.m * nb * 3;                                   // nB*nb*3
+  // emit mode, when it fits: a second copy of the pair lists in shared memory, [pair][thread].
+  // A few hundred threads run alone here, and the two Kabsch passes would otherwise wait for
+  // an L2 round trip per pair (stores do not allocate in L1): measured 0.14 -> see DESIGN.md
+  short2* sp = (EMIT && pairs_in_smem) ? reinterpret_cast<short2*>(sB + P.nB * nb * 3) + threadIdx.x : nullptr;
   L.load_table(tab, threadIdx.x, blockDim.x);
   for (int k = threadIdx.x; k < P.m * nb * 3; k += blockDim.x) sA[k] = A[k];
   for (int k = threadIdx.x; k < P.nB * nb * 3; k += blockDim.x) sB[k] = B[k];
@@ -508,14 +512,19 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
   short2* my = scratch + (size_t)(tid >> 5) * 32 * P.N + (tid & 31);
 #define MY(k) my[(size_t)(k) * 32]
   const uint32_t* tbo = tb + (size_t)s * L.words(P.nB);
-  L.template walk<EMIT>(tab, tbo, n, P.m, P.nB, [&](int k, int i0, int j0) { MY(k) = make_short2((short)i0, (short)j0); });
+  L.template walk<EMIT>(tab, tbo, n, P.m, P.nB, [&](int k, int i0, int j0) {
+    const short2 v = make_short2((short)i0, (short)j0);
+    MY(k) = v;
+    if (EMIT && sp) sp[(size_t)k * 128] = v;
+  });
+#define MYR(k) ((EMIT && sp) ? sp[(size_t)(k) * 128] : MY(k))
   float T[12];
   float ssd;
   if (P.refine_while_searching) {
     float rmsd;
     if (nb == 1) {
       rmsd = mr_superimpose(n, [&](int a, float* pf, float* pm) {
-        const short2 pr = MY(a);
+        const short2 pr = MYR(a);
         const float* f = sA + 3 * pr.x;
         const float* mv = sB + 3 * pr.y;
         pf[0] = f[0]; pf[1] = f[1]; pf[2] = f[2];
@@ -524,7 +533,7 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
     } else {
       rmsd = mr_superimpose(n * nb, [&](int a, float* pf, float* pm) {
         const int k = a / nb, q = a - k * nb;
-        const short2 pr = MY(k);
+        const short2 pr = MYR(k);
         const float* f = sA + 3 * (pr.x * nb + q);
         const float* mv = sB + 3 * (pr.y * nb + q);
         pf[0] = f[0]; pf[1] = f[1]; pf[2] = f[2];
@@ -550,13 +559,15 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
     if (pairs_out) {
       short* po = pairs_out + e * 2 * P.N;
       for (int k = 0; k < n; k++) {
-        po[2 * k] = MY(k).x;
-        po[2 * k + 1] = MY(k).y;
+        const short2 pr = MYR(k);
+        po[2 * k] = pr.x;
+        po[2 * k + 1] = pr.y;
       }
     }
   }
 }
 #undef MY
+#undef MYR
 
 // transforms of the winning orientations: out[k] = orient[idx[k]]
 __global__ void k_gather_orient(const float* __restrict__ orient, const int* __restrict__ idx, int n,
@@ -566,9 +577,86 @@ __global__ void k_gather_orient(const float* __restrict__ orient, const int* __r
 }
 
 // Refine: orientation that optimally superimposes an alignment
+// (PairwiseAlignment::CalcMinRMSD, pair_alignment.cc:714-820), one problem per block: block b
+// superimposes the n[b] pairs at pairs[b * N ...].  The host waits for this kernel, so the
+// block works as a team: every thread gathers / centres / multiplies for its points, and each
+// of the 6 centroid sums, 9 covariance sums and E0 is added up by ONE thread in point order
+// (the reference's order; float addition is not associative) from shared memory -- 16 short
+// dependent chains side by side instead of one thread walking all of them twice.
+__global__ void k_superimpose_pairs_batch(MrDevParams P, const float* __restrict__ A,
+                                          const float* __restrict__ B, const short2* __restrict__ pairs,
+                                          const int* __restrict__ n_of, int N, float* __restrict__ T_out) {
+  extern __shared__ float sp_smem[];
+  const int nb = P.nb, b = blockIdx.x, n = n_of[b], np = n * nb;
+  const int npp = N * nb;                 // pitch of the per-point arrays
+  float* val = sp_smem;                   // [12][npp]: f0 f1 f2 m0 m1 m2, then reused for the products
+  float* sq = val + 12 * (size_t)npp;     // [3][npp]: squared differences, point-major order below
+  __shared__ float cen[6];
+  __shared__ float sums[10];
+  const short2* mine = pairs + (size_t)b * N;
+  for (int a = threadIdx.x; a < np; a += blockDim.x) {
+    const int k = a / nb, q = a - k * nb;
+    const short2 pr = mine[k];
+    const float* f = A + 3 * ((size_t)pr.x * nb + q);
+    const float* mv = B + 3 * ((size_t)pr.y * nb + q);
+    val[a] = f[0]; val[npp + a] = f[1]; val[2 * npp + a] = f[2];
+    val[3 * npp + a] = mv[0]; val[4 * npp + a] = mv[1]; val[5 * npp + a] = mv[2];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {                  // centroids: cf0 cf1 cf2 cm0 cm1 cm2
+    const float* v = val + (size_t)threadIdx.x * npp;
+    float acc = 0.f;
+    for (int a = 0; a < np; a++) acc += v[a];
+    cen[threadIdx.x] = acc * (1.0f / (float)np);
+  }
+  __syncthreads();
+  for (int a = threadIdx.x; a < np; a += blockDim.x) {
+    float f[3], mv[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { f[i] = val[i * npp + a] - cen[i]; mv[i] = val[(3 + i) * npp + a] - cen[3 + i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float df = f[i] - mv[i];
+      sq[i * npp + a] = df * df;
+    }
+    // M[i][j] += mv[i] * f[j]: the 9 products of this point (overwrites the gathered values,
+    // which only this thread reads)
+    float pr9[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) pr9[3 * i + j] = mv[i] * f[j];
+#pragma unroll
+    for (int q = 0; q < 9; q++) val[q * npp + a] = pr9[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    const float* v = val + (size_t)threadIdx.x * npp;
+    float acc = 0.f;
+    for (int a = 0; a < np; a++) acc += v[a];
+    sums[threadIdx.x] = acc;
+  } else if (threadIdx.x == 32) {         // E0 += df0^2; += df1^2; += df2^2 per point, in point order
+    float acc = 0.f;
+    for (int a = 0; a < np; a++) { acc += sq[a]; acc += sq[npp + a]; acc += sq[2 * npp + a]; }
+    sums[9] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  float M[3][3], T[12];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) M[i][j] = sums[3 * i + j];
+  mr_superimpose_finish(np, cen[0], cen[1], cen[2], cen[3], cen[4], cen[5], M, sums[9], T);
+  for (int k = 0; k < 12; k++) T_out[12 * (size_t)b + k] = T[k];
+}
+
+// The same with one thread per problem: fallback when the team version's work space (15 floats
+// per point) exceeds the shared memory of a block.
+// Refine: orientation that optimally superimposes an alignment
 // (PairwiseAlignment::CalcMinRMSD, pair_alignment.cc:714-820), one single-threaded problem per
 // block: block b superimposes the n[b] pairs at pairs[b * N ...]
-__global__ void k_superimpose_pairs_batch(MrDevParams P, const float* __restrict__ A,
+__global__ void k_superimpose_pairs_batch_seq(MrDevParams P, const float* __restrict__ A,
                                           const float* __restrict__ B, const short2* __restrict__ pairs,
                                           const int* __restrict__ n_of, int N, float* __restrict__ T_out) {
   // the block stages both molecules and the pair list in shared memory (coalesced); thread 0
