@@ -52,6 +52,11 @@ __device__ __forceinline__ unsigned mr_cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ unsigned mr_cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
 
 struct MrTileMp {
   int w, c;              // global row strip, layer chunk (-1: idle thread)
@@ -83,11 +88,12 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
   float* sA = sB + 3 * nBp;
   const float INF = __int_as_float(0x7f800000);
   const int nsurv = *surv_count;
-  // split mode: the cluster (npasses CTAs) owns the orientation slot, the CTA rank is the pass
-  const int slot = SPLIT ? (int)blockIdx.x / npasses : (int)blockIdx.x;
-  const int nslots_grid = SPLIT ? (int)gridDim.x / npasses : (int)gridDim.x;
+  // split mode: the cluster (min(passes, 16) CTAs) owns the orientation slot, the CTA rank is the pass
+  // (more passes than CTAs in the cluster: CTA r takes passes r, r + cluster size, ... as a ring)
+  const int csize = SPLIT ? (int)mr_cluster_nctarank() : 1;
+  const int slot = (int)blockIdx.x / csize;
+  const int nslots_grid = (int)gridDim.x / csize;
   const int ps_first = SPLIT ? (int)mr_cluster_ctarank() : 0;
-  const int ps_end = SPLIT ? ps_first + 1 : npasses;
   float4* carry = carry_all + (size_t)slot * carry_pitch;
 
   const uint32_t exch0 = (uint32_t)__cvta_generic_to_shared(exch);
@@ -113,7 +119,8 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
     }
     uint4* const tb_o = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB));
 
-    for (int ps = ps_first; ps < ps_end; ps++) {
+    int cur_tick = 0;  // split mode: ticks this CTA has been through for this orientation
+    for (int ps = ps_first; ps < npasses; ps += csize) {
       const MrPass pass = passes[ps];
       const MrTileMp* ptiles = tiles + (size_t)ps * nthreads;
       const MrTileMp me = ptiles[tid];
@@ -148,7 +155,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
       const int tick0 = pass.lag;
       if constexpr (SPLIT) {
         __syncthreads();
-        for (int t = 1; t <= pass.lag; t++)  // the passes above are that far ahead
+        for (int t = cur_tick + 1; t <= pass.lag; t++)  // the passes above are that far ahead
           if ((t & (MR_SPLIT_GROUP - 1)) == 0) mr_cluster_sync();
       }
 
@@ -374,9 +381,11 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
           mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
         MR_MP_SYNC(s);
       }
+      cur_tick = pass.lag + nsteps;
       if constexpr (SPLIT)
-        for (int t = pass.lag + nsteps + 1; t <= pass.ticks; t++)  // the passes below finish
-          if ((t & (MR_SPLIT_GROUP - 1)) == 0) mr_cluster_sync();
+        if (ps + csize >= npasses)  // my last pass: the passes below finish
+          for (int t = cur_tick + 1; t <= pass.ticks; t++)
+            if ((t & (MR_SPLIT_GROUP - 1)) == 0) mr_cluster_sync();
     }
   }
 #undef MR_MP_SYNC
@@ -394,7 +403,8 @@ struct MrTiledMpPlan {
   size_t tb_words = 0, carry_pitch = 0;
   double lane_efficiency = 0.0;
   int split_ticks = 0;   // split mode: ticks per orientation
-  int split_cap = 0;     // split mode: orientations (clusters of npasses CTAs) resident at once; 0 = not available
+  int split_csize = 0;   // split mode: CTAs per cluster = min(passes, 16)
+  int split_cap = 0;     // split mode: orientations (clusters) resident at once; 0 = not available
   TbTiled layout;
   MrPass* d_passes = nullptr;
   MrTileMp* d_tiles = nullptr;
@@ -546,11 +556,18 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
   const int T_total = gid;
   // split mode: pass q runs lag_q steps behind pass 0: per pass above it, its strips (a column
   // leaves the pass that many steps after it entered) + the ticks between two cluster barriers
+  // With more than 16 passes the cluster (16 CTAs) works as a ring: CTA r takes passes r, r + 16,
+  // ..., and a pass also waits until its CTA has finished the previous one.
+  const int split_csize = std::min(npasses, 16);
   int split_ticks = 0;
   {
     int lag = 0;
+    std::vector<int> free_at(split_csize, 0);  // tick after which CTA r is idle
     for (int q = 0; q < npasses; q++) {
+      const int r = q % split_csize;
+      lag = std::max(lag, free_at[r] + (q >= split_csize ? MR_SPLIT_GROUP : 0));
       passes[q].lag = lag;
+      free_at[r] = lag + passes[q].nsteps;
       split_ticks = std::max(split_ticks, lag + passes[q].nsteps);
       lag += passes[q].nstrips + MR_SPLIT_GROUP;
     }
@@ -582,8 +599,9 @@ static inline void mr_plan_dp_tiled_mp(MrTiledMpPlan* p, const MrDevParams& P, c
   // clusters of up to 8 CTAs are portable; one CTA per SM; GPCs of a B200 hold 16-20 SMs, so a
   // conservative count of co-resident clusters is enough (more would only queue)
   // (9..16 passes: non-portable cluster size, opt-in per kernel; fewer such clusters fit a GPC)
-  p->split_cap = (threads == 512 && npasses >= 2 && npasses <= 16)
-                     ? std::max(1, (npasses <= 8 ? grid_cap * 3 / 4 : grid_cap / 2) / npasses) : 0;
+  p->split_csize = split_csize;
+  p->split_cap = (threads == 512 && npasses >= 2)
+                     ? std::max(1, (split_csize <= 8 ? grid_cap * 3 / 4 : grid_cap / 2) / split_csize) : 0;
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
   p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = T_total;
   p->layout.tile_of = p->d_tile_of;
@@ -609,7 +627,7 @@ static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevPar
                          const float*, const float*, const int*, const int*, float4*, size_t, uint32_t*, float*);
   if constexpr (MAXT == 512 && PP) {
     if (split && p.split_cap > 0) {
-      // one cluster of npasses CTAs per orientation (see the comment on split mode above)
+      // one cluster of min(passes, 16) CTAs per orientation (see the comment on split mode above)
       static const kern_t skerns[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false, PP, true>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true, PP, true>,
                                        k_dp_tiles_mp<4, 8, MAXT, MINB, true, false, PP, true>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true, PP, true>};
       const kern_t kern = skerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
@@ -624,13 +642,13 @@ static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevPar
         sattr_set[dev & 63] = p.smem;
       }
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(std::min(count, p.split_cap) * p.npasses));
+      cfg.gridDim = dim3((unsigned)(std::min(count, p.split_cap) * p.split_csize));
       cfg.blockDim = dim3((unsigned)p.threads);
       cfg.dynamicSmemBytes = p.smem;
       cfg.stream = stream;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = (unsigned)p.npasses;
+      at[0].val.clusterDim.x = (unsigned)p.split_csize;
       at[0].val.clusterDim.y = 1;
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;

@@ -424,7 +424,7 @@ def test_single_residue_molecule_has_no_sizes():
     (260, 240, 1, 80, 9.0, 5.0),       # banded windows and both cut-offs
     (400, 380, 1, 1, -1.0, -1.0),      # 5+ passes on one cluster
     (640, 600, 1, 1, -1.0, -1.0),      # 15 passes: a non-portable cluster of 15 CTAs
-    (900, 860, 1, 1, -1.0, -1.0),      # more passes than a cluster holds: one CTA per orientation
+    (900, 860, 1, 1, -1.0, -1.0),      # 30 passes on a ring of 16 CTAs
 ])
 def test_refine_with_cluster_split_dp_matches_oracle(case):
     """Refine() on chains beyond one CTA: the DP of its batches runs the passes of an orientation
