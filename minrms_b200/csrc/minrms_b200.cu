@@ -377,15 +377,13 @@ int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* ite
   }
   if (use_tiled(c)) {
     auto kern = k_traceback_kabsch<TbTiled, EMIT>;
-    if (EMIT && base + pairs_smem > 48 * 1024)
-      CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + pairs_smem)));
+    if (mr_ensure_smem(kern, base + pairs_smem)) MR_FAIL(c, "traceback kernel: shared memory attribute failed");
     kern<<<grid, 128, base + pairs_smem, c->stream>>>(
         c->P, tiled_layout(c), c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb,
         c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs, pairs_smem ? 1 : 0);
   } else {
     auto kern = k_traceback_kabsch<TbColumns, EMIT>;
-    if (EMIT && base + pairs_smem > 48 * 1024)
-      CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + pairs_smem)));
+    if (mr_ensure_smem(kern, base + pairs_smem)) MR_FAIL(c, "traceback kernel: shared memory attribute failed");
     kern<<<grid, 128, base + pairs_smem, c->stream>>>(
         c->P, c->Lc, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb, c->d_cost,
         items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs, pairs_smem ? 1 : 0);
@@ -427,8 +425,7 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
       static const nwk_t ks[2][4] = {{k_nw_filter_cta<5, 256>, k_nw_filter_cta<6, 256>, k_nw_filter_cta<7, 256>, k_nw_filter_cta<8, 256>},
                                      {k_nw_filter_cta<5, 1024>, k_nw_filter_cta<6, 1024>, k_nw_filter_cta<7, 1024>, k_nw_filter_cta<8, 1024>}};
       const nwk_t k = ks[nw > 8 ? 1 : 0][std::max(cp, 5) - 5];
-      if (sm > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
-        MR_FAIL(c, "NW filter: shared memory attribute failed");
+      if (mr_ensure_smem(k, sm)) MR_FAIL(c, "NW filter: shared memory attribute failed");
       k<<<grid, 32 * nw, sm, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, nwm, surv, c->d_surv_count);
     } else {
       // thread per orientation; the row scratch holds nw_threads_cap orientations at a time
@@ -697,8 +694,7 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
     c->dp_grid_cap = c->prop.multiProcessorCount * 2;
     c->gcol_bytes = colbytes * c->dp_grid_cap;  // allocated when the general kernel first runs
   }
-  if (cudaFuncSetAttribute(k_dp_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dp_smem) != cudaSuccess)
-    return bail("smem attribute");
+  if (mr_ensure_smem(k_dp_columns, c->dp_smem)) return bail("smem attribute");
   tick("general kernel setup");
   mr_plan_dp_tiled(&c->tiled, P, c->prop, c->NP);
   if (!c->tiled.ok || c->tiled.threads > 512) mr_plan_dp_tiled_mp(&c->tiled_mp, P, c->prop, c->NP);
@@ -1010,8 +1006,7 @@ static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* b
   {
     const size_t team = 4 * 15 * (size_t)N * c->hp.nb;
     if (team <= (size_t)c->prop.sharedMemPerBlockOptin) {
-      if (team > 48 * 1024)
-        CU(c, cudaFuncSetAttribute(k_superimpose_pairs_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team));
+      if (mr_ensure_smem(k_superimpose_pairs_batch, team)) MR_FAIL(c, "superposition kernel: shared memory attribute failed");
       k_superimpose_pairs_batch<<<k, 128, team, c->stream>>>(c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N,
                                                             c->d_ref_orient);
     } else {

@@ -7,6 +7,28 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <map>
+#include <mutex>
+#include <utility>
+
+// Opt-in dynamic shared memory of a kernel (cudaFuncAttributeMaxDynamicSharedMemorySize), raised
+// monotonically and recorded per (kernel, device).  Function attributes belong to the process:
+// contexts driven by several host threads (all-vs-all workers, one thread per GPU) must never
+// lower the limit another thread is about to launch with.  Returns 0 on success.
+template <class Kern>
+static inline int mr_ensure_smem(Kern kern, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;  // within the default limit
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> have;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& h = have[std::make_pair(reinterpret_cast<const void*>(kern), dev)];
+  if (h >= bytes) return 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return 1;
+  h = bytes;
+  return 0;
+}
 
 #define MR_UB 1.0e26f  // DistanceMetric::UPPER_BOUND (lib/dyn/distance_metric.cc:49)
 

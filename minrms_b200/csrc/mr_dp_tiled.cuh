@@ -637,15 +637,7 @@ static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& 
   static const kern_t kerns[4] = {k_dp_tiles<4, 8, MAXT, MINB, false, false, PP>, k_dp_tiles<4, 8, MAXT, MINB, false, true, PP>,
                                   k_dp_tiles<4, 8, MAXT, MINB, true, false, PP>, k_dp_tiles<4, 8, MAXT, MINB, true, true, PP>};
   const kern_t kern = kerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
-  // the opt-in shared-memory size is a per-device function attribute
-  static size_t attr_set[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (attr_set[dev & 63] < p.smem) {
-    for (int q = 0; q < 4; q++)
-      if (cudaFuncSetAttribute(kerns[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
-    attr_set[dev & 63] = p.smem;
-  }
+  if (mr_ensure_smem(kern, p.smem)) return 1;
   const int grid = std::min(count, p.grid_cap);
   kern<<<grid, p.threads, p.smem, stream>>>(P, p.layout, p.nslots, p.steps, p.d_tiles, A, B, orient,
                                            surv, surv_count, tb, cost);

@@ -631,16 +631,8 @@ static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevPar
       static const kern_t skerns[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false, PP, true>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true, PP, true>,
                                        k_dp_tiles_mp<4, 8, MAXT, MINB, true, false, PP, true>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true, PP, true>};
       const kern_t kern = skerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
-      static size_t sattr_set[64] = {0};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (sattr_set[dev & 63] < p.smem) {
-        for (int q = 0; q < 4; q++) {
-          if (cudaFuncSetAttribute(skerns[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
-          if (cudaFuncSetAttribute(skerns[q], cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return 1;
-        }
-        sattr_set[dev & 63] = p.smem;
-      }
+      if (mr_ensure_smem(kern, p.smem)) return 1;
+      if (p.split_csize > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return 1;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(std::min(count, p.split_cap) * p.split_csize));
       cfg.blockDim = dim3((unsigned)p.threads);
@@ -662,14 +654,7 @@ static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevPar
   static const kern_t kerns[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false, PP>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true, PP>,
                                   k_dp_tiles_mp<4, 8, MAXT, MINB, true, false, PP>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true, PP>};
   const kern_t kern = kerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
-  static size_t attr_set[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (attr_set[dev & 63] < p.smem) {
-    for (int q = 0; q < 4; q++)
-      if (cudaFuncSetAttribute(kerns[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return 1;
-    attr_set[dev & 63] = p.smem;
-  }
+  if (mr_ensure_smem(kern, p.smem)) return 1;
   const int grid = std::min(count, p.grid_cap);
   kern<<<grid, p.threads, p.smem, stream>>>(P, p.layout, p.nslots, p.npasses, p.wl_max, p.d_passes, p.d_tiles, A, B,
                                            orient, surv, surv_count, p.d_carry, p.carry_pitch, tb, cost);
