@@ -1023,8 +1023,8 @@ static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* b
   c->st.kernel_launches++;
   if (launch_dp(c, c->d_ref_orient, k, true)) return 1;
   if (launch_tb<true>(c, c->d_ref_orient, k, nullptr, 0, c->d_ref_T, nullptr, true)) return 1;
-  k_select<<<(k + 31) / 32, 32, 0, c->stream>>>(c->P, NP, c->d_surv, c->d_surv_count, c->d_cost, c->d_ssd, 0ll,
-                                              nullptr, c->d_valid, c->d_nlast);
+  k_select_warp<<<(k + 3) / 4, 128, 0, c->stream>>>(c->P, NP, c->d_surv, c->d_surv_count, c->d_cost, c->d_ssd, 0ll,
+                                                  nullptr, c->d_valid, c->d_nlast);
   CU(c, cudaGetLastError());
   c->st.kernel_launches++;
   CU(c, cudaMemcpyAsync(c->h_ref + c->ref_off_ssd, c->d_ssd, 4 * (size_t)NP * k, cudaMemcpyDeviceToHost, c->stream));

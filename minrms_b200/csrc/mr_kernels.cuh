@@ -684,6 +684,41 @@ __global__ void k_superimpose_pairs_batch_seq(MrDevParams P, const float* __rest
   for (int k = 0; k < 12; k++) T_out[12 * (size_t)b + k] = T[k];
 }
 
+// K7 for a handful of survivors whose result the host waits for (Refine batches, mr_eval_one):
+// one WARP per survivor.  The sequential n-loop of k_select is a prefix -- everything before
+// the first size at which the reference breaks -- so the lanes test 32 sizes at once and a
+// ballot finds the break: one memory latency per 32 sizes instead of one per 8.
+__global__ void k_select_warp(MrDevParams P, int NP, const int* __restrict__ surv,
+                              const int* __restrict__ surv_count, const float* __restrict__ cost,
+                              const float* __restrict__ ssd, long long id_base,
+                              unsigned long long* __restrict__ keys, unsigned char* __restrict__ valid,
+                              int* __restrict__ n_last_out) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= *surv_count) return;
+  const unsigned long long oid = (unsigned long long)(id_base + surv[s]);
+  int n_last = min(1, P.n_max);
+  for (int n0 = 2; n0 <= P.n_max; n0 += 32) {
+    const int n = n0 + lane;
+    const bool in = n <= P.n_max;
+    const size_t slot = (size_t)s * NP + (size_t)(min(n, NP) - 1);
+    const float cv = cost[slot], v = ssd[slot];
+    const bool brk = in && (cv >= MR_UB || (n >= P.n_min && P.max_rmsd >= 0.0f &&
+                                           v > (float)(n * P.nb) * (P.max_rmsd * P.max_rmsd)));
+    const unsigned m = __ballot_sync(0xffffffffu, brk);
+    const int n_break = m ? n0 + (__ffs(m) - 1) : 0x7fffffff;  // the loop stops AT this size
+    if (in && n < n_break && n >= P.n_min) {
+      if (valid) valid[slot] = 1;
+      if (keys && v < MR_UB) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | oid;
+        if (key < *(volatile unsigned long long*)&keys[n - P.n_min]) atomicMin(&keys[n - P.n_min], key);
+      }
+    }
+    if (m) { n_last = n_break; break; }
+    n_last = min(n0 + 31, P.n_max);
+  }
+  if (n_last_out && lane == 0) n_last_out[s] = n_last;
+}
+
 // ---------------------------------------------------------------------------
 // K7: one thread per survivor: replay the reference's sequential n-loop early exits
 // (search_or_dyn3d.cc:1714-1721 max-dist, 1810-1811 max-rmsd) as a prefix over n, then
