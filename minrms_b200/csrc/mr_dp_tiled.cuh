@@ -384,6 +384,131 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
         step(std::integral_constant<int, 1>(), s + 1, off_b, off_a);
       }
     } else {
+#ifdef MR_EXP_ROT9
+      // Experiment: one FMNMX3 per cell WITHOUT a second copy of the state.  Each layer keeps its
+      // R rows in R + 1 registers; the new value of row r goes to the register the old value of
+      // row r - 1 just left (row 0: the spare one), so the logical rows rotate by one register
+      // per step and the column loop is unrolled R + 1 = 9 times to keep every index static:
+      // at unrolled step U, row r is read from ph[k][(r - U) mod 9] and written to
+      // ph[k][(r - U - 1) mod 9].  ~40 state registers: two CTAs per SM.
+      float ph[K][R + 1], bprev[K];
+      uint32_t acc[K];
+  #pragma unroll
+      for (int k = 0; k < K; k++) {
+        const float v = (c * K + k == 0) ? 0.0f : INF;
+        bprev[k] = v;
+        acc[k] = 0;
+  #pragma unroll
+        for (int r = 0; r <= R; r++) ph[k][r] = v;
+      }
+      uint4* tbp = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid +
+                   (size_t)max(0, (tb_first - w - 1) >> 1) * nthreads;
+      int tb_next = tb_first;
+      __syncthreads();
+      s = 1;
+      for (; s < warp_lo && s <= nsteps; s++) {
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
+        MR_STEP_SYNC();
+      }
+      uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
+      auto step = [&](auto u_tag, const int s) {
+        constexpr int U = decltype(u_tag)::value;
+  #define MR_OLD(k, r) ph[k][((r) + 9 - U) % 9]
+  #define MR_NEW(k, r) ph[k][((r) + 17 - U) % 9]
+        float cv[R];
+        {
+          const uint32_t ca = a_c + (uint32_t)((s - w) & (MR_CRING - 1)) * c_row;
+          const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
+          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
+          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
+        }
+        float bin[K];
+        {
+          const float4 v = mr_lds128(a_up + rd_off);
+          bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
+        }
+        float dsh[R];
+        {
+          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
+          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
+        }
+  #pragma unroll
+        for (int k = K - 1; k >= 0; k--) {
+          float up = bin[k];
+  #pragma unroll
+          for (int r = 0; r < R; r++) {
+            const float dg = (k > 0) ? ((r > 0) ? MR_OLD(k - 1, r - 1) : bprev[k - 1]) : dsh[r];
+            const float d = dg + cv[r];
+            const float left = MR_OLD(k, r);
+            const float best = fminf(fminf(d, up), left);
+            const float s1 = __fsub_rn(d, up);
+            const float s2 = __fsub_rn(best, left);
+            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+            MR_NEW(k, r) = best;
+            up = best;
+          }
+        }
+        mr_sts128(a_me + wr_off, bin[K - 1], MR_NEW(K - 1, 0), MR_NEW(K - 1, 1), MR_NEW(K - 1, 2));
+        mr_sts128(a_me + wr_off + 16u, MR_NEW(K - 1, 3), MR_NEW(K - 1, 4), MR_NEW(K - 1, 5), MR_NEW(K - 1, 6));
+        mr_sts128(a_me + wr_off + 32u, MR_NEW(0, R - 1), MR_NEW(1, R - 1), MR_NEW(2, R - 1), MR_NEW(3, R - 1));
+  #pragma unroll
+        for (int k = 0; k < K; k++) bprev[k] = bin[k];
+        if (s == tb_next) {
+          *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+          tbp += nthreads;
+          tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
+        }
+        if (s == cost_step) {
+  #pragma unroll
+          for (int k = 0; k < K; k++) {
+            const int n = c * K + k;
+            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = MR_NEW(k, R - 1);
+          }
+        }
+        if (WINDOWED && has_tile) {
+          const int nq = s - w - P.wB + 1;
+          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
+            const int rho = nq + P.wA - 2 + pad;
+            if ((rho >> 3) == w) {
+              const int kq = nq & 3, rq = rho & 7;
+              float v = 0.0f;
+  #pragma unroll
+              for (int k = 0; k < K; k++)
+  #pragma unroll
+                for (int r = 0; r < R; r++)
+                  if (k == kq && r == rq) v = MR_NEW(k, r);
+              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
+            }
+          }
+        }
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
+        { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
+        MR_STEP_SYNC();
+  #undef MR_OLD
+  #undef MR_NEW
+      };
+      // every warp runs copy s mod 9 at step s (the state starts uniform, so a warp may enter at
+      // any phase): the warps of a CTA then fetch the same 4 KB of code at the same time.  With
+      // the phase tied to each warp's own window start the nine copies thrashed the instruction
+      // cache: 26.8 ms.
+      if (s <= warp_hi) {
+        int phase = s % 9;
+        for (;;) {
+  #define MR_ROT_STEP(U) case U: step(std::integral_constant<int, U>(), s); if (++s > warp_hi) goto rot_done;
+          switch (phase) {
+            MR_ROT_STEP(0) MR_ROT_STEP(1) MR_ROT_STEP(2) MR_ROT_STEP(3) MR_ROT_STEP(4)
+            MR_ROT_STEP(5) MR_ROT_STEP(6) MR_ROT_STEP(7) MR_ROT_STEP(8)
+          }
+  #undef MR_ROT_STEP
+          phase = 0;
+        }
+      }
+    rot_done:;
+#else
       float st[K][R], bprev[K];
       uint32_t acc[K];
   #pragma unroll
@@ -507,6 +632,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
         { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
         MR_STEP_SYNC();
       }
+#endif
     }
     // steps after this warp's window
     for (; s <= nsteps; s++) {
