@@ -401,9 +401,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
   #pragma unroll
         for (int r = 0; r <= R; r++) ph[k][r] = v;
       }
-      uint4* tbp = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid +
-                   (size_t)max(0, (tb_first - w - 1) >> 1) * nthreads;
-      int tb_next = tb_first;
+      uint4* const tb0 = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid;
       __syncthreads();
       s = 1;
       for (; s < warp_lo && s <= nsteps; s++) {
@@ -411,9 +409,10 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
           mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
         MR_STEP_SYNC();
       }
-      uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
+      uint32_t rd_off = (s & 1) ? 0u : par_bytes;
       auto step = [&](auto u_tag, const int s) {
         constexpr int U = decltype(u_tag)::value;
+        const uint32_t wr_off = par_bytes - rd_off;
   #define MR_OLD(k, r) ph[k][((r) + 9 - U) % 9]
   #define MR_NEW(k, r) ph[k][((r) + 17 - U) % 9]
         float cv[R];
@@ -456,11 +455,8 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
         mr_sts128(a_me + wr_off + 32u, MR_NEW(0, R - 1), MR_NEW(1, R - 1), MR_NEW(2, R - 1), MR_NEW(3, R - 1));
   #pragma unroll
         for (int k = 0; k < K; k++) bprev[k] = bin[k];
-        if (s == tb_next) {
-          *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-          tbp += nthreads;
-          tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
-        }
+        if (has_tile && ((s - tb_first) & 1) == 0 && s >= tb_first && s <= tb_hi)
+          tb0[(unsigned)((s - w - 1) >> 1) * (unsigned)nthreads] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
         if (s == cost_step) {
   #pragma unroll
           for (int k = 0; k < K; k++) {
@@ -486,7 +482,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
         }
         if ((s & (MR_CBATCH - 1)) == 0)
           mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-        { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
+        rd_off = wr_off;
         MR_STEP_SYNC();
   #undef MR_OLD
   #undef MR_NEW
