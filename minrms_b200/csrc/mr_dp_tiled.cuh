@@ -428,14 +428,14 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
           bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
         }
         float dsh[R];
-        {
-          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
-          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-        }
   #pragma unroll
         for (int k = K - 1; k >= 0; k--) {
           float up = bin[k];
+          if (k == 0) {  // the diagonal inputs of the lowest layer are only needed now
+            const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
+            dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+            dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
+          }
   #pragma unroll
           for (int r = 0; r < R; r++) {
             const float dg = (k > 0) ? ((r > 0) ? MR_OLD(k - 1, r - 1) : bprev[k - 1]) : dsh[r];
