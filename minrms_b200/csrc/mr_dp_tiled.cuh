@@ -428,14 +428,25 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
           bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
         }
         float dsh[R];
+  #ifndef MR_EXP_ROT9_LATE_DSH
+        {
+          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
+          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
+          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
+        }
+  #endif
   #pragma unroll
         for (int k = K - 1; k >= 0; k--) {
           float up = bin[k];
-          if (k == 0) {  // the diagonal inputs of the lowest layer are only needed now
+  #ifdef MR_EXP_ROT9_LATE_DSH
+          // the diagonal inputs of the lowest layer loaded only now: 24 / 32 B of spills instead of
+          // 40 / 148, but 11.79 ms (the load sits in front of the layer's dependent chain)
+          if (k == 0) {
             const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
             dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
             dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
           }
+  #endif
   #pragma unroll
           for (int r = 0; r < R; r++) {
             const float dg = (k > 0) ? ((r > 0) ? MR_OLD(k - 1, r - 1) : bprev[k - 1]) : dsh[r];
