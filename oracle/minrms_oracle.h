@@ -9,7 +9,11 @@
  * Parity status: PINNED.  Checked bit-for-bit against the unmodified reference built
  * with strict flags (oracle/_ref/strict, recipe oracle/build_ref.sh) through
  * oracle/ref_dump.cc on the reference's own test pair (configs 1 and 2), and against
- * the committed golden tables in tests/golden/ (see tests/test_oracle_golden.py).
+ * the committed golden tables in tests/golden/ (see tests/test_oracle_golden.py).  The
+ * align_chimera.plot statistics (orc_plot_stats) are pinned the same way: oracle/ref_plot.cc
+ * evaluates the reference's own FindFurthestResPair / LevittGerstein98 functions on the
+ * reference's best tables of five configurations (tests/golden/ref_plot.npz,
+ * tests/test_plot_stats.py: all nine values per size bit-identical).
  *
  * Every function cites the reference file:line (under /root/reference) it follows.
  */
