@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libminrms_b200.so")
+# MINRMS_B200_LIB: another build of the same library (kernel A/B measurements)
+LIB_PATH = os.environ.get("MINRMS_B200_LIB") or os.path.join(HERE, "libminrms_b200.so")
 
 
 class MrParams(C.Structure):

@@ -28,9 +28,10 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("MR_NVCC_EXTRA", "").split()   # experiments only, e.g. -DMR_DP_MIN3
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    out = os.environ.get("MR_BUILD_OUT", OUT)                # experiments only: variant builds for A/B runs
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -40,6 +40,7 @@
 #include <type_traits>
 #include <vector>
 #include "mr_device.cuh"
+#include "mr_tile_step.cuh"
 
 // Traceback storage of the tiled kernel.  Each tile (thread t of the CTA) writes, every
 // second column, one 32-bit word per layer of the tile: 2 columns x R=8 rows x 2 bits,
@@ -197,29 +198,13 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
   }
 }
 
-// 16-byte shared-memory accesses through 32-bit shared addresses (one register each)
-__device__ __forceinline__ float4 mr_lds128(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void mr_sts128(uint32_t a, float x, float y, float z, float w) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-
-#ifdef MR_EXP_NOSYNC
-#define MR_STEP_SYNC() __syncwarp()  // timing experiment only (results are wrong): cost of the per-step CTA barrier
-#else
-#define MR_STEP_SYNC() __syncthreads()
-#endif
-
 template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
            const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
            const int* __restrict__ surv, const int* __restrict__ surv_count,
            uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
-  static_assert(R == 8 && K == 4, "traceback word packing assumes 4 x 8 tiles");
+  static_assert(R == MR_TR && K == MR_TK, "traceback word packing assumes 4 x 8 tiles");
   extern __shared__ float4 smem4[];
   const int m = P.m, nB = P.nB, nb = P.nb;
   const int W = L.W, WR = W * R, pad = L.pad;
@@ -280,372 +265,91 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
     __syncthreads();
     mr_produce_c<NB1>(Cr, sA, sB, 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
 
+    // tile state: the ping-pong form keeps two copies (read one, write the other), the in-place
+    // form one; bprev = upper boundary A(n, i_lo-1, .) of the previous column (and, ping-pong, this one)
+    constexpr int NC = PP ? 2 : 1;
+    float st[NC][K][R], bprev[NC][K];
+    uint32_t acc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const float v = (c * K + k == 0) ? 0.0f : INF;
+      acc[k] = 0;
+#pragma unroll
+      for (int q = 0; q < NC; q++) {
+        bprev[q][k] = v;
+#pragma unroll
+        for (int r = 0; r < R; r++) st[q][k][r] = v;
+      }
+    }
+    uint4* tbp = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid +
+                 (size_t)max(0, (tb_first - w - 1) >> 1) * nthreads;
+    int tb_next = tb_first;
+    float* const cost_row = cost_out + (size_t)sv * L.NP;
+    __syncthreads();
+
+    // steps before this warp has live cells: keep pace with the CTA (barrier + C production)
     int s = 1;
-    if constexpr (PP) {
-      // Ping-pong form: two copies of the tile state, read from one and written to
-      // the other, so that best = min3(d, up, left) can be ONE instruction (FMNMX3) and the tie
-      // predicate still sees the old value: s2 = best - left.  3 ALU-pipe + 3 FMA-pipe
-      // instructions per cell instead of 4 + 3; needs ~40 more registers (1 CTA per SM).
-      float st[2][K][R], bprev[2][K];
-      uint32_t acc[K];
-  #pragma unroll
-      for (int k = 0; k < K; k++) {
-        const float v = (c * K + k == 0) ? 0.0f : INF;
-        bprev[0][k] = bprev[1][k] = v;
-        acc[k] = 0;
-  #pragma unroll
-        for (int r = 0; r < R; r++) st[0][k][r] = st[1][k][r] = v;
-      }
-      uint4* tbp = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid +
-                   (size_t)max(0, (tb_first - w - 1) >> 1) * nthreads;
-      int tb_next = tb_first;
+    for (; s < warp_lo && s <= nsteps; s++) {
+      if ((s & (MR_CBATCH - 1)) == 0)
+        mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
       __syncthreads();
-      s = 1;
-      for (; s < warp_lo && s <= nsteps; s++) {
-        if ((s & (MR_CBATCH - 1)) == 0)
-          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-        MR_STEP_SYNC();
+    }
+    // one column: read the neighbours' slots of parity rd_off, write mine of parity wr_off
+    auto step = [&](auto src_tag, const int s, const uint32_t rd_off, const uint32_t wr_off) {
+      constexpr int S = decltype(src_tag)::value, D = PP ? 1 - S : 0;
+      float cv[R], dsh[R];
+      mr_tile_load8(cv, a_c + (uint32_t)((s - w) & (MR_CRING - 1)) * c_row);  // ring column j & 31 (+inf outside the matrix)
+      const float4 ub = mr_lds128(a_up + rd_off);                             // A(n, i_lo-1, j): bottom row of the tile above
+      mr_tile_load8(dsh, a_dg + rd_off);
+      if constexpr (PP) {
+        bprev[D][0] = ub.x; bprev[D][1] = ub.y; bprev[D][2] = ub.z; bprev[D][3] = ub.w;
+        mr_tile_update_pp<S>(st, bprev, acc, cv, dsh);
+      } else {
+        const float bin[K] = {ub.x, ub.y, ub.z, ub.w};
+        mr_tile_update_ip(st[0], bprev[0], bin, acc, cv, dsh);
       }
-      const uint32_t off_a = (s & 1) ? 0u : par_bytes, off_b = par_bytes - off_a;
-      auto step = [&](auto src_tag, const int s, const uint32_t rd_off, const uint32_t wr_off) {
-        constexpr int S = decltype(src_tag)::value, D = 1 - S;
-        float cv[R];
-        {
-          const uint32_t ca = a_c + (uint32_t)((s - w) & (MR_CRING - 1)) * c_row;
-          const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
-          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
-          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
+      mr_tile_publish(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
+                      st[D][3][R - 1]);
+      // traceback: the K words of this tile every second column (j = s - w even)
+      if (s == tb_next) {
+        *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        tbp += nthreads;
+        tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
+      }
+      // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
+      if (s == cost_step) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const int n = c * K + k;
+          if (n >= P.n_min && n <= P.n_max) cost_row[n - 1] = st[D][k][R - 1];
         }
-        {
-          const float4 v = mr_lds128(a_up + rd_off);
-          bprev[D][0] = v.x; bprev[D][1] = v.y; bprev[D][2] = v.z; bprev[D][3] = v.w;
-        }
-        float dsh[R];
-        {
-          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
-          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-        }
-  #pragma unroll
-        for (int k = K - 1; k >= 0; k--) {
-          float up = bprev[D][k];
-  #pragma unroll
-          for (int r = 0; r < R; r++) {
-            const float dg = (k > 0) ? ((r > 0) ? st[S][k - 1][r - 1] : bprev[S][k - 1]) : dsh[r];
-            const float d = dg + cv[r];
-            const float left = st[S][k][r];
-            const float best = fminf(fminf(d, up), left);
-            const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
-            const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
-            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
-            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
-            st[D][k][r] = best;
-            up = best;
-          }
-        }
-        mr_sts128(a_me + wr_off, bprev[D][K - 1], st[D][K - 1][0], st[D][K - 1][1], st[D][K - 1][2]);
-        mr_sts128(a_me + wr_off + 16u, st[D][K - 1][3], st[D][K - 1][4], st[D][K - 1][5], st[D][K - 1][6]);
-        mr_sts128(a_me + wr_off + 32u, st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1], st[D][3][R - 1]);
-        if (s == tb_next) {
-          *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-          tbp += nthreads;
-          tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
-        }
-        if (s == cost_step) {
-  #pragma unroll
-          for (int k = 0; k < K; k++) {
-            const int n = c * K + k;
-            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[D][k][R - 1];
-          }
-        }
-        if (WINDOWED && has_tile) {
-          const int nq = s - w - P.wB + 1;
-          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
-            const int rho = nq + P.wA - 2 + pad;
-            if ((rho >> 3) == w) {
-              const int kq = nq & 3, rq = rho & 7;
-              float v = 0.0f;
-  #pragma unroll
-              for (int k = 0; k < K; k++)
-  #pragma unroll
-                for (int r = 0; r < R; r++)
-                  if (k == kq && r == rq) v = st[D][k][r];
-              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
-            }
-          }
-        }
-        if ((s & (MR_CBATCH - 1)) == 0)
-          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-        MR_STEP_SYNC();
-      };
+      }
+      if (WINDOWED && has_tile) mr_tile_window_cost(P, st[D], s - w, w, c, pad, cost_row);
+      // every MR_CBATCH steps all threads produce the next MR_CBATCH columns of C
+      if ((s & (MR_CBATCH - 1)) == 0)
+        mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
+      __syncthreads();
+    };
+    // parity of the exchange set written at step s: s & 1
+    const uint32_t off_a = (s & 1) ? 0u : par_bytes, off_b = par_bytes - off_a;
+    if constexpr (PP) {
       // the plan makes every warp window an even number of steps
       for (; s < warp_hi; s += 2) {
         step(std::integral_constant<int, 0>(), s, off_a, off_b);
         step(std::integral_constant<int, 1>(), s + 1, off_b, off_a);
       }
     } else {
-#ifdef MR_EXP_ROT9
-      // Experiment: one FMNMX3 per cell WITHOUT a second copy of the state.  Each layer keeps its
-      // R rows in R + 1 registers; the new value of row r goes to the register the old value of
-      // row r - 1 just left (row 0: the spare one), so the logical rows rotate by one register
-      // per step and the column loop is unrolled R + 1 = 9 times to keep every index static:
-      // at unrolled step U, row r is read from ph[k][(r - U) mod 9] and written to
-      // ph[k][(r - U - 1) mod 9].  ~40 state registers: two CTAs per SM.
-      float ph[K][R + 1], bprev[K];
-      uint32_t acc[K];
-  #pragma unroll
-      for (int k = 0; k < K; k++) {
-        const float v = (c * K + k == 0) ? 0.0f : INF;
-        bprev[k] = v;
-        acc[k] = 0;
-  #pragma unroll
-        for (int r = 0; r <= R; r++) ph[k][r] = v;
-      }
-      uint4* const tb0 = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid;
-      __syncthreads();
-      s = 1;
-      for (; s < warp_lo && s <= nsteps; s++) {
-        if ((s & (MR_CBATCH - 1)) == 0)
-          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-        MR_STEP_SYNC();
-      }
-      uint32_t rd_off = (s & 1) ? 0u : par_bytes;
-      auto step = [&](auto u_tag, const int s) {
-        constexpr int U = decltype(u_tag)::value;
-        const uint32_t wr_off = par_bytes - rd_off;
-  #define MR_OLD(k, r) ph[k][((r) + 9 - U) % 9]
-  #define MR_NEW(k, r) ph[k][((r) + 17 - U) % 9]
-        float cv[R];
-        {
-          const uint32_t ca = a_c + (uint32_t)((s - w) & (MR_CRING - 1)) * c_row;
-          const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
-          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
-          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
-        }
-        float bin[K];
-        {
-          const float4 v = mr_lds128(a_up + rd_off);
-          bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
-        }
-        float dsh[R];
-  #ifndef MR_EXP_ROT9_LATE_DSH
-        {
-          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
-          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-        }
-  #endif
-  #pragma unroll
-        for (int k = K - 1; k >= 0; k--) {
-          float up = bin[k];
-  #ifdef MR_EXP_ROT9_LATE_DSH
-          // the diagonal inputs of the lowest layer loaded only now: 24 / 32 B of spills instead of
-          // 40 / 148, but 11.79 ms (the load sits in front of the layer's dependent chain)
-          if (k == 0) {
-            const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
-            dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-            dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-          }
-  #endif
-  #pragma unroll
-          for (int r = 0; r < R; r++) {
-            const float dg = (k > 0) ? ((r > 0) ? MR_OLD(k - 1, r - 1) : bprev[k - 1]) : dsh[r];
-            const float d = dg + cv[r];
-            const float left = MR_OLD(k, r);
-            const float best = fminf(fminf(d, up), left);
-            const float s1 = __fsub_rn(d, up);
-            const float s2 = __fsub_rn(best, left);
-            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
-            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
-            MR_NEW(k, r) = best;
-            up = best;
-          }
-        }
-        mr_sts128(a_me + wr_off, bin[K - 1], MR_NEW(K - 1, 0), MR_NEW(K - 1, 1), MR_NEW(K - 1, 2));
-        mr_sts128(a_me + wr_off + 16u, MR_NEW(K - 1, 3), MR_NEW(K - 1, 4), MR_NEW(K - 1, 5), MR_NEW(K - 1, 6));
-        mr_sts128(a_me + wr_off + 32u, MR_NEW(0, R - 1), MR_NEW(1, R - 1), MR_NEW(2, R - 1), MR_NEW(3, R - 1));
-  #pragma unroll
-        for (int k = 0; k < K; k++) bprev[k] = bin[k];
-        if (has_tile && ((s - tb_first) & 1) == 0 && s >= tb_first && s <= tb_hi)
-          tb0[(unsigned)((s - w - 1) >> 1) * (unsigned)nthreads] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-        if (s == cost_step) {
-  #pragma unroll
-          for (int k = 0; k < K; k++) {
-            const int n = c * K + k;
-            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = MR_NEW(k, R - 1);
-          }
-        }
-        if (WINDOWED && has_tile) {
-          const int nq = s - w - P.wB + 1;
-          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
-            const int rho = nq + P.wA - 2 + pad;
-            if ((rho >> 3) == w) {
-              const int kq = nq & 3, rq = rho & 7;
-              float v = 0.0f;
-  #pragma unroll
-              for (int k = 0; k < K; k++)
-  #pragma unroll
-                for (int r = 0; r < R; r++)
-                  if (k == kq && r == rq) v = MR_NEW(k, r);
-              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
-            }
-          }
-        }
-        if ((s & (MR_CBATCH - 1)) == 0)
-          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-        rd_off = wr_off;
-        MR_STEP_SYNC();
-  #undef MR_OLD
-  #undef MR_NEW
-      };
-      // every warp runs copy s mod 9 at step s (the state starts uniform, so a warp may enter at
-      // any phase): the warps of a CTA then fetch the same 4 KB of code at the same time.  With
-      // the phase tied to each warp's own window start the nine copies thrashed the instruction
-      // cache: 26.8 ms.
-      if (s <= warp_hi) {
-        int phase = s % 9;
-        for (;;) {
-  #define MR_ROT_STEP(U) case U: step(std::integral_constant<int, U>(), s); if (++s > warp_hi) goto rot_done;
-          switch (phase) {
-            MR_ROT_STEP(0) MR_ROT_STEP(1) MR_ROT_STEP(2) MR_ROT_STEP(3) MR_ROT_STEP(4)
-            MR_ROT_STEP(5) MR_ROT_STEP(6) MR_ROT_STEP(7) MR_ROT_STEP(8)
-          }
-  #undef MR_ROT_STEP
-          phase = 0;
-        }
-      }
-    rot_done:;
-#else
-      float st[K][R], bprev[K];
-      uint32_t acc[K];
-  #pragma unroll
-      for (int k = 0; k < K; k++) {
-        const float v = (c * K + k == 0) ? 0.0f : INF;
-        bprev[k] = v;
-        acc[k] = 0;
-  #pragma unroll
-        for (int r = 0; r < R; r++) st[k][r] = v;
-      }
-      uint4* tbp = reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) + tid +
-                   (size_t)max(0, (tb_first - w - 1) >> 1) * nthreads;
-      int tb_next = tb_first;
-      __syncthreads();
-
-      // steps before this warp has live cells: keep pace with the CTA (barrier + C production)
-      s = 1;
-      for (; s < warp_lo && s <= nsteps; s++) {
-        if ((s & (MR_CBATCH - 1)) == 0)
-          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-        MR_STEP_SYNC();
-      }
-      // parity of the exchange set written at step s: s & 1
-      uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
-#ifdef MR_EXP_UNROLL
-      constexpr int kUnroll = MR_EXP_UNROLL;
-#pragma unroll kUnroll
-#endif
+      uint32_t rd_off = off_a, wr_off = off_b;
       for (; s <= warp_hi; s++) {
-        // C(i, j) for my R rows: ring column j & 31 (columns <= 0 and > nB hold +inf)
-        float cv[R];
-        {
-          const uint32_t ca = a_c + (uint32_t)((s - w) & (MR_CRING - 1)) * c_row;
-          const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
-          cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
-          cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
-        }
-        // A(n, i_lo-1, j): the bottom row the tile above published last step
-        float bin[K];
-        {
-          const float4 v = mr_lds128(a_up + rd_off);
-          bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
-        }
-        // A(n_lo-1, i-1, j-1) for my lowest layer: what the lower-layer tile published last
-        // step = {its upper boundary, rows 0..6} of its top layer after column j-1
-        float dsh[R];
-        {
-          const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
-          dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-          dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-        }
-  #pragma unroll
-        for (int k = K - 1; k >= 0; k--) {
-          float up = bin[k];
-  #pragma unroll
-          for (int r = 0; r < R; r++) {
-            const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
-            const float d = dg + cv[r];
-            const float left = st[k][r];
-#ifdef MR_EXP_MIN3IP
-            // experiment: one FMNMX3 with the state updated in place (register renaming + copies
-            // at the loop back-edge are left to ptxas)
-            const float best = fminf(fminf(d, up), left);
-            const float s1 = __fsub_rn(d, up);
-            const float s2 = __fsub_rn(best, left);
-#else
-            // two 2-input mins so the new value overwrites `left` in place (no register copy)
-            const float t = fminf(d, up);
-            const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
-            const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
-            const float best = fminf(t, left);
-#endif
-            acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
-            acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
-            st[k][r] = best;
-            up = best;
-          }
-        }
-        // publish: top layer shifted down one row (for the tile one chunk up, next column, next
-        // step) and bottom row (for the tile below, same column, next step)
-        mr_sts128(a_me + wr_off, bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
-        mr_sts128(a_me + wr_off + 16u, st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
-        mr_sts128(a_me + wr_off + 32u, st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
-  #pragma unroll
-        for (int k = 0; k < K; k++) bprev[k] = bin[k];
-        // traceback: the K words of this tile every second column (j = s - w even)
-        if (s == tb_next) {
-          *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-          tbp += nthreads;
-          tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
-        }
-        // cost(n) = A(n, m, nB) for n >= n_min (row m is the last row of the last strip)
-        if (s == cost_step) {
-  #pragma unroll
-          for (int k = 0; k < K; k++) {
-            const int n = c * K + k;
-            if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
-          }
-        }
-        // n < n_min: the reference reports the corner of the layer's window,
-        // A(n, n+wA-1, n+wB-1) (dyn3d.cc:385, dyn3d.h:407-408): one layer per column
-        if (WINDOWED && has_tile) {
-          const int nq = s - w - P.wB + 1;
-          if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
-            const int rho = nq + P.wA - 2 + pad;
-            if ((rho >> 3) == w) {
-              const int kq = nq & 3, rq = rho & 7;
-              float v = 0.0f;
-  #pragma unroll
-              for (int k = 0; k < K; k++)
-  #pragma unroll
-                for (int r = 0; r < R; r++)
-                  if (k == kq && r == rq) v = st[k][r];
-              cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
-            }
-          }
-        }
-        // every MR_CBATCH steps all threads produce the next MR_CBATCH columns of C
-        if ((s & (MR_CBATCH - 1)) == 0)
-          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-        { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
-        MR_STEP_SYNC();
+        step(std::integral_constant<int, 0>(), s, rd_off, wr_off);
+        const uint32_t t = rd_off; rd_off = wr_off; wr_off = t;
       }
-#endif
     }
     // steps after this warp's window
     for (; s <= nsteps; s++) {
       if ((s & (MR_CBATCH - 1)) == 0)
         mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads);
-      MR_STEP_SYNC();
+      __syncthreads();
     }
   }
 }
@@ -745,10 +449,7 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   p->threads = threads; p->nslots = nslots; p->steps = steps; p->pp = pp;
   p->smem = smem;
   const int by_smem = (int)(prop.sharedMemPerMultiprocessor / (smem + 1024));
-  int want = mr_dp_tiles_minb(threads);  // CTAs per SM the launch-bound bucket of this CTA size allows
-#ifdef MR_EXP_CTAS
-  want = MR_EXP_CTAS;
-#endif
+  const int want = mr_dp_tiles_minb(threads);  // CTAs per SM the launch-bound bucket of this CTA size allows
   p->ctas_per_sm = std::max(1, std::min(by_smem, want));
   p->grid_cap = prop.multiProcessorCount * p->ctas_per_sm;
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
@@ -782,13 +483,7 @@ static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& 
 // ping-pong form (one FMNMX3 per cell) ~150.  Small pairs have few tiles: several CTAs
 // (orientations) per SM keep the pipes fed; from 320 threads on, one CTA per SM in the
 // ping-pong form is faster than two in the two-min form (config 2: 2.07 vs 2.01 TCUPS).
-#ifdef MR_EXP_PP2
-#define MR_DP_BIG_BUCKETS(X) X(320, 2, true) X(352, 2, true) X(384, 2, true)  // experiment: ping-pong at 2 CTAs/SM (spills)
-#elif defined(MR_EXP_BIG2)
-#define MR_DP_BIG_BUCKETS(X) X(320, 2, false) X(352, 2, false) X(384, 2, false)  // experiment: in-place forms at 2 CTAs/SM
-#else
 #define MR_DP_BIG_BUCKETS(X) X(320, 1, true) X(352, 1, true) X(384, 1, true)
-#endif
 #define MR_DP_BUCKETS(X) \
   X(64, 10, false) X(128, 5, false) X(192, 3, false) X(256, 2, false) MR_DP_BIG_BUCKETS(X) X(512, 1, true)
 static inline int mr_dp_tiles_minb(int threads) {

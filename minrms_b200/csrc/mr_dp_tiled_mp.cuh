@@ -74,7 +74,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
               const float* __restrict__ orient, const int* __restrict__ surv,
               const int* __restrict__ surv_count, float4* carry_all, size_t carry_pitch,
               uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
-  static_assert(R == 8 && K == 4, "traceback word packing assumes 4 x 8 tiles");
+  static_assert(R == MR_TR && K == MR_TK, "traceback word packing assumes 4 x 8 tiles");
   extern __shared__ float4 smem4[];
   const int m = P.m, nB = P.nB, nb = P.nb;
   const int W = L.W, pad = L.pad, CN = L.CN;
@@ -159,221 +159,86 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
           if ((t & (MR_SPLIT_GROUP - 1)) == 0) mr_cluster_sync();
       }
 
+      // tile state and step: as in k_dp_tiles (mr_tile_step.cuh); the upper boundary of a pass's
+      // first strip comes from the carry buffer (fetched one column ahead into a register), and
+      // the bottom row of its last strip goes there
+      constexpr int NC = PP ? 2 : 1;
+      float st[NC][K][R], bprev[NC][K];
+      uint32_t acc[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const float v = (c * K + k == 0) ? 0.0f : INF;
+        acc[k] = 0;
+#pragma unroll
+        for (int q = 0; q < NC; q++) {
+          bprev[q][k] = v;
+#pragma unroll
+          for (int r = 0; r < R; r++) st[q][k][r] = v;
+        }
+      }
+      uint4* tbp = tb_o + (pass.gid_off + tid) + (size_t)max(0, (tb_first - wl - 1) >> 1) * L.T;
+      int tb_next = tb_first;
+      float* const cost_row = cost_out + (size_t)sv * L.NP;
+      __syncthreads();
       int s = 1;
+      for (; s < warp_lo && s <= nsteps; s++) {
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+        MR_MP_SYNC(s);
+      }
+      float4 gnext = make_float4(INF, INF, INF, INF);
+      if (from_carry) gnext = __ldcg(cme + (size_t)min(s, nBe + 1) * CN);
+      auto step = [&](auto src_tag, const int s, const uint32_t rd_off, const uint32_t wr_off) {
+        constexpr int S = decltype(src_tag)::value, D = PP ? 1 - S : 0;
+        float cv[R], dsh[R];
+        mr_tile_load8(cv, a_c + (uint32_t)((s - wl) & (MR_CRING - 1)) * c_row);
+        float4 ub = mr_lds128(a_up + rd_off);
+        if (from_carry) {
+          ub = ((unsigned)(s - me.s_lo) <= own_span) ? gnext : make_float4(c == 0 ? 0.0f : INF, INF, INF, INF);
+          gnext = __ldcg(cme + (size_t)min(s + 1, nBe + 1) * CN);
+        }
+        mr_tile_load8(dsh, a_dg + rd_off);
+        if constexpr (PP) {
+          bprev[D][0] = ub.x; bprev[D][1] = ub.y; bprev[D][2] = ub.z; bprev[D][3] = ub.w;
+          mr_tile_update_pp<S>(st, bprev, acc, cv, dsh);
+        } else {
+          const float bin[K] = {ub.x, ub.y, ub.z, ub.w};
+          mr_tile_update_ip(st[0], bprev[0], bin, acc, cv, dsh);
+        }
+        mr_tile_publish(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
+                        st[D][3][R - 1]);
+        // bottom row of the pass -> carry[column j = s - wl]
+        if ((unsigned)(s - out_lo) <= own_span)
+          __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1], st[D][3][R - 1]));
+        if (s == tb_next) {
+          *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+          tbp += L.T;
+          tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
+        }
+        if (s == cost_step) {
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const int n = c * K + k;
+            if (n >= P.n_min && n <= P.n_max) cost_row[n - 1] = st[D][k][R - 1];
+          }
+        }
+        if (WINDOWED && has_tile) mr_tile_window_cost(P, st[D], s - wl, w, c, pad, cost_row);
+        if ((s & (MR_CBATCH - 1)) == 0)
+          mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
+        MR_MP_SYNC(s);
+      };
+      const uint32_t off_a = (s & 1) ? 0u : par_bytes, off_b = par_bytes - off_a;
       if constexpr (PP) {
-        // ping-pong form of the tile update (see k_dp_tiles): best = min3(d, up, left) in one
-        // instruction, s2 = best - left from the untouched source copy of the state
-        float st[2][K][R], bprev[2][K];
-        uint32_t acc[K];
-  #pragma unroll
-        for (int k = 0; k < K; k++) {
-          const float v = (c * K + k == 0) ? 0.0f : INF;
-          bprev[0][k] = bprev[1][k] = v;
-          acc[k] = 0;
-  #pragma unroll
-          for (int r = 0; r < R; r++) st[0][k][r] = st[1][k][r] = v;
-        }
-        uint4* tbp = tb_o + (pass.gid_off + tid) + (size_t)max(0, (tb_first - wl - 1) >> 1) * L.T;
-        int tb_next = tb_first;
-        __syncthreads();
-        s = 1;
-        for (; s < warp_lo && s <= nsteps; s++) {
-          if ((s & (MR_CBATCH - 1)) == 0)
-            mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
-          MR_MP_SYNC(s);
-        }
-        const uint32_t off_a = (s & 1) ? 0u : par_bytes, off_b = par_bytes - off_a;
-        float4 gnext = make_float4(INF, INF, INF, INF);
-        if (from_carry) gnext = __ldcg(cme + (size_t)min(s, nBe + 1) * CN);
-        auto step = [&](auto src_tag, const int s, const uint32_t rd_off, const uint32_t wr_off) {
-          constexpr int S = decltype(src_tag)::value, D = 1 - S;
-          float cv[R];
-          {
-            const uint32_t ca = a_c + (uint32_t)((s - wl) & (MR_CRING - 1)) * c_row;
-            const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
-            cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
-            cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
-          }
-          {
-            float4 v = mr_lds128(a_up + rd_off);
-            if (from_carry) {
-              v = ((unsigned)(s - me.s_lo) <= own_span) ? gnext : make_float4(c == 0 ? 0.0f : INF, INF, INF, INF);
-              gnext = __ldcg(cme + (size_t)min(s + 1, nBe + 1) * CN);
-            }
-            bprev[D][0] = v.x; bprev[D][1] = v.y; bprev[D][2] = v.z; bprev[D][3] = v.w;
-          }
-          float dsh[R];
-          {
-            const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
-            dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-            dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-          }
-  #pragma unroll
-          for (int k = K - 1; k >= 0; k--) {
-            float up = bprev[D][k];
-  #pragma unroll
-            for (int r = 0; r < R; r++) {
-              const float dg = (k > 0) ? ((r > 0) ? st[S][k - 1][r - 1] : bprev[S][k - 1]) : dsh[r];
-              const float d = dg + cv[r];
-              const float left = st[S][k][r];
-              const float best = fminf(fminf(d, up), left);
-              const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
-              const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
-              acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
-              acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
-              st[D][k][r] = best;
-              up = best;
-            }
-          }
-          mr_sts128(a_me + wr_off, bprev[D][K - 1], st[D][K - 1][0], st[D][K - 1][1], st[D][K - 1][2]);
-          mr_sts128(a_me + wr_off + 16u, st[D][K - 1][3], st[D][K - 1][4], st[D][K - 1][5], st[D][K - 1][6]);
-          mr_sts128(a_me + wr_off + 32u, st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1], st[D][3][R - 1]);
-          if ((unsigned)(s - out_lo) <= own_span)
-            __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1], st[D][3][R - 1]));
-          if (s == tb_next) {
-            *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-            tbp += L.T;
-            tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
-          }
-          if (s == cost_step) {
-  #pragma unroll
-            for (int k = 0; k < K; k++) {
-              const int n = c * K + k;
-              if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[D][k][R - 1];
-            }
-          }
-          if (WINDOWED && has_tile) {
-            const int nq = s - wl - P.wB + 1;
-            if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
-              const int rho = nq + P.wA - 2 + pad;
-              if ((rho >> 3) == w) {
-                const int kq = nq & 3, rq = rho & 7;
-                float v = 0.0f;
-  #pragma unroll
-                for (int k = 0; k < K; k++)
-  #pragma unroll
-                  for (int r = 0; r < R; r++)
-                    if (k == kq && r == rq) v = st[D][k][r];
-                cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
-              }
-            }
-          }
-          if ((s & (MR_CBATCH - 1)) == 0)
-            mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
-          MR_MP_SYNC(s);
-        };
         // the plan makes every warp window an even number of steps
         for (; s < warp_hi; s += 2) {
           step(std::integral_constant<int, 0>(), s, off_a, off_b);
           step(std::integral_constant<int, 1>(), s + 1, off_b, off_a);
         }
       } else {
-        float st[K][R], bprev[K];
-        uint32_t acc[K];
-  #pragma unroll
-        for (int k = 0; k < K; k++) {
-          const float v = (c * K + k == 0) ? 0.0f : INF;
-          bprev[k] = v;
-          acc[k] = 0;
-  #pragma unroll
-          for (int r = 0; r < R; r++) st[k][r] = v;
-        }
-        uint4* tbp = tb_o + (pass.gid_off + tid) + (size_t)max(0, (tb_first - wl - 1) >> 1) * L.T;
-        int tb_next = tb_first;
-        __syncthreads();
-
-        s = 1;
-        for (; s < warp_lo && s <= nsteps; s++) {
-          if ((s & (MR_CBATCH - 1)) == 0)
-            mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
-          MR_MP_SYNC(s);
-        }
-        uint32_t rd_off = (s & 1) ? 0u : par_bytes, wr_off = par_bytes - rd_off;
-        // upper boundary of the first strip: column j = s of the carry, fetched one step ahead
-        float4 gnext = make_float4(INF, INF, INF, INF);
-        if (from_carry) gnext = __ldcg(cme + (size_t)min(s, nBe + 1) * CN);
+        uint32_t rd_off = off_a, wr_off = off_b;
         for (; s <= warp_hi; s++) {
-          float cv[R];
-          {
-            const uint32_t ca = a_c + (uint32_t)((s - wl) & (MR_CRING - 1)) * c_row;
-            const float4 v0 = mr_lds128(ca), v1 = mr_lds128(ca + 16u);
-            cv[0] = v0.x; cv[1] = v0.y; cv[2] = v0.z; cv[3] = v0.w;
-            cv[4] = v1.x; cv[5] = v1.y; cv[6] = v1.z; cv[7] = v1.w;
-          }
-          float bin[K];
-          {
-            float4 v = mr_lds128(a_up + rd_off);
-            if (from_carry) {
-              v = ((unsigned)(s - me.s_lo) <= own_span) ? gnext : make_float4(c == 0 ? 0.0f : INF, INF, INF, INF);
-              gnext = __ldcg(cme + (size_t)min(s + 1, nBe + 1) * CN);
-            }
-            bin[0] = v.x; bin[1] = v.y; bin[2] = v.z; bin[3] = v.w;
-          }
-          float dsh[R];
-          {
-            const float4 a4 = mr_lds128(a_dg + rd_off), b4 = mr_lds128(a_dg + rd_off + 16u);
-            dsh[0] = a4.x; dsh[1] = a4.y; dsh[2] = a4.z; dsh[3] = a4.w;
-            dsh[4] = b4.x; dsh[5] = b4.y; dsh[6] = b4.z; dsh[7] = b4.w;
-          }
-  #pragma unroll
-          for (int k = K - 1; k >= 0; k--) {
-            float up = bin[k];
-  #pragma unroll
-            for (int r = 0; r < R; r++) {
-              const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
-              const float d = dg + cv[r];
-              const float left = st[k][r];
-              const float t = fminf(d, up);
-              const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
-              const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
-              const float best = fminf(t, left);
-              acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
-              acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
-              st[k][r] = best;
-              up = best;
-            }
-          }
-          mr_sts128(a_me + wr_off, bin[K - 1], st[K - 1][0], st[K - 1][1], st[K - 1][2]);
-          mr_sts128(a_me + wr_off + 16u, st[K - 1][3], st[K - 1][4], st[K - 1][5], st[K - 1][6]);
-          mr_sts128(a_me + wr_off + 32u, st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]);
-  #pragma unroll
-          for (int k = 0; k < K; k++) bprev[k] = bin[k];
-          // bottom row of the pass -> carry[column j = s - wl]
-          if ((unsigned)(s - out_lo) <= own_span)
-            __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[0][R - 1], st[1][R - 1], st[2][R - 1], st[3][R - 1]));
-          if (s == tb_next) {
-            *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-            tbp += L.T;
-            tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
-          }
-          if (s == cost_step) {
-  #pragma unroll
-            for (int k = 0; k < K; k++) {
-              const int n = c * K + k;
-              if (n >= P.n_min && n <= P.n_max) cost_out[(size_t)sv * L.NP + (n - 1)] = st[k][R - 1];
-            }
-          }
-          // n < n_min: corner of the layer's window (dyn3d.cc:385, dyn3d.h:407-408)
-          if (WINDOWED && has_tile) {
-            const int nq = s - wl - P.wB + 1;
-            if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
-              const int rho = nq + P.wA - 2 + pad;
-              if ((rho >> 3) == w) {
-                const int kq = nq & 3, rq = rho & 7;
-                float v = 0.0f;
-  #pragma unroll
-                for (int k = 0; k < K; k++)
-  #pragma unroll
-                  for (int r = 0; r < R; r++)
-                    if (k == kq && r == rq) v = st[k][r];
-                cost_out[(size_t)sv * L.NP + (nq - 1)] = v;
-              }
-            }
-          }
-          if ((s & (MR_CBATCH - 1)) == 0)
-            mr_produce_c<NB1>(Cr, sA, sB, s + 1, WR, WRp, pad, nB, nBp, nb, P.dp_cutoff, tid, nthreads, rho0);
-          { const uint32_t t = rd_off; rd_off = wr_off; wr_off = t; }
-          MR_MP_SYNC(s);
+          step(std::integral_constant<int, 0>(), s, rd_off, wr_off);
+          const uint32_t t = rd_off; rd_off = wr_off; wr_off = t;
         }
       }
       for (; s <= nsteps; s++) {

@@ -1,0 +1,166 @@
+// mr_tile_step.cuh -- one column of a 4-layer x 8-row register tile of the 3-D DP
+// (Dyn3d::Solve_IncrN, lib/dyn/dyn3d.cc:283-382), shared by the single-pass kernel
+// (mr_dp_tiled.cuh) and the multi-pass kernel (mr_dp_tiled_mp.cuh).
+//
+//     A(n,i,j) = min{ d = A(n-1,i-1,j-1) + C(i,j),  up = A(n,i-1,j),  left = A(n,i,j-1) }
+// with the reference's tie order (match first, then "<=" skip-i, then "<=" skip-j).  Two bits
+// per cell go to the traceback word of the layer, MSB first in processing order (rows
+// ascending): (p1, p2) with
+//     p2 = 1  <=>  NOT (left <= min(d, up))         (the cell did not take skip-j)
+//     p1 = 1  <=>  NOT (up <= d), read only where p2 = 1
+// decoded as p2 = 0 -> skip-j, else p1 ? match : skip-i (TbTiled::decode).  Both predicates are
+// sign bits of float differences (exact in IEEE arithmetic; the cells never hold -0 or a
+// finite negative).  Two forms:
+//   ping-pong: the tile state is kept twice, read from one copy and written to the other, so
+//     best = min3(d, up, left) is one FMNMX3 and both predicates come from the new value:
+//     p2 = sign(best - left), p1 = sign(best - up) (where p2 = 1, best = min(d, up), so
+//     best < up <=> d < up).  The four layers are handled as two register pairs (layers 0/1
+//     and 2/3): d, best - up and best - left are packed FADD2 (sm_100 add.f32x2: two IEEE adds
+//     per issue slot); measured on B200 (scratch/ubench): +6 % over the scalar form.
+//   in place (two-min): t = min(d, up); p1 = sign(d - up); p2 = sign(t - left);
+//     best = min(t, left) written over `left`: one more FMNMX, half the registers.
+#pragma once
+#include "mr_device.cuh"
+
+// 16-byte shared-memory accesses through 32-bit shared addresses (one register each)
+__device__ __forceinline__ float4 mr_lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mr_sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+constexpr int MR_TK = 4;  // layers per tile
+constexpr int MR_TR = 8;  // rows per tile
+
+// inputs of a step: C(i, j) of the tile's rows (two 16-byte reads at ca), and the R values
+// A(n_lo-1, i-1, j-1) the lower-layer tile published last step (= its upper boundary and
+// rows 0..6 of its top layer after column j-1)
+__device__ __forceinline__ void mr_tile_load8(float (&v)[MR_TR], uint32_t a) {
+  const float4 v0 = mr_lds128(a), v1 = mr_lds128(a + 16u);
+  v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
+  v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+}
+
+// ping-pong form; S = source copy (the destination is 1 - S).  bprev[1 - S] must already hold
+// this column's upper boundary A(n, i_lo-1, j), bprev[S] still holds the previous column's.
+#ifndef MR_PP_FORM
+#define MR_PP_FORM 0  // 0: scalar, p1 = sign(d - up)   1: scalar, p1 = sign(best - up)   2: layer pairs, FADD2
+#endif
+template <int S>
+__device__ __forceinline__ void mr_tile_update_pp(float (&st)[2][MR_TK][MR_TR], float (&bprev)[2][MR_TK],
+                                                  uint32_t (&acc)[MR_TK], const float (&cv)[MR_TR],
+                                                  const float (&dsh)[MR_TR]) {
+  constexpr int D = 1 - S;
+#if MR_PP_FORM == 2
+  float2 upA = make_float2(bprev[D][0], bprev[D][1]), upB = make_float2(bprev[D][2], bprev[D][3]);
+  float2 dgA = make_float2(bprev[S][0], bprev[S][1]), dgB = make_float2(bprev[S][2], bprev[S][3]);
+#pragma unroll
+  for (int r = 0; r < MR_TR; r++) {
+    const float2 c2 = make_float2(cv[r], cv[r]);
+    // d of layers (1, 2) from the old values of layers (0, 1) one row up; layer 3 from layer 2
+    // (the upper lane of the second add is unused); layer 0 from the lower chunk's tile
+    const float2 d12 = __fadd2_rn(dgA, c2), d3x = __fadd2_rn(dgB, c2);
+    const float d0 = dsh[r] + cv[r];
+    const float2 lA = make_float2(st[S][0][r], st[S][1][r]), lB = make_float2(st[S][2][r], st[S][3][r]);
+    float2 bA, bB;
+    bA.x = fminf(fminf(d0, upA.x), lA.x);
+    bA.y = fminf(fminf(d12.x, upA.y), lA.y);
+    bB.x = fminf(fminf(d12.y, upB.x), lB.x);
+    bB.y = fminf(fminf(d3x.x, upB.y), lB.y);
+    const float2 zA = __fadd2_rn(bA, make_float2(-upA.x, -upA.y)), zB = __fadd2_rn(bB, make_float2(-upB.x, -upB.y));
+    const float2 sA = __fadd2_rn(bA, make_float2(-lA.x, -lA.y)), sB = __fadd2_rn(bB, make_float2(-lB.x, -lB.y));
+    acc[0] = __funnelshift_l(__float_as_uint(zA.x), acc[0], 1);
+    acc[1] = __funnelshift_l(__float_as_uint(zA.y), acc[1], 1);
+    acc[2] = __funnelshift_l(__float_as_uint(zB.x), acc[2], 1);
+    acc[3] = __funnelshift_l(__float_as_uint(zB.y), acc[3], 1);
+    acc[0] = __funnelshift_l(__float_as_uint(sA.x), acc[0], 1);
+    acc[1] = __funnelshift_l(__float_as_uint(sA.y), acc[1], 1);
+    acc[2] = __funnelshift_l(__float_as_uint(sB.x), acc[2], 1);
+    acc[3] = __funnelshift_l(__float_as_uint(sB.y), acc[3], 1);
+    dgA = lA; dgB = lB;
+    st[D][0][r] = bA.x; st[D][1][r] = bA.y; st[D][2][r] = bB.x; st[D][3][r] = bB.y;
+    upA = bA; upB = bB;
+  }
+#else
+#pragma unroll
+  for (int k = MR_TK - 1; k >= 0; k--) {
+    float up = bprev[D][k];
+#pragma unroll
+    for (int r = 0; r < MR_TR; r++) {
+      const float dg = (k > 0) ? ((r > 0) ? st[S][k - 1][r - 1] : bprev[S][k - 1]) : dsh[r];
+      const float d = dg + cv[r];
+      const float left = st[S][k][r];
+      const float best = fminf(fminf(d, up), left);
+#if MR_PP_FORM == 1
+      const float s1 = __fsub_rn(best, up);
+#else
+      const float s1 = __fsub_rn(d, up);       // sign set <=> NOT (up <= d)
+#endif
+      const float s2 = __fsub_rn(best, left);  // sign set <=> NOT (left <= min(d, up))
+      acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+      acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+      st[D][k][r] = best;
+      up = best;
+    }
+  }
+#endif
+}
+
+// in-place form; bin = this column's upper boundary, bprev = the previous column's (updated here)
+__device__ __forceinline__ void mr_tile_update_ip(float (&st)[MR_TK][MR_TR], float (&bprev)[MR_TK],
+                                                  const float (&bin)[MR_TK], uint32_t (&acc)[MR_TK],
+                                                  const float (&cv)[MR_TR], const float (&dsh)[MR_TR]) {
+#pragma unroll
+  for (int k = MR_TK - 1; k >= 0; k--) {
+    float up = bin[k];
+#pragma unroll
+    for (int r = 0; r < MR_TR; r++) {
+      const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
+      const float d = dg + cv[r];
+      const float left = st[k][r];
+      const float t = fminf(d, up);
+      const float s1 = __fsub_rn(d, up);    // sign set <=> NOT (up <= d)
+      const float s2 = __fsub_rn(t, left);  // sign set <=> NOT (left <= min(d, up))
+      const float best = fminf(t, left);
+      acc[k] = __funnelshift_l(__float_as_uint(s1), acc[k], 1);
+      acc[k] = __funnelshift_l(__float_as_uint(s2), acc[k], 1);
+      st[k][r] = best;
+      up = best;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MR_TK; k++) bprev[k] = bin[k];
+}
+
+// publish after a column: {upper boundary of the top layer, its rows 0..6} for the tile one chunk
+// up (next column, next step) and the bottom row of the 4 layers for the tile below (same column,
+// next step): 48 bytes at a_wr
+__device__ __forceinline__ void mr_tile_publish(uint32_t a_wr, float btop, const float (&top)[MR_TR], float b0, float b1,
+                                                float b2, float b3) {
+  mr_sts128(a_wr, btop, top[0], top[1], top[2]);
+  mr_sts128(a_wr + 16u, top[3], top[4], top[5], top[6]);
+  mr_sts128(a_wr + 32u, b0, b1, b2, b3);
+}
+
+// n < n_min: the reference reports the corner of the layer's window, A(n, n+wA-1, n+wB-1)
+// (dyn3d.cc:385, dyn3d.h:407-408): one layer per column.  j = column of this step.
+__device__ __forceinline__ void mr_tile_window_cost(const MrDevParams& P, const float (&st)[MR_TK][MR_TR], int j, int w, int c,
+                                                    int pad, float* __restrict__ cost_row) {
+  const int nq = j - P.wB + 1;
+  if (nq >= 1 && nq < P.n_min && nq <= P.n_max && (nq >> 2) == c) {
+    const int rho = nq + P.wA - 2 + pad;
+    if ((rho >> 3) == w) {
+      const int kq = nq & 3, rq = rho & 7;
+      float v = 0.0f;
+#pragma unroll
+      for (int k = 0; k < MR_TK; k++)
+#pragma unroll
+        for (int r = 0; r < MR_TR; r++)
+          if (k == kq && r == rq) v = st[k][r];
+      cost_row[nq - 1] = v;
+    }
+  }
+}
