@@ -93,6 +93,7 @@ struct mr_ctx {
   int64_t opt_chunk = 0;
   int64_t opt_nw_general = 0;   // force the thread-per-orientation NW filter
   int64_t opt_dp_only = 0;      // experiments: skip traceback/select (results invalid)
+  int64_t opt_costs_only_off = 0;  // tests / measurements: -IR FirstPass through the full kernel
   mr_stats st;
   std::vector<EventPair> events;
   size_t events_used = 0;
@@ -326,19 +327,21 @@ int ensure_chunk(mr_ctx* c, int64_t want) {
 // launch the 3-D DP for the survivors of the current chunk
 // latency: a few orientations whose result the host waits for (Refine batches): the multi-pass
 // kernel then spreads the passes of an orientation over a cluster of CTAs (split mode)
-int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count, bool latency = false) {
+// costs_only: no tie predicates and no traceback table (tiled kernels only; the general kernel
+// always writes its table) -- FirstPass under -IR, see search_device
+int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count, bool latency = false, bool costs_only = false) {
   EventPair* ev = next_events(c, 0);
   if (!ev) MR_FAIL(c, "cudaEventCreate failed");
   CU(c, cudaEventRecord(ev->a, c->stream));
   const int path = dp_path(c);
   if (path == 1) {
     if (mr_launch_dp_tiled(c->tiled, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
-                           c->d_tb, c->d_cost, count, c->stream) != 0)
+                           c->d_tb, c->d_cost, count, c->stream, costs_only) != 0)
       MR_FAIL(c, "tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else if (path == 2) {
     if (mr_launch_dp_tiled_mp(c->tiled_mp, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
                               c->d_tb, c->d_cost, count, c->stream,
-                              latency && c->opt_refine_split && count <= c->tiled_mp.split_cap) != 0)
+                              latency && c->opt_refine_split && count <= c->tiled_mp.split_cap, costs_only) != 0)
       MR_FAIL(c, "multi-pass tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   } else {
     if (c->use_gcol && !c->d_gcol) CU(c, cudaMalloc(&c->d_gcol, c->gcol_bytes));
@@ -449,6 +452,11 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
 // FirstPass over a device-resident list
 int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first_id) {
   if (count <= 0) return 0;
+  // -IR (refine_while_searching = 0): the score of an orientation is cost(n) itself
+  // (search_or_dyn3d.cc:576-589), so FirstPass needs no alignment: the DP runs without tie
+  // predicates / traceback words and the select kernel reads the costs.  The <= R winners get
+  // their paths in fetch_payload, which re-evaluates them with the full kernel.
+  const bool costs_only = !c->hp.refine_while_searching && use_tiled(c) && !c->opt_costs_only_off;
   if (c->hp.use_filter) {
     // Phase 1: filter the whole list (it needs nothing per orientation but two ints), so that
     // phase 2 runs the DP over full chunks of survivors whatever the pass rate -- at config-4
@@ -479,11 +487,12 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
       k_set_int<<<1, 1, 0, c->stream>>>(c->d_surv_count, cnt);
       CU(c, cudaGetLastError());
       c->surv = c->d_surv_all + s0;  // indices into the whole list
-      if (launch_dp(c, d_orient, cnt)) return 1;
+      if (launch_dp(c, d_orient, cnt, false, costs_only)) return 1;
       if (c->opt_dp_only) continue;
-      if (launch_tb<false>(c, d_orient, cnt, nullptr, 0)) return 1;
-      k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->surv, c->d_surv_count, c->d_cost, c->d_ssd,
-                                                        (long long)first_id, c->d_keys, nullptr, nullptr);
+      if (!costs_only && launch_tb<false>(c, d_orient, cnt, nullptr, 0)) return 1;
+      k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->surv, c->d_surv_count, c->d_cost,
+                                                        costs_only ? c->d_cost : c->d_ssd, (long long)first_id, c->d_keys,
+                                                        nullptr, nullptr);
       CU(c, cudaGetLastError());
       c->st.kernel_launches += 2;
     }
@@ -503,12 +512,12 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
     const int slot = (int)c->pending_counts.size();
     CU(c, cudaMemcpyAsync(&c->h_pinned[slot], c->d_surv_count, 4, cudaMemcpyDeviceToHost, c->stream));
     c->pending_counts.push_back({slot, cnt});
-    if (launch_dp(c, oc, cnt)) return 1;
+    if (launch_dp(c, oc, cnt, false, costs_only)) return 1;
     if (c->opt_dp_only) { c->st.orientations += cnt; continue; }
-    if (launch_tb<false>(c, oc, cnt, nullptr, 0)) return 1;
+    if (!costs_only && launch_tb<false>(c, oc, cnt, nullptr, 0)) return 1;
     k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->surv, c->d_surv_count,
-                                                      c->d_cost, c->d_ssd, (long long)(first_id + start),
-                                                      c->d_keys, nullptr, nullptr);
+                                                      c->d_cost, costs_only ? c->d_cost : c->d_ssd,
+                                                      (long long)(first_id + start), c->d_keys, nullptr, nullptr);
     CU(c, cudaGetLastError());
     c->st.kernel_launches++;
     c->st.orientations += cnt;
@@ -747,6 +756,7 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "budget_mb")) { c->opt_budget_mb = std::max<int64_t>(64, value); c->budget_is_default = false; }
   else if (!strcmp(name, "chunk")) c->opt_chunk = value;
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
+  else if (!strcmp(name, "ir_costs_only")) c->opt_costs_only_off = value == 0;
   else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);
   else if (!strcmp(name, "refine_batch")) c->opt_refine_batch = std::max<int64_t>(0, value);
   else if (!strcmp(name, "refine_split")) c->opt_refine_split = value != 0;

@@ -130,6 +130,7 @@ struct MrTiledPlan {
   size_t smem = 0;
   int ctas_per_sm = 1;
   int grid_cap = 0;
+  int grid_cap_costs = 0;  // costs-only kernel (fewer registers: two CTAs per SM up to 384 threads)
   size_t tb_words = 0;
   double lane_efficiency = 0.0;
   TbTiled layout;
@@ -198,7 +199,7 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
   }
 }
 
-template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP>
+template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP, bool COSTS = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
            const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
@@ -267,6 +268,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
 
     // tile state: the ping-pong form keeps two copies (read one, write the other), the in-place
     // form one; bprev = upper boundary A(n, i_lo-1, .) of the previous column (and, ping-pong, this one)
+    static_assert(!(COSTS && PP), "the costs-only update is in place");
     constexpr int NC = PP ? 2 : 1;
     float st[NC][K][R], bprev[NC][K];
     uint32_t acc[K];
@@ -306,12 +308,13 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
         mr_tile_update_pp<S>(st, bprev, acc, cv, dsh);
       } else {
         const float bin[K] = {ub.x, ub.y, ub.z, ub.w};
-        mr_tile_update_ip(st[0], bprev[0], bin, acc, cv, dsh);
+        if constexpr (COSTS) mr_tile_update_costs(st[0], bprev[0], bin, cv, dsh);
+        else mr_tile_update_ip(st[0], bprev[0], bin, acc, cv, dsh);
       }
       mr_tile_publish(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
                       st[D][3][R - 1]);
       // traceback: the K words of this tile every second column (j = s - w even)
-      if (s == tb_next) {
+      if (!COSTS && s == tb_next) {
         *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
         tbp += nthreads;
         tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
@@ -356,6 +359,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
 
 // ---------------------------------------------------------------------------------- host
 static inline int mr_dp_tiles_minb(int threads);
+static inline int mr_dp_tiles_minb_costs(int threads);
 static inline bool mr_dp_tiles_pp(int threads);
 static inline void mr_free_dp_tiled(MrTiledPlan* p) {
   if (p->d_tiles) cudaFree(p->d_tiles);
@@ -452,6 +456,7 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   const int want = mr_dp_tiles_minb(threads);  // CTAs per SM the launch-bound bucket of this CTA size allows
   p->ctas_per_sm = std::max(1, std::min(by_smem, want));
   p->grid_cap = prop.multiProcessorCount * p->ctas_per_sm;
+  p->grid_cap_costs = prop.multiProcessorCount * std::max(1, std::min(by_smem, mr_dp_tiles_minb_costs(threads)));
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
   p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = threads;
   p->layout.tile_of = p->d_tile_of;
@@ -465,14 +470,17 @@ template <int MAXT, int MINB, bool PP>
 static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& P, const float* A,
                                        const float* B, const float* orient, const int* surv,
                                        const int* surv_count, uint32_t* tb, float* cost, int count,
-                                       cudaStream_t stream) {
+                                       cudaStream_t stream, bool costs_only) {
   typedef void (*kern_t)(MrDevParams, TbTiled, int, int, const MrTile*, const float*, const float*, const float*,
                          const int*, const int*, uint32_t*, float*);
   static const kern_t kerns[4] = {k_dp_tiles<4, 8, MAXT, MINB, false, false, PP>, k_dp_tiles<4, 8, MAXT, MINB, false, true, PP>,
                                   k_dp_tiles<4, 8, MAXT, MINB, true, false, PP>, k_dp_tiles<4, 8, MAXT, MINB, true, true, PP>};
-  const kern_t kern = kerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
+  constexpr int MINB_C = MAXT <= 384 ? (MINB > 2 ? MINB : 2) : 1;
+  static const kern_t kerns_c[4] = {k_dp_tiles<4, 8, MAXT, MINB_C, false, false, false, true>, k_dp_tiles<4, 8, MAXT, MINB_C, false, true, false, true>,
+                                    k_dp_tiles<4, 8, MAXT, MINB_C, true, false, false, true>, k_dp_tiles<4, 8, MAXT, MINB_C, true, true, false, true>};
+  const kern_t kern = (costs_only ? kerns_c : kerns)[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
   if (mr_ensure_smem(kern, p.smem)) return 1;
-  const int grid = std::min(count, p.grid_cap);
+  const int grid = std::min(count, costs_only ? p.grid_cap_costs : p.grid_cap);
   kern<<<grid, p.threads, p.smem, stream>>>(P, p.layout, p.nslots, p.steps, p.d_tiles, A, B, orient,
                                            surv, surv_count, tb, cost);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -492,6 +500,10 @@ static inline int mr_dp_tiles_minb(int threads) {
 #undef MR_X
   return 1;
 }
+static inline int mr_dp_tiles_minb_costs(int threads) {
+  const int b = mr_dp_tiles_minb(threads);
+  return threads <= 384 ? std::max(b, 2) : 1;
+}
 static inline bool mr_dp_tiles_pp(int threads) {
 #define MR_X(MAXT, MINB, PP) if (threads <= MAXT) return PP;
   MR_DP_BUCKETS(MR_X)
@@ -502,10 +514,10 @@ static inline bool mr_dp_tiles_pp(int threads) {
 static inline int mr_launch_dp_tiled(const MrTiledPlan& p, const MrDevParams& P, const float* A,
                                      const float* B, const float* orient, const int* surv,
                                      const int* surv_count, uint32_t* tb, float* cost, int count,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, bool costs_only = false) {
 #define MR_X(MAXT, MINB, PP) \
-  if (p.threads <= MAXT) return mr_launch_dp_tiles_t<MAXT, MINB, PP>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+  if (p.threads <= MAXT) return mr_launch_dp_tiles_t<MAXT, MINB, PP>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream, costs_only);
   MR_DP_BUCKETS(MR_X)
 #undef MR_X
-  return mr_launch_dp_tiles_t<1024, 1, false>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+  return mr_launch_dp_tiles_t<1024, 1, false>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream, costs_only);
 }

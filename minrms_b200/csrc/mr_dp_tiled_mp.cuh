@@ -67,7 +67,7 @@ struct MrTileMp {
   int pad_;
 };
 
-template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP, bool SPLIT = false>
+template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP, bool SPLIT = false, bool COSTS = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, const MrPass* __restrict__ passes,
               const MrTileMp* __restrict__ tiles, const float* __restrict__ A, const float* __restrict__ B,
@@ -162,6 +162,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
       // tile state and step: as in k_dp_tiles (mr_tile_step.cuh); the upper boundary of a pass's
       // first strip comes from the carry buffer (fetched one column ahead into a register), and
       // the bottom row of its last strip goes there
+      static_assert(!(COSTS && PP), "the costs-only update is in place");
       constexpr int NC = PP ? 2 : 1;
       float st[NC][K][R], bprev[NC][K];
       uint32_t acc[K];
@@ -203,14 +204,15 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
           mr_tile_update_pp<S>(st, bprev, acc, cv, dsh);
         } else {
           const float bin[K] = {ub.x, ub.y, ub.z, ub.w};
-          mr_tile_update_ip(st[0], bprev[0], bin, acc, cv, dsh);
+          if constexpr (COSTS) mr_tile_update_costs(st[0], bprev[0], bin, cv, dsh);
+          else mr_tile_update_ip(st[0], bprev[0], bin, acc, cv, dsh);
         }
         mr_tile_publish(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
                         st[D][3][R - 1]);
         // bottom row of the pass -> carry[column j = s - wl]
         if ((unsigned)(s - out_lo) <= own_span)
           __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1], st[D][3][R - 1]));
-        if (s == tb_next) {
+        if (!COSTS && s == tb_next) {
           *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
           tbp += L.T;
           tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;
@@ -487,7 +489,7 @@ template <int MAXT, int MINB, bool PP>
 static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevParams& P, const float* A,
                                           const float* B, const float* orient, const int* surv,
                                           const int* surv_count, uint32_t* tb, float* cost, int count,
-                                          cudaStream_t stream, bool split = false) {
+                                          cudaStream_t stream, bool split = false, bool costs_only = false) {
   typedef void (*kern_t)(MrDevParams, TbTiled, int, int, int, const MrPass*, const MrTileMp*, const float*,
                          const float*, const float*, const int*, const int*, float4*, size_t, uint32_t*, float*);
   if constexpr (MAXT == 512 && PP) {
@@ -518,7 +520,9 @@ static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevPar
   }
   static const kern_t kerns[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false, PP>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true, PP>,
                                   k_dp_tiles_mp<4, 8, MAXT, MINB, true, false, PP>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true, PP>};
-  const kern_t kern = kerns[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
+  static const kern_t kerns_c[4] = {k_dp_tiles_mp<4, 8, MAXT, MINB, false, false, false, false, true>, k_dp_tiles_mp<4, 8, MAXT, MINB, false, true, false, false, true>,
+                                    k_dp_tiles_mp<4, 8, MAXT, MINB, true, false, false, false, true>, k_dp_tiles_mp<4, 8, MAXT, MINB, true, true, false, false, true>};
+  const kern_t kern = (costs_only ? kerns_c : kerns)[(P.nb == 1 ? 2 : 0) + (P.n_min > 1 ? 1 : 0)];
   if (mr_ensure_smem(kern, p.smem)) return 1;
   const int grid = std::min(count, p.grid_cap);
   kern<<<grid, p.threads, p.smem, stream>>>(P, p.layout, p.nslots, p.npasses, p.wl_max, p.d_passes, p.d_tiles, A, B,
@@ -529,12 +533,12 @@ static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevPar
 static inline int mr_launch_dp_tiled_mp(const MrTiledMpPlan& p, const MrDevParams& P, const float* A,
                                         const float* B, const float* orient, const int* surv,
                                         const int* surv_count, uint32_t* tb, float* cost, int count,
-                                        cudaStream_t stream, bool split = false) {
+                                        cudaStream_t stream, bool split = false, bool costs_only = false) {
 #define MR_TRY(MAXT, MINB, PP) \
-  if (p.threads == MAXT) return mr_launch_dp_tiles_mp_t<MAXT, MINB, PP>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream, split)
+  if (p.threads == MAXT) return mr_launch_dp_tiles_mp_t<MAXT, MINB, PP>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream, split && !costs_only, costs_only)
   MR_TRY(512, 1, true);
   MR_TRY(640, 1, false);
   MR_TRY(768, 1, false);
 #undef MR_TRY
-  return mr_launch_dp_tiles_mp_t<1024, 1, false>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream);
+  return mr_launch_dp_tiles_mp_t<1024, 1, false>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream, false, costs_only);
 }

@@ -135,6 +135,28 @@ __device__ __forceinline__ void mr_tile_update_ip(float (&st)[MR_TK][MR_TR], flo
   for (int k = 0; k < MR_TK; k++) bprev[k] = bin[k];
 }
 
+// costs only (no tie predicates, no traceback words): FirstPass under -IR, where the score of an
+// orientation is the DP cost itself (search_or_dyn3d.cc:576-589) and only the <= R winners need a
+// path (they are re-evaluated by the full kernel).  In place: layers descend, so the old value of
+// (k-1, r-1) is still there when (k, r) reads it.  1 FADD + 1 FMNMX3 per cell.
+__device__ __forceinline__ void mr_tile_update_costs(float (&st)[MR_TK][MR_TR], float (&bprev)[MR_TK],
+                                                     const float (&bin)[MR_TK], const float (&cv)[MR_TR],
+                                                     const float (&dsh)[MR_TR]) {
+#pragma unroll
+  for (int k = MR_TK - 1; k >= 0; k--) {
+    float up = bin[k];
+#pragma unroll
+    for (int r = 0; r < MR_TR; r++) {
+      const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
+      const float best = fminf(fminf(dg + cv[r], up), st[k][r]);
+      st[k][r] = best;
+      up = best;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MR_TK; k++) bprev[k] = bin[k];
+}
+
 // publish after a column: {upper boundary of the top layer, its rows 0..6} for the tile one chunk
 // up (next column, next step) and the bottom row of the 4 layers for the tile below (same column,
 // next step): 48 bytes at a_wr

@@ -453,3 +453,25 @@ def test_refine_with_cluster_split_dp_matches_oracle(case):
         assert got_ev == ev
         assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "refine")
     assert np.any(best["ssd"] < 1e26)
+
+
+@pytest.mark.parametrize("kernel", [0, 3])
+def test_ir_costs_only_first_pass_equals_full_kernel(kernel, golden_ir_off):
+    """-IR: FirstPass scores an orientation by the DP cost (search_or_dyn3d.cc:576-589), so it
+    runs the costs-only form of the tiled kernels (no tie predicates, no traceback table) and
+    only the winners are re-evaluated with the full kernel: same table as FirstPass through
+    the full kernel, and as the reference (strict_search_* of the -IR fixture)"""
+    from minrms_b200 import OrientationGenerator
+    g = golden_ir_off
+    tabs = []
+    for costs_only in (1, 0):
+        s = make_search(g["A"], g["B"], settings_from_golden(g), kernel)
+        s.set_option("ir_costs_only", costs_only)
+        og = OrientationGenerator(s)
+        s.Search(og, 0, og.size())
+        tabs.append(s.best_table())
+        s.close()
+    a, b = tabs
+    assert_table_equal(a["ssd"], a["T"], a["pairs"], b["ssd"], b["T"], b["pairs"], int(g["n_min"]), "costs-only vs full")
+    assert_table_equal(a["ssd"], a["T"], a["pairs"], g["strict_search_ssd"], g["strict_search_T"],
+                       g["strict_search_pairs"], int(g["n_min"]), "costs-only vs reference")
