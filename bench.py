@@ -1,19 +1,32 @@
 #!/usr/bin/env python3
 """bench.py -- MINRMS per-orientation search throughput on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config {1,2,3,4,5}]
+                  [--scaling {weak,strong}] [--orientations M] [--impl reference]
 
-Workload (BASELINE.json configs[1]): the reference's own test pair -- hemoglobin chain A
-(141 CA) vs myoglobin (151 CA), tests/test_typical_usage.sh -- searched UNCONSTRAINED:
-`minrms -fm 4 -HS -ir` = 20 424 orientations x 1 044 481 DP cells, all 140 alignment sizes
-refined by Kabsch for every orientation.  One "step" = one complete FirstPass over the
-orientation list of this rank.  With N GPUs every rank gets its own copy of the list under
-distinct orientation ids (weak scaling: per-GPU work fixed), followed by the NCCL
-min-reduction of the per-size best records.
+Default workload (BASELINE.json configs[1], `--config 2`): the reference's own test pair --
+hemoglobin chain A (141 CA) vs myoglobin (151 CA), tests/test_typical_usage.sh -- searched
+UNCONSTRAINED: `minrms -fm 4 -HS -ir` = 20 424 orientations x 1 044 481 DP cells, all 140
+alignment sizes refined by Kabsch for every orientation.  One "step" = one complete FirstPass
+over the orientations of this rank, followed (N > 1) by the cross-GPU reduction of the per-size
+records: an NCCL all_reduce(MIN) over the 64-bit keys in device memory, the winners' payload
+from the owning ranks, one all_gather (minrms_b200/dist.py).
+
+  --scaling weak    every rank searches its own copy of the list under its own ids (per-GPU
+                    work fixed; the driver's SCALE run)
+  --scaling strong  ONE list, partitioned over the ranks (dist.partition): what `minrms A B`
+                    on N GPUs does; the merged table is checked against rank 0's own search
+  --config 1        the test pair with the reference's test flags (-of 8.0,0.33 -minN 0.33
+                    -max-rmsd 3.5): NW filter + early exits
+  --config 3 / 4    synthetic 600x600 (-fm 3) / 2000x1500 (-of 8.0,0.33) pairs, seeded
+  --config 5        all-vs-all of --chains synthetic chains (150-400 residues), pairs sharded
+  --orientations M  search only the first M orientations of the list per step
 
 Prints ONE JSON line (rank 0).  `value` = orientations/s with the orientation list already
 resident in HBM; `e2e` = the same through the host-buffer C-ABI call (mr_search: H2D of the
-list from pinned memory + D2H of the best table inside the timed region).
+list from pinned memory + D2H of the best table inside the timed region).  On the default
+line also: `full_run` (orientation generation + FirstPass + Refine through the public API)
+and `nw_filter` (the NW orientation filter of config 1 with its own roofline).
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/fast, built by
 oracle/build_ref.sh) on the host cores instead.
 """
@@ -23,6 +36,7 @@ import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -31,9 +45,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-REF_ARGS = ["-fm", "4", "-HS", "-ir", "-R"]   # config 2, FirstPass only (the timed path)
-WORKLOAD = "hemoglobin(4hhb:A,141)xmyoglobin(1a6m,151) unconstrained: minrms -fm 4 -HS -ir (config 2)"
-M, NB, NMIN, NMAX, FRAG = 141, 151, 1, 141, 4
+CPU_CELLS_PER_S_PER_CORE = 0.22e9   # Dyn3d::Solve_IncrN of the reference, measured; used only where stated
 
 
 def peaks():
@@ -82,66 +94,209 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def ref_bench(procs, per_proc, repeat):
+# ---------------------------------------------------------------------------------- workloads
+def workload(cfg):
+    """pair, settings and the reference command line of a BASELINE.json configuration"""
+    from minrms_b200 import Settings, load_ca_pdb
+    from minrms_b200.search import interpret_num_matches
+    from minrms_b200.synth import random_chain, related_chain
+    if cfg in (1, 2):
+        A = load_ca_pdb(os.path.join(GOLDEN, "hemoglobin.pdb"))
+        B = load_ca_pdb(os.path.join(GOLDEN, "myoglobin.pdb"))
+        pdbs = (os.path.join(GOLDEN, "hemoglobin.pdb") + ",*.A", os.path.join(GOLDEN, "myoglobin.pdb"))
+        data = "fixture (CA traces of the reference's test pair, tests/golden/*.pdb)"
+        if cfg == 2:
+            return dict(cfg=2, A=A, B=B, pdbs=pdbs, data=data, settings=Settings(fm_fragment_size=4),
+                        ref_args=["-fm", "4", "-HS", "-ir", "-R"],
+                        name="hemoglobin(4hhb:A,141)xmyoglobin(1a6m,151) unconstrained: minrms -fm 4 -HS -ir (config 2)")
+        k = interpret_num_matches(0.33, 141, 151)
+        st = Settings(fm_fragment_size=4, n_min=k, dyn3d_max_rmsd=3.5, orientation_filter_nw=True,
+                      orientation_filter_nw_max_dist=8.0, orientation_filter_nw_min_num_matches=k)
+        return dict(cfg=1, A=A, B=B, pdbs=pdbs, data=data, settings=st,
+                    ref_args=["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.5", "-ir", "-R"],
+                    name="hemoglobin(4hhb:A,141)xmyoglobin(1a6m,151): minrms -fm 4 -of 8.0,0.33 -HS -minN 0.33 -max-rmsd 3.5 -ir (config 1)")
+    if cfg == 3:
+        A = random_chain(np.random.default_rng(3000), 600)
+        B = related_chain(np.random.default_rng(3001), A, 600, noise=1.5)
+        return dict(cfg=3, A=A, B=B, pdbs=None, data="synthetic (seeds 3000/3001, minrms_b200/synth.py)",
+                    settings=Settings(fm_fragment_size=3), ref_args=["-fm", "3", "-HS", "-ir", "-R"],
+                    name="synthetic 600x600, minrms -fm 3 -HS -ir, all sizes (config 3)")
+    if cfg == 4:
+        A = random_chain(np.random.default_rng(4000), 2000)
+        B = related_chain(np.random.default_rng(4001), A, 1500, noise=1.0)
+        k = interpret_num_matches(0.33, 2000, 1500)
+        st = Settings(fm_fragment_size=4, orientation_filter_nw=True, orientation_filter_nw_max_dist=8.0,
+                      orientation_filter_nw_min_num_matches=k)
+        return dict(cfg=4, A=A, B=B, pdbs=None, data="synthetic (seeds 4000/4001, minrms_b200/synth.py)", settings=st,
+                    ref_args=["-fm", "4", "-of", "8.0,0.33", "-HS", "-ir", "-R"],
+                    name="synthetic 2000x1500, minrms -fm 4 -of 8.0,0.33 -HS -ir (config 4)")
+    raise SystemExit("unknown --config %r" % cfg)
+
+
+def ref_bench(w, procs, per_proc, repeat):
     """the reference's own Search(og,start,stop) on `procs` host processes (oracle/ref_bench.cc)"""
     exe = os.path.join(ROOT, "oracle", "_ref", "fast", "ref_bench")
     if not os.path.exists(exe):
         return None
-    out = subprocess.run([exe, str(procs), str(per_proc), str(repeat)] + REF_ARGS +
-                         ["hemoglobin.pdb,*.A", "myoglobin.pdb"], cwd=GOLDEN, capture_output=True, text=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        pdbs = w["pdbs"]
+        if pdbs is None:
+            from minrms_b200.synth import write_ca_pdb
+            write_ca_pdb(os.path.join(tmp, "a.pdb"), w["A"])
+            write_ca_pdb(os.path.join(tmp, "b.pdb"), w["B"])
+            pdbs = (os.path.join(tmp, "a.pdb"), os.path.join(tmp, "b.pdb"))
+        out = subprocess.run([exe, str(procs), str(per_proc), str(repeat)] + w["ref_args"] + list(pdbs),
+                             cwd=tmp, capture_output=True, text=True)
     res = []
     for line in out.stdout.splitlines():
         if line.startswith("ref_bench"):
             kv = dict(x.split("=") for x in line.split()[1:])
             if int(kv["failed"]) == 0:
-                res.append((int(kv["orientations"]), float(kv["seconds"])))
+                res.append((int(kv["orientations"]), float(kv["seconds"]), int(kv["total"])))
     return res
+
+
+def ref_sample_size(w):
+    """orientations per process and step for about a second of reference work per step"""
+    from minrms_b200.search import dp_cells_per_orientation
+    m, nB = w["A"].shape[0], w["B"].shape[0]
+    if w["cfg"] == 1:
+        return 1100          # NW filter on all, DP on 15 %: the whole list in ~1 s on 16 cores
+    cells = dp_cells_per_orientation(m, nB, 1, min(m, nB))
+    return max(1, int(CPU_CELLS_PER_S_PER_CORE / cells))
+
+
+def common_config(w, args, per_step):
+    """the keys both arms print (the driver compares the two `config` objects)"""
+    return {"workload": w["name"], "config": w["cfg"], "scaling": args.scaling,
+            "orientations_in_list": per_step}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from minrms_b200.search import dp_cells_per_orientation
+    w = workload(args.config)
+    m, nB = w["A"].shape[0], w["B"].shape[0]
     cores = os.cpu_count() or 1
-    per_proc = 160                       # ~1 s per process per step at ~160 orientations/s/core
-    cells = 1044481
-    res = ref_bench(cores, per_proc, args.warmup + args.steps)
+    per_proc = ref_sample_size(w)
+    if w["cfg"] in (3, 4):
+        # one orientation costs minutes of a host core here (72 M / 1 689 M cells at ~0.2 GCUPS; at
+        # config-4 size any survivor of the filter): no bounded sample exists
+        print(json.dumps({"impl": "reference", "unavailable": "config %d: one orientation costs minutes of a host core "
+                          "(DESIGN.md 3: CPU figures for configs 3-4 are extrapolated from the measured cell rate)" % w["cfg"]}))
+        return
+    res = ref_bench(w, cores, per_proc, args.warmup + args.steps)
     if not res:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fast/ref_bench not built"}))
         return
+    total = res[0][2]
     res = res[args.warmup:]
     n = sum(r[0] for r in res)
     t = sum(r[1] for r in res)
     v = n / t
-    sample = "%d orientations/step (%d per process x %d processes) of the 20424, Search(og,start,stop) of the unmodified reference, shipped flags -O3 -ffast-math" % (res[0][0], per_proc, cores)
+    cells = dp_cells_per_orientation(m, nB, w["settings"].n_min, min(m, nB))
+    sample = ("%d orientations/step (%d per process x %d processes) of the %d, Search(og,start,stop) of the unmodified "
+              "reference, shipped flags -O3 -ffast-math" % (res[0][0], res[0][0] // cores, cores, total))
     line = {"metric": "orientations_per_sec", "value": v, "unit": "orientations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(res),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "fixture", "impl": "reference", "dp_gcups": v * cells / 1e9,
-            "config": {"workload": WORKLOAD, "orientations_per_step": res[0][0]},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": w["data"], "impl": "reference", "dp_gcups": v * cells / 1e9,
+            "config": common_config(w, args, total),
             "cpu_baseline": {"value": v, "unit": "orientations/s", "cores": cores, "kind": "reference",
                              "sample": sample},
             "e2e": {"value": v, "unit": "orientations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------- config 5
+def run_all_vs_all(args):
+    """BASELINE config 5 shape: every unordered pair of --chains synthetic chains (150-400
+    residues, seeds 5000+i), -fm 4, FirstPass (+ Refine with --refine); pairs sharded over the
+    ranks by cost (minrms_b200/batch.py), no exchange.  A step = the whole batch."""
+    import torch
+    import torch.distributed as dist
+    from minrms_b200 import Settings
+    from minrms_b200.batch import all_vs_all, pair_cost
+    from minrms_b200.synth import random_chain
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    chains = []
+    for i in range(args.chains):
+        rng = np.random.default_rng(5000 + i)
+        chains.append(random_chain(rng, int(rng.integers(150, 401))))
+    st = Settings(fm_fragment_size=4)
+    lens = [c.shape[0] for c in chains]
+    cells = sum(pair_cost(lens[i], lens[j], st) for i in range(len(lens)) for j in range(i + 1, len(lens)))
+    times, ori = [], 0
+    for it in range(args.warmup_batches + args.steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = all_vs_all(chains, st, rank, world, local, refine=args.refine, workers=args.workers)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0, float(sum(r.orientations for r in res.values())), float(len(res))],
+                         dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t[0] = tm[0]
+        if it >= args.warmup_batches:
+            times.append(float(t[0]))
+        ori, npairs = int(t[1]), int(t[2])
+    if rank == 0:
+        sec = sum(times) / len(times)
+        print(json.dumps({
+            "metric": "orientations_per_sec", "value": ori / sec, "unit": "orientations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup_batches, "ms_per_step": 1e3 * sec, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeds 5000+i, minrms_b200/synth.py)",
+            "config": {"workload": "all-vs-all of %d synthetic chains (%d..%d residues), -fm 4%s (config 5 shape)" % (
+                len(lens), min(lens), max(lens), " + Refine" if args.refine else ", FirstPass only"),
+                "config": 5, "pairs": npairs, "orientations": ori, "dp_cells": cells, "workers_per_gpu": args.workers,
+                "parallelism": "pairs sharded over %d rank(s) by cost (LPT), no exchange" % world},
+            "pairs_per_sec": npairs / sec, "dp_gcups": cells / sec / 1e9,
+            "note": "end to end per batch: contexts, orientation generation, FirstPass%s, tables to the host" % (
+                ", Refine" if args.refine else "")}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=160)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--orientations", type=int, default=0, help="search only the first M orientations per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip full_run / nw_filter / strong-scaling extras")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 column-sweep, 2 tiled")
+    ap.add_argument("--chains", type=int, default=8, help="config 5: number of chains")
+    ap.add_argument("--workers", type=int, default=1, help="config 5: host threads (contexts) per GPU")
+    ap.add_argument("--refine", action="store_true", help="config 5: Refine after FirstPass")
+    ap.add_argument("--warmup-batches", type=int, default=1, help="config 5: untimed batches")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 5:
+        return run_all_vs_all(args)
     args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
-    from minrms_b200 import OrientationGenerator, SearchOrCuda, Settings, load_ca_pdb
-    from minrms_b200.dist import allreduce_best
+    from minrms_b200 import OrientationGenerator, SearchOrCuda
+    from minrms_b200.dist import partition, reduce_best_device
+    from minrms_b200.search import dp_cells_per_orientation
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -159,9 +314,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    A = load_ca_pdb(os.path.join(GOLDEN, "hemoglobin.pdb"))
-    B = load_ca_pdb(os.path.join(GOLDEN, "myoglobin.pdb"))
-    st = Settings(n_min=NMIN, n_max=NMAX, fm_fragment_size=FRAG)
+    w = workload(args.config)
+    A, B, st = w["A"], w["B"], w["settings"]
+    m, nB = A.shape[0], B.shape[0]
     s = SearchOrCuda(A, B, st, device=local)
     if args.kernel:
         s.set_option("dp_kernel", args.kernel)
@@ -170,11 +325,17 @@ def main():
     if os.environ.get("MR_EXP_DP_ONLY"):
         s.set_option("exp_dp_only", 1)   # kernel experiments only: results are invalid
     og = OrientationGenerator(s)
-    count = og.size()
-    cells_per = s.lib.mr_dp_cells_per_orientation(M, NB, NMIN, NMAX)
-    id0 = rank * count                      # this rank's ids (weak scaling: own copy of the list)
+    total = og.size()
+    count = min(total, args.orientations) if args.orientations > 0 else total   # list searched per step
+    cells_per = dp_cells_per_orientation(m, nB, s.n_min, s.n_max)
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        first, stop = partition(count, rank, world)      # my share of ONE list, global ids
+        id0, mine, job = first, stop - first, count
+    else:
+        first, id0, mine, job = 0, rank * count, count, count * world   # own copy, own ids
     pinned = torch.empty((count, 12), dtype=torch.float32).pin_memory()
-    pinned.copy_(torch.from_numpy(og.orientations))
+    pinned.copy_(torch.from_numpy(og.orientations[:count]))
     host_orient = pinned.numpy()
 
     # ---------------- device-resident arm: `value` -----------------------------------
@@ -182,7 +343,10 @@ def main():
 
     def step_resident():
         s.reset_best()
-        s.search_resident(0, count, id0)
+        s.search_resident(first, mine, id0)
+        if world > 1:
+            return reduce_best_device(s, dev)
+        return None
 
     for _ in range(args.warmup):
         step_resident()
@@ -192,56 +356,86 @@ def main():
         sampler.start()
         time.sleep(0.3)
     barrier()
-    s.event_record(0)
     t0 = time.perf_counter()
+    search_ms = 0.0
     for _ in range(args.steps):
-        step_resident()
-    s.event_record(1)
-    dev_ms = s.event_elapsed_ms(0, 1)
+        s.event_record(0)
+        s.reset_best()
+        s.search_resident(first, mine, id0)
+        s.event_record(1)
+        search_ms += s.event_elapsed_ms(0, 1)        # CUDA events on the library's stream
+        if world > 1:
+            table = reduce_best_device(s, dev)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
     stats = s.stats()
-    t = torch.tensor([dev_ms / 1e3, wall], dtype=torch.float64, device=dev)
+    t = torch.tensor([search_ms / 1e3, wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s, wall_s = float(t[0]), float(t[1])
-    # the (tiny) cross-GPU reduction of the per-size records, timed separately
-    s.fetch_best()
-    table = s.best_table()
-    red_ms = 0.0
-    if world > 1:
-        allreduce_best(table, device=dev)    # first use sets up the NCCL channels
-        barrier()
-        r0 = time.perf_counter()
-        table = allreduce_best(table, device=dev)
-        barrier()
-        red_ms = 1e3 * (time.perf_counter() - r0)
-    # N > 1: every search ends with the cross-GPU reduction of the per-size records, so its
-    # time (max over ranks, measured above) is charged to every step of `value`
-    step_s = dev_s / args.steps + red_ms * 1e-3
-    value = count * world / step_s
+    if world == 1:
+        s.fetch_best()
+        table = s.best_table()
+        step_s = dev_s / args.steps                 # device time (events), one GPU: nothing else in a step
+    else:
+        step_s = wall_s / args.steps                # barrier to barrier, max over ranks: search + reduction
+    red_ms = max(0.0, 1e3 * (wall_s - dev_s) / args.steps) if world > 1 else 0.0
+    value = job / step_s
+
+    # strong scaling: the merged table must be what one GPU finds on the whole list
+    strong_check = None
+    if strong and not args.no_extras:
+        s.reset_best()
+        s.search_resident(0, count, 0)
+        s.fetch_best()
+        solo = s.best_table()
+        strong_check = bool(np.array_equal(solo["ssd"].view(np.uint32), table["ssd"].view(np.uint32)) and
+                            np.array_equal(solo["o_id"], table["o_id"]) and
+                            np.array_equal(solo["T"].view(np.uint32), table["T"].view(np.uint32)))
 
     # ---------------- end-to-end arm through the host-buffer C ABI: `e2e` -------------
+    def step_e2e():
+        s.reset_best()
+        s.Search(host_orient, first, first + mine, first_id=id0)   # mr_search: H2D list, kernels, D2H table
+        if world > 1:
+            reduce_best_device(s, dev)
+
+    e_steps = max(3, min(args.steps, 40))
     for _ in range(2):
-        s.reset_best(); s.Search(host_orient)
+        step_e2e()
     st_before = s.stats()
     barrier()
     e0 = time.perf_counter()
-    for _ in range(args.steps):
-        s.reset_best()
-        s.Search(host_orient)               # mr_search: H2D list, kernels, D2H table
-        if world > 1:
-            allreduce_best(s.best_table(), device=dev)
+    for _ in range(e_steps):
+        step_e2e()
     barrier()
     e_wall = time.perf_counter() - e0
     te = torch.tensor([e_wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     st_after = s.stats()
-    e2e_value = count * world * args.steps / float(te[0])
-    h2d = (st_after["h2d_bytes"] - st_before["h2d_bytes"]) // args.steps
-    d2h = (st_after["d2h_bytes"] - st_before["d2h_bytes"]) // args.steps
+    e2e_value = job * e_steps / float(te[0])
+    h2d = (st_after["h2d_bytes"] - st_before["h2d_bytes"]) // e_steps
+    d2h = (st_after["d2h_bytes"] - st_before["d2h_bytes"]) // e_steps
+
+    # ---------------- extras on one GPU: the whole run, and the NW filter ---------------
+    full_run = nw_filter = None
+    if world == 1 and not args.no_extras:
+        reps = 3 if cells_per * total < 5e11 else 1
+        evals = 0
+        f0 = time.perf_counter()
+        for _ in range(reps):
+            s2 = SearchOrCuda(A, B, st, device=local)
+            og2 = OrientationGenerator(s2)
+            s2.Search(og2, 0, count)
+            evals = s2.Refine() if np.any(s2.aSumSqdDists[:s2.R] < 1e26) else 0
+            s2.close()
+        f_s = (time.perf_counter() - f0) / reps
+        full_run = {"value": count / f_s, "unit": "orientations/s", "ms": 1e3 * f_s, "refine_evaluations": int(evals),
+                    "what": "context + orientation generation (GPU) + FirstPass + Refine + tables on the host, "
+                            "through SearchOrCuda (the calls bin/minrms/main.cc:123-173 makes), warm process"}
+        nw_filter = measure_nw_filter(local, clocks)
 
     if rank != 0:
         if world > 1:
@@ -260,7 +454,7 @@ def main():
     tb_bytes = 0.25 * stats["dp_cells"] / launches          # 2-bit traceback, algorithmic
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):                                # dram bytes from one ncu --set full capture
+    if os.path.exists(tpath) and w["cfg"] == 2:              # dram bytes from one ncu --set full capture
         tj = json.load(open(tpath))
         per_o = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["orientations_in_launch"]
         traffic = per_o * stats["orientations_dp"] / launches
@@ -272,47 +466,106 @@ def main():
                 "avg_launch_ms": dp_ms / launches,
                 "cells_per_launch": stats["dp_cells"] / launches,
                 "traffic": traffic,
-                "alu_pipe_ceiling": {"peak": sms * 64 * f_mhz * 1e6 / 2 / 1e9, "unit": "GCUPS",
-                                     "def": "2 FMIN per cell on the half-rate ALU pipe (64 lanes/clk/SM)",
-                                     "frac": dp_gcups_kernel / (sms * 64 * f_mhz * 1e6 / 2 / 1e9)},
+                "measured_ceilings": {
+                    "unit": "GCUPS",
+                    "cell_update_all_lanes_live": 4700.0,
+                    "with_exchange_and_barrier": 3700.0,
+                    "def": "scratch/ubench/cell_ubench.cu on B200: the kernel's 6-instruction cell update (3 FADD, FMNMX3, 2 SHF) "
+                           "alone in registers, 12 warps/SM, every lane live; and with the per-column shared-memory exchange and "
+                           "CTA barrier.  The register file delivers 2 operands/clk/sub-partition (op_ubench.cu: FADD2 2 clk, "
+                           "FFMA2 3 clk) and a cell reads 13: profiles/README.md"},
                 "hbm": {"bound": "hbm", "achieved": tb_bytes / (dp_ms / launches * 1e-3) / 1e9 if dp_ms else 0.0,
                         "peak": pk["hbm_gbs"], "unit": "GB/s", "peak_kind": pk_kind,
                         "algorithmic_bytes_per_launch": tb_bytes,
                         "note": "2-bit traceback codes written once; the DP is issue-bound, not HBM-bound"},
                 "share_of_step": {"dp": dp_ms / (dev_s * 1e3) if dev_s else None,
-                                  "traceback_kabsch": stats["tb_kernel_ms"] / (dev_s * 1e3) if dev_s else None}}
+                                  "traceback_kabsch": stats["tb_kernel_ms"] / (dev_s * 1e3) if dev_s else None,
+                                  "nw_filter": stats["nw_kernel_ms"] / (dev_s * 1e3) if dev_s else None}}
 
+    cfgd = common_config(w, args, count)
+    cfgd.update({"orientations_per_gpu_per_step": mine, "dp_cells_per_orientation": int(cells_per),
+                 "alignment_sizes": int(s.n_max - max(2, s.n_min) + 1),
+                 "l2": "no explicit flush: each step writes and re-reads >= %.1f GB of traceback tables per GPU (>> 126 MB L2)" % (
+                     0.25 * cells_per * stats["orientations_dp"] / max(args.steps, 1) / 1e9),
+                 "parallelism": ("one list partitioned over %d ranks (contiguous ranges, global ids)" % world if strong else
+                                 "%d rank(s), each its own copy of the list under its own ids" % world) +
+                                "; per step: NCCL all_reduce(MIN) of the 64-bit per-size keys in device memory, payload from "
+                                "the owning ranks, one all_gather"})
     line = {"metric": "orientations_per_sec", "value": value, "unit": "orientations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "fixture (CA traces of the reference's test pair, tests/golden/*.pdb)",
-            "config": {"workload": WORKLOAD, "orientations_per_gpu_per_step": count,
-                       "dp_cells_per_orientation": int(cells_per), "alignment_sizes": NMAX - 1,
-                       "l2": "no explicit flush: each step writes and re-reads >= %.1f GB of traceback tables per GPU (>> 126 MB L2)" % (0.25 * cells_per * count / 1e9),
-                       "parallelism": "orientations partitioned, %d rank(s), NCCL min-reduction of per-size keys (reduction_ms is charged to every step of `value`)" % world},
-            "dp_gcups": value * cells_per / 1e9,
-            "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": w["data"], "config": cfgd,
+            "dp_gcups": value * cells_per * (stats["orientations_dp"] / max(stats["orientations"], 1)) / 1e9,
+            "timed_region_s": wall_s,
+            "search_ms_per_step": 1e3 * dev_s / args.steps,
             "reduction_ms": red_ms,
             "gpu_launches": int(stats["kernel_launches"]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "orientations/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
+                    "d2h_bytes_per_step": int(d2h), "steps": e_steps},
             "roofline": roofline,
-            "result_check": {"sizes_with_solution": int((table["ssd"] < 1e26).sum()),
-                             "rmsd_100": float(np.sqrt(table["ssd"][100 - NMIN] / 100.0))}}
+            "result_check": {"sizes_with_solution": int((table["ssd"] < 1e26).sum())}}
+    if s.n_min <= 100 <= s.n_max and table["ssd"][100 - s.n_min] < 1e26:
+        line["result_check"]["rmsd_100"] = float(np.sqrt(table["ssd"][100 - s.n_min] / 100.0))
+    if strong_check is not None:
+        line["result_check"]["merged_table_equals_one_gpu_search"] = strong_check
+    if full_run:
+        line["full_run"] = full_run
+    if nw_filter:
+        line["nw_filter"] = nw_filter
 
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        res = ref_bench(cores, 160, 2)
-        if res:
-            n, tt = res[-1]
-            line["cpu_baseline"] = {"value": n / tt, "unit": "orientations/s", "cores": cores, "kind": "reference",
-                                    "sample": "%d of the 20424 orientations (160 per process x %d processes), unmodified reference Search(og,start,stop), shipped flags" % (n, cores)}
+        if w["cfg"] in (1, 2):
+            res = ref_bench(w, cores, ref_sample_size(w), 2)
+            if res:
+                n, tt, tot = res[-1]
+                line["cpu_baseline"] = {"value": n / tt, "unit": "orientations/s", "cores": cores, "kind": "reference",
+                                        "sample": "%d of the %d orientations (%d per process x %d processes), unmodified "
+                                                  "reference Search(og,start,stop), shipped flags" % (n, tot, n // cores, cores)}
+            else:
+                line["cpu_baseline"] = None
         else:
-            line["cpu_baseline"] = None
+            # one orientation costs minutes of a core: no bounded sample; the reference's measured cell rate instead
+            per_core = CPU_CELLS_PER_S_PER_CORE / cells_per
+            line["cpu_baseline"] = {"value": per_core * cores, "unit": "orientations/s", "cores": cores, "kind": "reference",
+                                    "sample": "EXTRAPOLATED, not run: %.2e cells per orientation / 0.22 GCUPS per core (Solve_IncrN of "
+                                              "the reference measured on config 2, SURVEY.md 6) x %d cores; DP only, the NW filter "
+                                              "not counted" % (cells_per, cores)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_nw_filter(local, clocks):
+    """NW orientation filter (DynNW, lib/dyn/dynNW.cc:243-475) of config 1 on the test pair:
+    18 532 orientations x 19 129 banded cells, timed alone over repeated launches"""
+    from minrms_b200 import OrientationGenerator, SearchOrCuda
+    import torch
+    w = workload(1)
+    s = SearchOrCuda(w["A"], w["B"], w["settings"], device=local)
+    og = OrientationGenerator(s)
+    s.upload_orientations(og.orientations)
+    for _ in range(3):
+        s.reset_best(); s.search_resident(0, og.size(), 0)
+    s.stats(reset=True)
+    reps = 20
+    for _ in range(reps):
+        s.reset_best(); s.search_resident(0, og.size(), 0)
+    stt = s.stats()
+    s.close()
+    pk, _ = peaks()
+    f_mhz = (clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    gcups = stt["nw_cells"] / (stt["nw_kernel_ms"] * 1e-3) / 1e9 if stt["nw_kernel_ms"] > 0 else 0.0
+    peak = sms * 128 * f_mhz * 1e6 / 5 / 1e9
+    return {"workload": w["name"], "orientations": og.size(), "survivors": int(stt["orientations_dp"] // reps),
+            "cells_per_orientation": int(stt["nw_cells"] // max(stt["orientations"], 1)),
+            "avg_launch_ms": stt["nw_kernel_ms"] / reps,
+            "roofline": {"bound": "alu_issue", "achieved": gcups, "peak": peak, "unit": "GCUPS", "frac": gcups / peak,
+                         "peak_def": "%d SM x 128 lanes x f_SM / 5 ops per NW cell: 3 FADD (two gap steps + the match cost) and "
+                                     "2 FMIN; the distance build (8 FP32 ops per cell, no FMA contraction), the strict-< tie "
+                                     "order and the carried match count come on top" % sms}}
 
 
 if __name__ == "__main__":

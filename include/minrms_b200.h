@@ -98,6 +98,23 @@ int mr_fetch_best(mr_ctx *ctx, mr_best *best);
  * rank whose key equals the reduced key owns the payload for that size. */
 int mr_fetch_keys(mr_ctx *ctx, uint64_t *keys /* [R] */);
 
+/* The same reduction without staging through the host (the reference's rule is
+ * bin/minrms/search_or_dyn3d.cc:1825-1835).  Orientations are partitioned over ranks, one
+ * context per GPU:
+ *   1. mr_device_keys: device address of the R keys of this context (it also snapshots them);
+ *      the caller reduces the buffer IN PLACE over the ranks with an element-wise MIN on
+ *      64-bit integers (ncclAllReduce(ncclMin, ncclUint64) / torch.distributed.all_reduce on a
+ *      tensor that aliases the buffer) and waits for it;
+ *   2. mr_fetch_rows_device: the sizes whose reduced key equals the snapshot were won by an
+ *      orientation of THIS context: only those are re-evaluated for their payload, written
+ *      as rows of *ints_per_row = 2 + 12 + N int32 in device memory, row r (size n_min + r) =
+ *      {key lo, key hi, transform (12 float bit patterns), N pairs as i | j << 16}; the rows
+ *      of sizes won elsewhere carry the key of "no solution" (0x6aa56fa6ffffffff).
+ *   3. one all-gather of the R rows and, per size, the row whose key is the minimum, give
+ *      the merged table on every rank. */
+int mr_device_keys(mr_ctx *ctx, uint64_t **d_keys, int32_t *count);
+int mr_fetch_rows_device(mr_ctx *ctx, int32_t **d_rows, int32_t *ints_per_row);
+
 /* One orientation, the body of the FirstPass / Refine n-loop, with every per-size
  * result returned (used by Refine and by the parity tests).  Arrays are indexed n-1:
  *   cost[N], valid[N] (1 = the reference would have compared this size), ssd[N],

@@ -31,7 +31,7 @@ class MrStats(C.Structure):
 
 EXPORTS = ["mr_create", "mr_destroy", "mr_last_error", "mr_best_init", "mr_search",
            "mr_upload_orientations", "mr_search_resident", "mr_reset_best", "mr_fetch_best",
-           "mr_fetch_keys", "mr_eval_one", "mr_refine", "mr_gen_orientations",
+           "mr_fetch_keys", "mr_device_keys", "mr_fetch_rows_device", "mr_eval_one", "mr_refine", "mr_gen_orientations",
            "mr_superimpose_batch", "mr_plot_stats", "mr_get_stats", "mr_reset_stats", "mr_set_option",
            "mr_dp_cells_per_orientation", "mr_event_record", "mr_event_elapsed_ms"]
 
@@ -61,6 +61,8 @@ def load():
     L.mr_reset_best.argtypes = [vp]
     L.mr_fetch_best.argtypes = [vp, C.POINTER(MrBest)]
     L.mr_fetch_keys.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mr_device_keys.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    L.mr_fetch_rows_device.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.mr_eval_one.argtypes = [vp, fp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), fp,
                               C.POINTER(C.c_uint8), fp, fp, C.POINTER(C.c_int16)]
     L.mr_refine.argtypes = [vp, C.POINTER(MrBest), C.c_int32, C.POINTER(C.c_int32)]

@@ -65,6 +65,10 @@ struct mr_ctx {
   int use_gcol = 0;
   size_t dp_smem = 0;
   unsigned long long* d_keys = nullptr;
+  // multi-GPU reduction on the device (mr_keys_snapshot / mr_fetch_rows_device)
+  unsigned long long* d_keys_local = nullptr;  // this context's keys before the cross-rank MIN
+  int32_t* d_rows = nullptr;                   // [R][2 + 12 + N] int32: key, transform, pairs of the sizes this context owns
+  int* d_item_row = nullptr;                   // [R] table row of each emitted item
   // winner / eval payload
   float* d_orient_w = nullptr;  // [max(R,1)] transforms
   int* d_widx = nullptr;
@@ -542,21 +546,61 @@ void best_init_host(const mr_ctx* c, mr_best* b) {  // search_or_dyn3d.cc:165-18
   }
 }
 
+// rows of the device-side payload table: {key lo, key hi, 12 transform floats, N x (i | j << 16)}
+static inline int row_ints(const mr_ctx* c) { return 2 + 12 + c->N; }
+
+__global__ void k_rows_init(int32_t* __restrict__ rows, int R, int C) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R * C) return;
+  const int k = t % C;
+  rows[t] = k == 0 ? (int32_t)0xffffffffu : k == 1 ? (int32_t)0x6aa56fa6 : 0;  // KEY_NONE, then zeros
+}
+// one block per emitted item: row[item_row[k]] = {key, T_out[k], pairs_out[k]}
+__global__ void k_rows_pack(const int* __restrict__ item_row, const unsigned long long* __restrict__ keys,
+                            const float* __restrict__ T_out, const short* __restrict__ pairs_out, int N, int C,
+                            int32_t* __restrict__ rows) {
+  const int k = blockIdx.x, r = item_row[k];
+  int32_t* row = rows + (size_t)r * C;
+  const int32_t* pr = reinterpret_cast<const int32_t*>(pairs_out + (size_t)k * 2 * N);
+  for (int q = threadIdx.x; q < C; q += blockDim.x) {
+    int32_t v;
+    if (q == 0) v = (int32_t)(keys[r] & 0xffffffffull);
+    else if (q == 1) v = (int32_t)(keys[r] >> 32);
+    else if (q < 14) v = __float_as_int(T_out[12 * (size_t)k + (q - 2)]);
+    else v = pr[q - 14];
+    row[q] = v;
+  }
+}
+
 // Turn the device key table into a full best table: re-run the DP for the (few) winning
 // orientations and emit transform + alignment for exactly the winning (orientation,size)
 // pairs.  d_orient / id_offset locate a winner's transform: index = o_id - id_offset.
+//   out != NULL: the host table is filled (mr_fetch_best, mr_search).
+//   out == NULL: multi-GPU reduction: d_keys holds the cross-rank minima, d_keys_local this
+//     context's own keys; only the sizes this context owns (equal keys) are emitted, as rows
+//     of c->d_rows in device memory (nothing but the two key vectors is copied to the host).
 int fetch_payload(mr_ctx* c, const float* d_orient, long long id_offset, mr_best* out) {
-  std::vector<unsigned long long> keys((size_t)c->R);
+  const bool to_rows = out == nullptr;
+  std::vector<unsigned long long> keys((size_t)c->R), local;
   CU(c, cudaMemcpyAsync(keys.data(), c->d_keys, 8 * (size_t)c->R, cudaMemcpyDeviceToHost, c->stream));
+  if (to_rows) {
+    local.resize((size_t)c->R);
+    CU(c, cudaMemcpyAsync(local.data(), c->d_keys_local, 8 * (size_t)c->R, cudaMemcpyDeviceToHost, c->stream));
+    const int C = row_ints(c), total = c->R * C;
+    k_rows_init<<<(total + 255) / 256, 256, 0, c->stream>>>(c->d_rows, c->R, C);
+    CU(c, cudaGetLastError());
+    c->st.kernel_launches++;
+  }
   CU(c, cudaStreamSynchronize(c->stream));
-  c->st.d2h_bytes += 8 * (int64_t)c->R;
-  best_init_host(c, out);
+  c->st.d2h_bytes += 8 * (int64_t)c->R * (to_rows ? 2 : 1);
+  if (out) best_init_host(c, out);
   std::map<long long, int> widx;  // o_id -> winner slot
   std::vector<int> idx;
   std::vector<int2> items;
   std::vector<int> item_r;
   for (int r = 0; r < c->R; r++) {
     if (keys[r] == KEY_NONE) continue;
+    if (to_rows && local[r] != keys[r]) continue;  // another rank's orientation won this size
     const long long oid = (long long)(keys[r] & 0xffffffffull);
     auto it = widx.find(oid);
     int w;
@@ -586,12 +630,20 @@ int fetch_payload(mr_ctx* c, const float* d_orient, long long id_offset, mr_best
     const int ni = (int)sub.size();
     CU(c, cudaMemcpyAsync(c->d_widx, idx.data() + g0, 4 * (size_t)nw, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_items, sub.data(), sizeof(int2) * (size_t)ni, cudaMemcpyHostToDevice, c->stream));
+    if (to_rows) CU(c, cudaMemcpyAsync(c->d_item_row, sub_r.data(), 4 * (size_t)ni, cudaMemcpyHostToDevice, c->stream));
     k_gather_orient<<<(nw * 12 + 127) / 128, 128, 0, c->stream>>>(d_orient, c->d_widx, nw, c->d_orient_w);
     CU(c, cudaGetLastError());
     c->st.kernel_launches++;
     if (launch_filter(c, c->d_orient_w, nw, false)) return 1;
     if (launch_dp(c, c->d_orient_w, nw)) return 1;
     if (launch_tb<true>(c, c->d_orient_w, nw, c->d_items, ni)) return 1;
+    if (to_rows) {
+      k_rows_pack<<<ni, 128, 0, c->stream>>>(c->d_item_row, c->d_keys, c->d_Tout, c->d_pairs_out, c->N, row_ints(c), c->d_rows);
+      CU(c, cudaGetLastError());
+      c->st.kernel_launches++;
+      CU(c, cudaStreamSynchronize(c->stream));  // the host vectors above go out of scope
+      continue;
+    }
     std::vector<float> T((size_t)ni * 12);
     std::vector<short> pairs((size_t)ni * 2 * c->N);
     CU(c, cudaMemcpyAsync(T.data(), c->d_Tout, 4 * T.size(), cudaMemcpyDeviceToHost, c->stream));
@@ -734,6 +786,7 @@ void mr_destroy(mr_ctx* c) {
   cudaFree(c->dA); cudaFree(c->dB); cudaFree(c->d_orient); cudaFree(c->d_surv_count);
   cudaFree(c->d_surv_all); cudaFree(c->d_nw_all);
   cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w);
+  cudaFree(c->d_keys_local); cudaFree(c->d_rows); cudaFree(c->d_item_row);
   cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
   cudaFree(c->d_ref_pairs_in); cudaFree(c->d_ref_n); cudaFree(c->d_ref_orient); cudaFree(c->d_ref_T);
   if (c->h_ref) cudaFreeHost(c->h_ref);
@@ -824,6 +877,36 @@ int mr_fetch_best(mr_ctx* c, mr_best* best) {
   CU(c, cudaSetDevice(c->device));
   if (fetch_payload(c, c->d_orient, c->id_offset, best)) return 1;
   harvest(c);
+  return 0;
+}
+
+int mr_device_keys(mr_ctx* c, uint64_t** d_keys, int32_t* count) {
+  if (!c || !d_keys) return 1;
+  CU(c, cudaSetDevice(c->device));
+  const size_t RR = (size_t)std::max(c->R, 1);
+  if (!c->d_keys_local) {
+    CU(c, cudaMalloc(&c->d_keys_local, 8 * RR));
+    CU(c, cudaMalloc(&c->d_rows, 4 * RR * (size_t)row_ints(c)));
+    CU(c, cudaMalloc(&c->d_item_row, 4 * RR));
+  }
+  // snapshot of this context's own keys: after the caller's MIN all-reduce over d_keys, a size
+  // whose reduced key still equals the snapshot is owned here
+  CU(c, cudaMemcpyAsync(c->d_keys_local, c->d_keys, 8 * (size_t)c->R, cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *d_keys = reinterpret_cast<uint64_t*>(c->d_keys);
+  if (count) *count = c->R;
+  return 0;
+}
+
+int mr_fetch_rows_device(mr_ctx* c, int32_t** d_rows, int32_t* ints_per_row) {
+  if (!c || !d_rows) return 1;
+  CU(c, cudaSetDevice(c->device));
+  if (!c->d_keys_local) MR_FAIL(c, "mr_fetch_rows_device: call mr_device_keys first");
+  if (fetch_payload(c, c->d_orient, c->id_offset, nullptr)) return 1;
+  CU(c, cudaStreamSynchronize(c->stream));
+  harvest(c);
+  *d_rows = c->d_rows;
+  if (ints_per_row) *ints_per_row = row_ints(c);
   return 0;
 }
 

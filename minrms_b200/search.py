@@ -141,14 +141,15 @@ class SearchOrCuda:
         self._check(self.lib.mr_set_option(self.ctx, name.encode(), int(value)))
 
     # -- SearchOr interface -----------------------------------------------------
-    def Search(self, og, start=0, stop=None):
+    def Search(self, og, start=0, stop=None, first_id=None):
         """SearchOr::Search(og, start, stop) (search_or.h:87-104): FirstPass over
-        og[start:stop]; ids are the positions in og, so disjoint ranges merge exactly."""
+        og[start:stop]; ids are the positions in og, so disjoint ranges merge exactly
+        (first_id: id of og[start] when several lists share one id space)."""
         orient = og.orientations if hasattr(og, "orientations") else np.asarray(og, np.float32)
         orient = np.ascontiguousarray(orient, np.float32).reshape(-1, 12)
         stop = orient.shape[0] if stop is None else stop
         part = np.ascontiguousarray(orient[start:stop])
-        self._check(self.lib.mr_search(self.ctx, _fp(part), part.shape[0], start,
+        self._check(self.lib.mr_search(self.ctx, _fp(part), part.shape[0], start if first_id is None else first_id,
                                        C.byref(self._best)))
 
     def check_solutions(self):
@@ -184,6 +185,26 @@ class SearchOrCuda:
         keys = np.zeros(max(self.R, 1), np.uint64)
         self._check(self.lib.mr_fetch_keys(self.ctx, keys.ctypes.data_as(C.POINTER(C.c_uint64))))
         return keys[:self.R]
+
+    def device_keys(self):
+        """(device address, R) of the per-size keys; also snapshots them (mr_device_keys)"""
+        ptr, n = C.c_void_p(), C.c_int32(0)
+        self._check(self.lib.mr_device_keys(self.ctx, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def fetch_rows_device(self):
+        """(device address, int32 per row) of the payload rows of the sizes this context owns
+        after the cross-rank MIN over device_keys() (mr_fetch_rows_device)"""
+        ptr, n = C.c_void_p(), C.c_int32(0)
+        self._check(self.lib.mr_fetch_rows_device(self.ctx, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def load_table(self, table):
+        """make `table` (dict ssd, T, pairs, o_id) the stored best table"""
+        self.aSumSqdDists[:self.R] = table["ssd"]
+        self.aTransforms[:self.R] = table["T"]
+        self.aAlignments[:self.R] = table["pairs"]
+        self.aOrientationIds[:self.R] = table["o_id"]
 
     # -- single orientation (Refine building block, parity tests) ---------------
     def eval_one(self, T12, apply_filter=True):

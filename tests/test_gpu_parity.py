@@ -475,3 +475,46 @@ def test_ir_costs_only_first_pass_equals_full_kernel(kernel, golden_ir_off):
     assert_table_equal(a["ssd"], a["T"], a["pairs"], b["ssd"], b["T"], b["pairs"], int(g["n_min"]), "costs-only vs full")
     assert_table_equal(a["ssd"], a["T"], a["pairs"], g["strict_search_ssd"], g["strict_search_T"],
                        g["strict_search_pairs"], int(g["n_min"]), "costs-only vs reference")
+
+
+def test_device_side_reduction_of_two_contexts(golden_c1):
+    """the multi-GPU reduction without staging through the host (mr_device_keys /
+    mr_fetch_rows_device, minrms_b200/dist.py), two "ranks" as two contexts on one GPU: each
+    searches its half of ONE list, the keys are reduced with an element-wise MIN in device
+    memory (what the NCCL all_reduce does), every context emits only the rows it owns, and
+    the per-size row with the minimum key gives the table of a single search"""
+    import torch
+    from minrms_b200 import OrientationGenerator
+    from minrms_b200.dist import KEY_NONE, _DeviceArray, partition, table_from_rows
+    g = golden_c1
+    dev = torch.device("cuda", 0)
+    ctxs = [make_search(g["A"], g["B"], settings_from_golden(g)) for _ in range(2)]
+    og = OrientationGenerator(ctxs[0])
+    keys = []
+    for r, s in enumerate(ctxs):
+        a, b = partition(og.size(), r, 2)
+        s.upload_orientations(og.orientations)
+        s.search_resident(a, b - a, a)
+        ptr, R = s.device_keys()
+        keys.append(torch.as_tensor(_DeviceArray(ptr, (R,), "<i8"), device=dev))
+    red = torch.minimum(keys[0], keys[1])
+    owned = []
+    for k in keys:
+        owned.append(int(((k == red) & (red != KEY_NONE)).sum()))
+        k.copy_(red)
+    torch.cuda.synchronize()
+    rows = []
+    for s in ctxs:
+        ptr, C = s.fetch_rows_device()
+        rows.append(torch.as_tensor(_DeviceArray(ptr, (s.R, C), "<i4"), device=dev).clone())
+    allrows = torch.stack(rows)
+    allkeys = allrows[:, :, :2].contiguous().view(torch.int64).squeeze(-1)
+    for r in range(2):   # a context emits exactly the sizes it won
+        assert int((allkeys[r] != KEY_NONE).sum()) == owned[r]
+    sel = allrows[allkeys.argmin(dim=0), torch.arange(ctxs[0].R, device=dev)]
+    merged = table_from_rows(sel.cpu().numpy(), ctxs[0].n_min)
+    assert_table_equal(merged["ssd"], merged["T"], merged["pairs"], g["strict_search_ssd"], g["strict_search_T"],
+                       g["strict_search_pairs"], int(g["n_min"]), "device-side reduction")
+    assert sum(owned) == int((g["strict_search_ssd"] < 1e26).sum())
+    for s in ctxs:
+        s.close()
