@@ -295,7 +295,7 @@ def main():
     import torch
     import torch.distributed as dist
     from minrms_b200 import OrientationGenerator, SearchOrCuda
-    from minrms_b200.dist import partition, reduce_best_device
+    from minrms_b200.dist import gather_payload_device, partition, reduce_best_device, reduce_keys_device
     from minrms_b200.search import dp_cells_per_orientation
 
     rank = int(os.environ.get("RANK", "0"))
@@ -341,15 +341,19 @@ def main():
     # ---------------- device-resident arm: `value` -----------------------------------
     s.upload_orientations(host_orient)
 
+    # a step with the list resident: FirstPass + (N > 1) the cross-GPU MIN of the per-size keys in
+    # device memory.  Like at N = 1, the winners' payload (transform + alignment) is fetched when
+    # the table is wanted: once after the loop here, inside every step of the `e2e` arm.
     def step_resident():
         s.reset_best()
         s.search_resident(first, mine, id0)
         if world > 1:
-            return reduce_best_device(s, dev)
-        return None
+            reduce_keys_device(s, dev)
 
     for _ in range(args.warmup):
         step_resident()
+    if world > 1:
+        gather_payload_device(s, dev)      # first use: row buffers, all_gather channels
     s.stats(reset=True)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -365,7 +369,7 @@ def main():
         s.event_record(1)
         search_ms += s.event_elapsed_ms(0, 1)        # CUDA events on the library's stream
         if world > 1:
-            table = reduce_best_device(s, dev)
+            reduce_keys_device(s, dev)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
@@ -374,12 +378,20 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s, wall_s = float(t[0]), float(t[1])
+    payload_ms = 0.0
     if world == 1:
         s.fetch_best()
         table = s.best_table()
         step_s = dev_s / args.steps                 # device time (events), one GPU: nothing else in a step
     else:
-        step_s = wall_s / args.steps                # barrier to barrier, max over ranks: search + reduction
+        step_s = wall_s / args.steps                # barrier to barrier, max over ranks: search + key reduction
+        barrier()
+        p0 = time.perf_counter()
+        table = gather_payload_device(s, dev)       # winners' payload from the owning ranks + all_gather + D2H
+        barrier()
+        tp = torch.tensor([time.perf_counter() - p0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        payload_ms = 1e3 * float(tp[0])
     red_ms = max(0.0, 1e3 * (wall_s - dev_s) / args.steps) if world > 1 else 0.0
     value = job / step_s
 
@@ -489,8 +501,9 @@ def main():
                      0.25 * cells_per * stats["orientations_dp"] / max(args.steps, 1) / 1e9),
                  "parallelism": ("one list partitioned over %d ranks (contiguous ranges, global ids)" % world if strong else
                                  "%d rank(s), each its own copy of the list under its own ids" % world) +
-                                "; per step: NCCL all_reduce(MIN) of the 64-bit per-size keys in device memory, payload from "
-                                "the owning ranks, one all_gather"})
+                                "; per step: NCCL all_reduce(MIN) of the 64-bit per-size keys in device memory (reduction_ms); "
+                                "the winners' payload from the owning ranks + one all_gather once per search "
+                                "(payload_ms_once_per_search; inside every step of e2e)"})
     line = {"metric": "orientations_per_sec", "value": value, "unit": "orientations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
             "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
@@ -499,6 +512,7 @@ def main():
             "timed_region_s": wall_s,
             "search_ms_per_step": 1e3 * dev_s / args.steps,
             "reduction_ms": red_ms,
+            "payload_ms_once_per_search": payload_ms,
             "gpu_launches": int(stats["kernel_launches"]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "orientations/s", "h2d_bytes_per_step": int(h2d),

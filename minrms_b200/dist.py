@@ -116,16 +116,30 @@ class _DeviceArray:
                                          "version": 2}
 
 
-def reduce_best_device(search, device, group=None):
-    """Cross-rank reduction of the device-side table of `search` (a SearchOrCuda after
-    search_resident / Search over this rank's share of the orientations).  Returns the merged
-    host table, identical on every rank, and leaves it in `search` (ready for Refine())."""
+def reduce_keys_device(search, device, group=None):
+    """The cross-rank selection itself: one all_reduce(MIN) over the R 64-bit keys, in place in
+    the device buffer of `search` (its own keys are snapshotted first, so that
+    gather_payload_device knows which sizes it won)."""
     kptr, R = search.device_keys()                    # snapshot of my keys + address of the live ones
     keys = torch.as_tensor(_DeviceArray(kptr, (R,), "<i8"), device=device)   # keys < 2^63: signed order = unsigned order
     dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
     torch.cuda.current_stream(device).synchronize()   # the library works on its own stream
-    rptr, C = search.fetch_rows_device()              # payload of the sizes won by my orientations
-    rows = torch.as_tensor(_DeviceArray(rptr, (R, C), "<i4"), device=device)
+
+
+def gather_payload_device(search, device, group=None):
+    """After reduce_keys_device: every rank re-evaluates only the sizes its own orientations won
+    (transform + alignment, as rows in device memory), one all_gather moves the rows and the
+    merged table is copied to the host once.  Returns it (identical on every rank) and leaves
+    it in `search`, ready for Refine()."""
+    rptr, C = search.fetch_rows_device()
+    rows = torch.as_tensor(_DeviceArray(rptr, (search.R, C), "<i4"), device=device)
     merged = table_from_rows(_gather_select(rows, group).cpu().numpy(), search.n_min)
     search.load_table(merged)
     return merged
+
+
+def reduce_best_device(search, device, group=None):
+    """Cross-rank reduction of the device-side table of `search` (a SearchOrCuda after
+    search_resident / Search over this rank's share of the orientations): keys, then payload."""
+    reduce_keys_device(search, device, group)
+    return gather_payload_device(search, device, group)

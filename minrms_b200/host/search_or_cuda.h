@@ -11,11 +11,25 @@
 #ifndef MINRMS_SEARCH_OR_CUDA_H
 #define MINRMS_SEARCH_OR_CUDA_H
 
+// Everything search_or_dyn3d.h includes is included first, under the keywords' own meaning
+// (their include guards then skip them), so that the redefinition reaches the declaration
+// of SearchOrDyn3d and nothing else -- no standard or library header is parsed with it.
+#include <fstream>
+#include <set>
+#include <string>
+#include <vector>
+#include <sys/time.h>
+#include <biopolymer.h>
+#include <pair_alignment.h>
+#include <superimpose.h>
+#include <dyn3d.h>
+#include "search_or.h"
+#include "or_gen.h"
+
 #define private protected
 #include "search_or_dyn3d.h"
 #undef private
 
-#include <vector>
 #include "minrms_b200.h"
 
 namespace minrms {
