@@ -69,6 +69,10 @@ struct mr_ctx {
   unsigned long long* d_keys_local = nullptr;  // this context's keys before the cross-rank MIN
   int32_t* d_rows = nullptr;                   // [R][2 + 12 + N] int32: key, transform, pairs of the sizes this context owns
   int* d_item_row = nullptr;                   // [R] table row of each emitted item
+  // grow-only device scratch of the small entry points (mr_superimpose_batch, mr_plot_stats,
+  // mr_gen_orientations): they synchronise before they return, so one buffer serves them all
+  char* d_misc = nullptr;
+  size_t misc_bytes = 0;
   // winner / eval payload
   float* d_orient_w = nullptr;  // [max(R,1)] transforms
   int* d_widx = nullptr;
@@ -85,6 +89,7 @@ struct mr_ctx {
   char* h_ref = nullptr;             // pinned staging
   size_t ref_off_n = 0, ref_off_ssd = 0, ref_off_valid = 0, ref_off_nlast = 0, ref_off_T = 0, ref_off_pairs = 0;
   int64_t opt_refine_batch = 0;      // 0: all flagged sizes per batch; k > 0: at most k (1 = sequential)
+  int64_t opt_refine_seq_superpose = 0;  // tests: the set-up superposition of a Refine batch by the sequential kernel
   int64_t opt_refine_split = 1;      // Refine batches of the multi-pass DP: passes of an orientation on a cluster of CTAs
   int ref_host_item = -1;            // batch item whose transforms / alignments sit in the pinned buffer
   int* h_pinned = nullptr;      // surv counts per chunk
@@ -152,6 +157,24 @@ int64_t nw_cells(int m, int nB, int of_min) {
     c += jhi - jlo + 1;
   }
   return c;
+}
+
+// at least `bytes` of device scratch, 256-byte aligned, owned by the context (freed in mr_destroy)
+int misc_reserve(mr_ctx* c, size_t bytes, char** out) {
+  if (bytes > c->misc_bytes) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (c->d_misc) cudaFree(c->d_misc);
+    c->d_misc = nullptr;
+    c->misc_bytes = 0;
+    const size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    if (cudaMalloc(&c->d_misc, want) != cudaSuccess) {
+      cudaGetLastError();
+      MR_FAIL(c, "out of device memory: %zu bytes of scratch", want);
+    }
+    c->misc_bytes = want;
+  }
+  *out = c->d_misc;
+  return 0;
 }
 
 EventPair* next_events(mr_ctx* c, int kind) {
@@ -417,7 +440,8 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
       // warp per orientation, wavefront in registers
       const int grid = (count + 3) / 4;
       const size_t sm = 4 * 3 * (size_t)c->m;
-#define MR_NW(CPL) k_nw_filter_warp<CPL><<<grid, 128, sm, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, nwm, surv, c->d_surv_count)
+#define MR_NW(CPL) if (mr_ensure_smem(k_nw_filter_warp<CPL>, sm)) MR_FAIL(c, "NW filter: shared memory attribute failed"); \
+      k_nw_filter_warp<CPL><<<grid, 128, sm, c->stream>>>(c->P, c->dA, c->dB, d_orient_chunk, count, nwm, surv, c->d_surv_count)
       switch (cpl) {
         case 1: MR_NW(1); break; case 2: MR_NW(2); break; case 3: MR_NW(3); break; case 4: MR_NW(4); break;
         case 5: MR_NW(5); break; case 6: MR_NW(6); break; case 7: MR_NW(7); break; default: MR_NW(8); break;
@@ -786,7 +810,7 @@ void mr_destroy(mr_ctx* c) {
   cudaFree(c->dA); cudaFree(c->dB); cudaFree(c->d_orient); cudaFree(c->d_surv_count);
   cudaFree(c->d_surv_all); cudaFree(c->d_nw_all);
   cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w);
-  cudaFree(c->d_keys_local); cudaFree(c->d_rows); cudaFree(c->d_item_row);
+  cudaFree(c->d_keys_local); cudaFree(c->d_rows); cudaFree(c->d_item_row); cudaFree(c->d_misc);
   cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
   cudaFree(c->d_ref_pairs_in); cudaFree(c->d_ref_n); cudaFree(c->d_ref_orient); cudaFree(c->d_ref_T);
   if (c->h_ref) cudaFreeHost(c->h_ref);
@@ -813,6 +837,7 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);
   else if (!strcmp(name, "refine_batch")) c->opt_refine_batch = std::max<int64_t>(0, value);
   else if (!strcmp(name, "refine_split")) c->opt_refine_split = value != 0;
+  else if (!strcmp(name, "refine_seq_superpose")) c->opt_refine_seq_superpose = value != 0;
   else if (!strcmp(name, "mp_threads")) {
     if (value != 0 && (value < 32 || value > 1024 || value % 32)) MR_FAIL(c, "mr_set_option: mp_threads must be a multiple of 32 in [32, 1024]");
     c->opt_mp_threads = value;
@@ -1098,13 +1123,18 @@ static int refine_launch(mr_ctx* c, const std::vector<int>& rs, const mr_best* b
   // orientation that optimally superimposes each alignment (:2401-2407)
   {
     const size_t team = 4 * 15 * (size_t)N * c->hp.nb;
-    if (team <= (size_t)c->prop.sharedMemPerBlockOptin) {
+    if (team <= (size_t)c->prop.sharedMemPerBlockOptin && !c->opt_refine_seq_superpose) {
       if (mr_ensure_smem(k_superimpose_pairs_batch, team)) MR_FAIL(c, "superposition kernel: shared memory attribute failed");
       k_superimpose_pairs_batch<<<k, 128, team, c->stream>>>(c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N,
                                                             c->d_ref_orient);
     } else {
-      k_superimpose_pairs_batch_seq<<<k, 128, 4 * 3 * (size_t)(c->m + c->nB) * c->hp.nb + 4 * (size_t)N, c->stream>>>(
-          c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N, c->d_ref_orient);
+      // chains too long for the team kernel's 60 bytes per point (N * nb > ~3 800)
+      const size_t seq = 4 * 3 * (size_t)(c->m + c->nB) * c->hp.nb + 4 * (size_t)N;
+      if (seq > (size_t)c->prop.sharedMemPerBlockOptin)
+        MR_FAIL(c, "Refine: the coordinates of both molecules (%zu bytes) do not fit shared memory", seq);
+      if (mr_ensure_smem(k_superimpose_pairs_batch_seq, seq)) MR_FAIL(c, "superposition kernel: shared memory attribute failed");
+      k_superimpose_pairs_batch_seq<<<k, 128, seq, c->stream>>>(c->P, c->dA, c->dB, c->d_ref_pairs_in, c->d_ref_n, N,
+                                                              c->d_ref_orient);
     }
   }
   CU(c, cudaGetLastError());
@@ -1231,19 +1261,19 @@ int mr_superimpose_batch(mr_ctx* c, int32_t batch, int32_t np, const float* fixe
   if (!c) return 1;
   CU(c, cudaSetDevice(c->device));
   if (batch <= 0 || np <= 0) return 0;
-  float *df = nullptr, *dm = nullptr, *dT = nullptr, *dr = nullptr;
-  const size_t pts = (size_t)batch * np * 3 * 4;
-  CU(c, cudaMalloc(&df, pts)); CU(c, cudaMalloc(&dm, pts));
-  CU(c, cudaMalloc(&dT, (size_t)batch * 48)); CU(c, cudaMalloc(&dr, (size_t)batch * 4));
-  CU(c, cudaMemcpyAsync(df, fixed, pts, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemcpyAsync(dm, moveable, pts, cudaMemcpyHostToDevice, c->stream));
+  const size_t pts = ((size_t)batch * np * 3 * 4 + 255) & ~(size_t)255, bT = ((size_t)batch * 48 + 255) & ~(size_t)255;
+  char* base = nullptr;
+  if (misc_reserve(c, 2 * pts + bT + (size_t)batch * 4, &base)) return 1;
+  float *df = reinterpret_cast<float*>(base), *dm = reinterpret_cast<float*>(base + pts),
+        *dT = reinterpret_cast<float*>(base + 2 * pts), *dr = reinterpret_cast<float*>(base + 2 * pts + bT);
+  CU(c, cudaMemcpyAsync(df, fixed, (size_t)batch * np * 12, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(dm, moveable, (size_t)batch * np * 12, cudaMemcpyHostToDevice, c->stream));
   k_superimpose_batch<<<(batch + 63) / 64, 64, 0, c->stream>>>(batch, np, df, dm, dT, dr);
   CU(c, cudaGetLastError());
   c->st.kernel_launches++;
   CU(c, cudaMemcpyAsync(T, dT, (size_t)batch * 48, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(rmsd, dr, (size_t)batch * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  cudaFree(df); cudaFree(dm); cudaFree(dT); cudaFree(dr);
   return 0;
 }
 
@@ -1299,7 +1329,8 @@ int mr_plot_stats(mr_ctx* c, const mr_best* best, int32_t ca_index, double* rows
   char* d = nullptr;
   const size_t off_T = (b_ssd + 15) & ~(size_t)15, off_pairs = off_T + b_T, off_far = (off_pairs + b_pairs + 15) & ~(size_t)15,
                off_s = off_far + b_ssd, off_has = off_s + b_ssd, total = off_has + b_ssd;
-  CU(c, cudaMalloc(&d, total));
+  if (misc_reserve(c, total, &d)) return 1;
+  if (mr_ensure_smem(k_plot_stats, 2 * (size_t)N * sizeof(float))) MR_FAIL(c, "plot statistics kernel: shared memory attribute failed");
   std::vector<float> far(R), sstr(R);
   std::vector<int> has(R);
   cudaError_t e = cudaMemcpyAsync(d, best->ssd, b_ssd, cudaMemcpyHostToDevice, c->stream);
@@ -1316,7 +1347,6 @@ int mr_plot_stats(mr_ctx* c, const mr_best* best, int32_t ca_index, double* rows
   if (e == cudaSuccess) e = cudaMemcpyAsync(sstr.data(), d + off_s, b_ssd, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(has.data(), d + off_has, b_ssd, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(d);
   CU(c, e);
   c->st.h2d_bytes += (int64_t)(b_ssd + b_T + b_pairs);
   c->st.d2h_bytes += (int64_t)(3 * b_ssd);
@@ -1391,11 +1421,11 @@ int mr_gen_orientations(mr_ctx* c, int32_t L, float cutoff_rmsd, const int32_t* 
   const int64_t cand = (int64_t)ij.size();
   std::vector<float> T((size_t)cand * 12), rm((size_t)cand);
   if (cand > 0) {
-    int2* dij = nullptr;
-    float *dT = nullptr, *dr = nullptr;
-    CU(c, cudaMalloc(&dij, sizeof(int2) * (size_t)cand));
-    CU(c, cudaMalloc(&dT, 48 * (size_t)cand));
-    CU(c, cudaMalloc(&dr, 4 * (size_t)cand));
+    const size_t b_ij = (sizeof(int2) * (size_t)cand + 255) & ~(size_t)255, b_T = (48 * (size_t)cand + 255) & ~(size_t)255;
+    char* base = nullptr;
+    if (misc_reserve(c, b_ij + b_T + 4 * (size_t)cand, &base)) return 1;
+    int2* dij = reinterpret_cast<int2*>(base);
+    float *dT = reinterpret_cast<float*>(base + b_ij), *dr = reinterpret_cast<float*>(base + b_ij + b_T);
     CU(c, cudaMemcpyAsync(dij, ij.data(), sizeof(int2) * (size_t)cand, cudaMemcpyHostToDevice, c->stream));
     k_fragment_fit<<<(unsigned)((cand + 63) / 64), 64, 0, c->stream>>>(c->dA, c->dB, nb, L, dij, cand, dT, dr);
     CU(c, cudaGetLastError());
@@ -1403,7 +1433,6 @@ int mr_gen_orientations(mr_ctx* c, int32_t L, float cutoff_rmsd, const int32_t* 
     CU(c, cudaMemcpyAsync(T.data(), dT, 48 * (size_t)cand, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(rm.data(), dr, 4 * (size_t)cand, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    cudaFree(dij); cudaFree(dT); cudaFree(dr);
   }
   std::vector<int64_t> keep;
   for (int64_t k = 0; k < cand; k++)

@@ -518,3 +518,49 @@ def test_device_side_reduction_of_two_contexts(golden_c1):
     assert sum(owned) == int((g["strict_search_ssd"] < 1e26).sum())
     for s in ctxs:
         s.close()
+
+
+def test_refine_with_sequential_setup_superposition(golden_c1):
+    """Refine batches start from the orientation that superimposes each stored alignment; chains
+    too long for the team kernel (60 bytes of shared memory per point) take the sequential
+    kernel with > 48 KB of dynamic shared memory.  Forced here on the test pair: same table and
+    evaluation count as the default path (the opt-in was missing)."""
+    from minrms_b200 import OrientationGenerator
+    g = golden_c1
+    out = []
+    for seq in (0, 1):
+        s = make_search(g["A"], g["B"], settings_from_golden(g))
+        s.set_option("refine_seq_superpose", seq)
+        og = OrientationGenerator(s)
+        s.Search(og)
+        ev = s.Refine()
+        out.append((ev, s.best_table()))
+        s.close()
+    assert out[0][0] == out[1][0]
+    a, b = out[0][1], out[1][1]
+    assert_table_equal(a["ssd"], a["T"], a["pairs"], b["ssd"], b["T"], b["pairs"], int(g["n_min"]), "refine")
+    assert_table_equal(a["ssd"], a["T"], a["pairs"], g["strict_refine_ssd"], g["strict_refine_T"],
+                       g["strict_refine_pairs"], int(g["n_min"]), "refine vs reference")
+
+
+def test_nw_filter_with_more_than_4096_rows():
+    """warp-per-orientation NW filter with molecule 1 longer than 4096 residues: its row
+    coordinates need more than the default 48 KB of dynamic shared memory"""
+    rng = np.random.default_rng(77)
+    m, nB = 4200, 120
+    A = random_chain(rng, m)
+    B, idx = related_chain(rng, A[:400], nB, noise=0.8, return_idx=True)
+    p = oc.make_params(n_min=1, m=m, nB=nB, use_filter=True, of_dist=8.0, of_min=30)
+    s = make_search(A, B, settings_from_params(p, 4))
+    ws = oc.Workspace(A, B, p)
+    # the orientation that superimposes B on the stretch of A it was cut from (passes the
+    # filter), and the identity (does not)
+    from minrms_b200 import superimpose_batch
+    T_fit = superimpose_batch(s, A[idx][None], B[:idx.shape[0]][None])[1][0]
+    for T in (T_fit, IDENT):
+        res = s.eval_one(T)
+        ref = ws.eval(T)
+        assert res["nw_matches"] == ref["nw_matches"]
+        assert res["n_last"] == ref["n_last"]
+    assert s.eval_one(T_fit)["n_last"] > 0 and s.eval_one(IDENT)["n_last"] == 0
+    s.close()
