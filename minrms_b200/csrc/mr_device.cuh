@@ -30,6 +30,23 @@ static inline int mr_ensure_smem(Kern kern, size_t bytes) {
   return 0;
 }
 
+// -DMR_CHECK: device-side bounds checks on every table / scratch / carry index the kernels
+// form (printf + trap); a checking build of the library is run over scratch/sanitize_case.py and
+// the parity tests (profiles/r02_safety.md) -- compute-sanitizer is closed on this GPU pool.
+#ifdef MR_CHECK
+#include <cstdio>
+#define MR_ASSERT(cond)                                                                                   \
+  do {                                                                                                    \
+    if (!(cond)) {                                                                                        \
+      printf("MR_ASSERT failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, blockIdx.x, \
+             threadIdx.x);                                                                                \
+      __trap();                                                                                           \
+    }                                                                                                     \
+  } while (0)
+#else
+#define MR_ASSERT(cond) ((void)0)
+#endif
+
 #define MR_UB 1.0e26f  // DistanceMetric::UPPER_BOUND (lib/dyn/distance_metric.cc:49)
 
 struct MrDevParams {

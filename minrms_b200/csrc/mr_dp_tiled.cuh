@@ -82,7 +82,9 @@ struct TbTiled {
     uint4 grp = make_uint4(0, 0, 0, 0);
     int have = -1;
     while (cn > 0) {
+      MR_ASSERT(rho >= pad && jm >= 0 && (rho >> 3) < W && (cn >> 2) < CN);  // a path never leaves the live cells
       const int t = tab[(rho >> 3) * CN + (cn >> 2)];
+      MR_ASSERT(t >= 0 && t < T && (jm >> 1) < JP);
       uint32_t word;
       if (GROUP) {
         const int gi = (jm >> 1) * T + t;
@@ -224,6 +226,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
   const int nsurv = *surv_count;
 
   const MrTile me = tiles[tid];
+  MR_ASSERT(me.up_slot >= 0 && me.up_slot < nslots && me.dg_slot >= 0 && me.dg_slot < nslots && (int)blockDim.x + 2 == nslots);
   const bool has_tile = me.w >= 0;
   const int w = has_tile ? me.w : 0, c = has_tile ? me.c : 0;
   const int warp_lo = me.warp_lo, warp_hi = min(me.warp_hi, nsteps);
@@ -315,6 +318,8 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
                       st[D][3][R - 1]);
       // traceback: the K words of this tile every second column (j = s - w even)
       if (!COSTS && s == tb_next) {
+        MR_ASSERT(tbp >= reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) &&
+                  tbp + 1 <= reinterpret_cast<uint4*>(tb + (size_t)(sv + 1) * L.words(nB)));
         *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
         tbp += nthreads;
         tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;

@@ -124,6 +124,7 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
       const MrPass pass = passes[ps];
       const MrTileMp* ptiles = tiles + (size_t)ps * nthreads;
       const MrTileMp me = ptiles[tid];
+      MR_ASSERT(me.up_slot < nslots && me.dg_slot >= 0 && me.dg_slot < nslots && (size_t)(nBe + 1) * CN + (CN - 1) < carry_pitch);
       const bool has_tile = me.w >= 0;
       const int w = has_tile ? me.w : pass.w0, c = has_tile ? me.c : 0;
       const int wl = w - pass.w0;  // strip within the pass: this tile runs wl columns behind
@@ -210,9 +211,11 @@ k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, con
         mr_tile_publish(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
                         st[D][3][R - 1]);
         // bottom row of the pass -> carry[column j = s - wl]
+        MR_ASSERT(!((unsigned)(s - out_lo) <= own_span) || (s - wl >= 0 && (size_t)(s - wl) * CN + c < carry_pitch));
         if ((unsigned)(s - out_lo) <= own_span)
           __stcg(cme + (size_t)(s - wl) * CN, make_float4(st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1], st[D][3][R - 1]));
         if (!COSTS && s == tb_next) {
+          MR_ASSERT(tbp >= tb_o && tbp + 1 <= tb_o + L.words(nB) / 4);
           *tbp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
           tbp += L.T;
           tb_next = (s + 2 <= tb_hi) ? s + 2 : 0x3fffffff;

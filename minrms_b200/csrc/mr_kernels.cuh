@@ -32,6 +32,7 @@ struct TbColumns {
   __device__ __forceinline__ void walk(const int*, const uint32_t* __restrict__ tbo, int n, int m, int nB, Emit emit) const {
     int cn = n, ci = m, cj = nB;
     while (cn > 0) {
+      MR_ASSERT(ci >= cn && cj >= cn && ci <= m && cj <= nB);  // a path never leaves the live cells
       const uint32_t code = (tbo[word(cn, ci, cj)] >> shift(ci)) & 3u;  // 0 match, 1 skip-i, 2 skip-j
       if (code == 0) emit(cn - 1, ci - 1, cj - 1);
       cn -= (code == 0);
@@ -510,6 +511,7 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
   const size_t slot = (size_t)s * NP + (n - 1);
   // warp-interleaved slice: entry k of lane l sits at [warp][k][l] (coalesced per warp)
   short2* my = scratch + (size_t)(tid >> 5) * 32 * P.N + (tid & 31);
+  MR_ASSERT(n >= 1 && n <= P.N && s >= 0);
 #define MY(k) my[(size_t)(k) * 32]
   const uint32_t* tbo = tb + (size_t)s * L.words(P.nB);
   L.template walk<EMIT>(tab, tbo, n, P.m, P.nB, [&](int k, int i0, int j0) {
