@@ -2,7 +2,7 @@
 import re, subprocess, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from minrms_b200 import build as b
-cmd = ["nvcc"] + b.NVCC_FLAGS + os.environ.get("MR_NVCC_EXTRA", "").split() + ["-Xptxas", "-v", "-o", b.OUT, b.SRC]
+cmd = ["nvcc"] + b.NVCC_FLAGS + os.environ.get("MR_NVCC_EXTRA", "").split() + ["-Xptxas", "-v", "-o", os.environ.get("MR_BUILD_OUT", b.OUT), b.SRC]
 out = subprocess.run(cmd, capture_output=True, text=True)
 txt = out.stderr + out.stdout
 if out.returncode: print(txt[-3000:]); sys.exit(1)
