@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -101,6 +102,12 @@ struct mr_ctx {
   bool budget_is_default = true;
   int64_t opt_chunk = 0;
   int64_t opt_nw_general = 0;   // force the thread-per-orientation NW filter
+  // decision-only NW filter (k_nw_cost_*): the optimal cost decides NumMatches >= of_min when the
+  // cost intervals of of_min and of_min - 1 matches do not touch (see mr_kernels.cuh)
+  bool nw_cost_ok = false;
+  float nw_cost_thr = 0.0f;     // pass <=> A(m, nB) <= thr
+  double nw_cost_margin = 0.0;
+  int64_t opt_nw_cost = 1;      // 0: FirstPass filters with the counting kernels
   int64_t opt_dp_only = 0;      // experiments: skip traceback/select (results invalid)
   int64_t opt_costs_only_off = 0;  // tests / measurements: -IR FirstPass through the full kernel
   mr_stats st;
@@ -425,8 +432,9 @@ int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* ite
 }
 
 // filter (or identity) -> survivors of the chunk
+// decision_only: the caller needs the survivors, not the match counts (FirstPass)
 int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_filter,
-                  int* surv_out = nullptr, int* nw_out = nullptr) {
+                  int* surv_out = nullptr, int* nw_out = nullptr, bool decision_only = false) {
   int* const surv = surv_out ? surv_out : c->d_surv;
   int* const nwm = nw_out ? nw_out : c->d_nw;
   c->surv = surv;
@@ -436,7 +444,28 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
     if (!ev) MR_FAIL(c, "cudaEventCreate failed");
     CU(c, cudaEventRecord(ev->a, c->stream));
     const int cpl = (c->nB + 31) / 32;
-    if (c->hp.nb == 1 && cpl <= 8 && !c->opt_nw_general) {
+    const bool by_cost = decision_only && c->nw_cost_ok && c->opt_nw_cost && c->hp.nb == 1 && !c->opt_nw_general;
+    if (by_cost && cpl <= 8) {
+      const int grid = (count + 3) / 4;
+      const size_t sm = 4 * 3 * (size_t)c->m;
+#define MR_NWC(CPL) if (mr_ensure_smem(k_nw_cost_warp<CPL>, sm)) MR_FAIL(c, "NW filter: shared memory attribute failed"); \
+      k_nw_cost_warp<CPL><<<grid, 128, sm, c->stream>>>(c->P, c->nw_cost_thr, c->dA, c->dB, d_orient_chunk, count, surv, c->d_surv_count)
+      switch (cpl) {
+        case 1: MR_NWC(1); break; case 2: MR_NWC(2); break; case 3: MR_NWC(3); break; case 4: MR_NWC(4); break;
+        case 5: MR_NWC(5); break; case 6: MR_NWC(6); break; case 7: MR_NWC(7); break; default: MR_NWC(8); break;
+      }
+#undef MR_NWC
+    } else if (by_cost && c->nB <= 8192) {
+      const int nw = (c->nB + 255) / 256, cp = (c->nB + 32 * nw - 1) / (32 * nw);
+      const size_t sm = 4 * (size_t)((3 * c->m + 3) & ~3) + 4 * 128 * (size_t)(nw - 1);
+      const int grid = std::min(count, c->prop.multiProcessorCount * 16);
+      typedef void (*nwk_t)(MrDevParams, float, const float*, const float*, const float*, int, int*, int*);
+      static const nwk_t ks[2][4] = {{k_nw_cost_cta<5, 256>, k_nw_cost_cta<6, 256>, k_nw_cost_cta<7, 256>, k_nw_cost_cta<8, 256>},
+                                     {k_nw_cost_cta<5, 1024>, k_nw_cost_cta<6, 1024>, k_nw_cost_cta<7, 1024>, k_nw_cost_cta<8, 1024>}};
+      const nwk_t k = ks[nw > 8 ? 1 : 0][std::max(cp, 5) - 5];
+      if (mr_ensure_smem(k, sm)) MR_FAIL(c, "NW filter: shared memory attribute failed");
+      k<<<grid, 32 * nw, sm, c->stream>>>(c->P, c->nw_cost_thr, c->dA, c->dB, d_orient_chunk, count, surv, c->d_surv_count);
+    } else if (c->hp.nb == 1 && cpl <= 8 && !c->opt_nw_general) {
       // warp per orientation, wavefront in registers
       const int grid = (count + 3) / 4;
       const size_t sm = 4 * 3 * (size_t)c->m;
@@ -500,7 +529,7 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
       c->filter_cap = count;
     }
     if (c->chunk_cap == 0 && ensure_chunk(c, std::min<int64_t>(count, 4096))) return 1;  // row scratch of the fallback filter
-    if (launch_filter(c, d_orient, (int)count, true, c->d_surv_all, c->d_nw_all)) return 1;
+    if (launch_filter(c, d_orient, (int)count, true, c->d_surv_all, c->d_nw_all, true)) return 1;
     int* h_total = &c->h_pinned[c->h_pinned_cap - 1];
     CU(c, cudaMemcpyAsync(h_total, c->d_surv_count, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -751,6 +780,21 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   P.of_min = p->of_min;
   P.w0 = m - p->of_min + 1; P.w1 = nB - p->of_min + 1;
   P.refine_while_searching = p->refine_while_searching;
+  if (p->use_filter) {
+    // decision-only NW filter: cost intervals of "k >= of_min" and "k <= of_min - 1" matches
+    // (derivation at k_nw_cost_warp); E = half an ulp of the running value per rounding on a path
+    const double G = (double)P.nw_gap, cut = (double)P.nw_cutoff;
+    double E = 0.0;
+    auto half_ulp = [](double x) { int e; frexp(x, &e); return ldexp(1.0, e - 1 - 23) * 0.5; };  // float ulp / 2
+    for (int sgap = 1; sgap <= m + nB; sgap++) E += half_ulp(1.001 * sgap * G);
+    E += half_ulp(1.001 * (m + nB) * G);
+    const double U = (double)(m + nB - 2 * p->of_min) * G + (double)p->of_min * cut + E;   // most a cost with k >= of_min can be
+    const double L = (double)(m + nB - 2 * (p->of_min - 1)) * G - E;                       // least a cost with k <= of_min - 1 can be
+    const float thr = (float)(0.5 * (U + L));
+    c->nw_cost_margin = L - U;
+    c->nw_cost_ok = U < (double)thr && (double)thr < L;
+    c->nw_cost_thr = thr;
+  }
   c->Lc.IW = (m + 15) / 16;
   c->Lc.NP = c->NP;
   auto bail = [&](const char* what) {
@@ -835,6 +879,7 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
   else if (!strcmp(name, "ir_costs_only")) c->opt_costs_only_off = value == 0;
   else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);
+  else if (!strcmp(name, "nw_cost_filter")) c->opt_nw_cost = value != 0;
   else if (!strcmp(name, "refine_batch")) c->opt_refine_batch = std::max<int64_t>(0, value);
   else if (!strcmp(name, "refine_split")) c->opt_refine_split = value != 0;
   else if (!strcmp(name, "refine_seq_superpose")) c->opt_refine_seq_superpose = value != 0;

@@ -348,6 +348,169 @@ k_nw_filter_cta(MrDevParams P, const float* __restrict__ A, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------
+// K1+K2, decision-only form of the NW filter (FirstPass needs "NumMatches >= of_min", not the
+// number itself, orientation_filter.cc:129).  The optimal cost decides it exactly:
+//   along the traceback from (m, nB) to the border cell (ib, jb) it starts from
+//   (value fl((ib+jb) G), count 0; dynNW.cc:200-234, 484-498) there are k match steps and
+//   g = m + nB - ib - jb - 2k gap steps, every matched C is <= cutoff (a clipped 1e26 never wins
+//   against the all-gap path), so in exact arithmetic
+//        (m + nB - 2k) G  <=  cost  <=  (m + nB - 2k) G + k cutoff
+//   and the float table differs from that by at most E = sum over the <= m+nB+1 roundings on the
+//   path of half an ulp of the running value (<= s G at i + j = s).  With
+//   2G - of_min cutoff - 2E > 0 the cost intervals of "k >= of_min" and "k <= of_min - 1" do not
+//   touch, and one comparison with a threshold between them reproduces the reference's decision
+//   (the threshold and the margin are computed in mr_create; without a margin the counting
+//   kernels above run).  The cost table is the reference's, bit for bit (same float operations;
+//   a min does not depend on the tie order), but nothing else is carried: no match counts, no
+//   compare-and-select pairs -- 13 instead of ~35 instructions per cell.
+//   (best + G is formed once per cell for both of its uses.)
+// Same thread mapping as k_nw_filter_warp / k_nw_filter_cta.
+// ---------------------------------------------------------------------------
+template <int CPL>
+__global__ void __launch_bounds__(128)
+k_nw_cost_warp(MrDevParams P, float thr, const float* __restrict__ A, const float* __restrict__ B,
+               const float* __restrict__ orient, int count, int* __restrict__ surv,
+               int* __restrict__ surv_count) {
+  extern __shared__ float nw_sA[];  // m*3 (one atom per residue)
+  const int m = P.m, nB = P.nB, w0 = P.w0, w1 = P.w1;
+  for (int k = threadIdx.x; k < m * 3; k += blockDim.x) nw_sA[k] = A[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= count) return;
+  const float G = P.nw_gap, cutoff = P.nw_cutoff;
+  float T[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) T[k] = orient[12 * (size_t)o + k];
+  const int j0 = lane * CPL;  // my columns are j0+1 .. j0+CPL
+  float bx[CPL], by[CPL], bz[CPL], up[CPL], upg[CPL];  // up = A(i-1, j), upg = up + G
+#pragma unroll
+  for (int c = 0; c < CPL; c++) {
+    const int j = j0 + 1 + c;
+    bx[c] = by[c] = bz[c] = 0.0f;
+    if (j <= nB) mr_xform(T, B[3 * (j - 1)], B[3 * (j - 1) + 1], B[3 * (j - 1) + 2], bx[c], by[c], bz[c]);
+    up[c] = (float)j * G;  // row 0
+    upg[c] = up[c] + G;
+  }
+  float last = 0.0f, diag_in = (float)j0 * G;  // my last column at my current row; A[i-1][j0]
+  for (int t = 1; t <= m + 31; t++) {
+    float left = __shfl_up_sync(0xffffffffu, last, 1);
+    const int i = t - lane;
+    if (lane == 0) left = (float)i * G;  // column 0
+    if (i >= 1 && i <= m) {
+      const int jlo = (i <= w0) ? 1 : i - w0 + 1;
+      const int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
+      const float ax = nw_sA[3 * (i - 1)], ay = nw_sA[3 * (i - 1) + 1], az = nw_sA[3 * (i - 1) + 2];
+      float diag = diag_in;
+      diag_in = left;  // A[i][j0] is the diagonal input of my first column at the next row
+      float leftg = left + G;
+      const bool inside = (j0 + 1 >= jlo) && (j0 + CPL <= jhi);
+#pragma unroll
+      for (int c = 0; c < CPL; c++) {
+        const int j = j0 + 1 + c;
+        float cc = mr_d2(ax, ay, az, bx[c], by[c], bz[c]);
+        if (cc > cutoff) cc = MR_UB;
+        float best = fminf(fminf(upg[c], leftg), diag + cc);
+        if (!inside && (j < jlo || j > jhi)) best = (float)(i + j) * G;
+        diag = up[c];
+        up[c] = best;
+        leftg = best + G;
+        upg[c] = leftg;
+        left = best;
+      }
+      last = left;
+    }
+  }
+  // the lane that owns column nB holds A(m, nB): its row-m value of that column
+  const int owner = (nB - 1) / CPL;
+  float result = 0.0f;
+#pragma unroll
+  for (int c = 0; c < CPL; c++)
+    if (c == (nB - 1) - owner * CPL) result = up[c];
+  result = __shfl_sync(0xffffffffu, result, owner);
+  if (lane == 0 && result <= thr) surv[atomicAdd(surv_count, 1)] = o;
+}
+
+template <int CPL, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_nw_cost_cta(MrDevParams P, float thr, const float* __restrict__ A, const float* __restrict__ B,
+              const float* __restrict__ orient, int count, int* __restrict__ surv,
+              int* __restrict__ surv_count) {
+  extern __shared__ float nw_sA[];  // m*3 floats, then the rings
+  const int m = P.m, nB = P.nB, w0 = P.w0, w1 = P.w1;
+  float* ring = nw_sA + ((m * 3 + 3) & ~3);  // [warps-1][128] cost of the warp's last column
+  for (int k = threadIdx.x; k < m * 3; k += blockDim.x) nw_sA[k] = A[k];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float G = P.nw_gap, cutoff = P.nw_cutoff;
+  const int nblk_local = (m + 31 + 31) / 32;
+  const int nblk = nblk_local + 2 * (nwarps - 1);
+  const int j0 = (warp * 32 + lane) * CPL;  // my columns are j0+1 .. j0+CPL
+  for (int o = blockIdx.x; o < count; o += gridDim.x) {
+    __syncthreads();
+    float T[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) T[k] = orient[12 * (size_t)o + k];
+    float bx[CPL], by[CPL], bz[CPL], up[CPL], upg[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      const int j = j0 + 1 + c;
+      bx[c] = by[c] = bz[c] = 0.0f;
+      if (j <= nB) mr_xform(T, B[3 * (j - 1)], B[3 * (j - 1) + 1], B[3 * (j - 1) + 2], bx[c], by[c], bz[c]);
+      up[c] = (float)j * G;  // row 0
+      upg[c] = up[c] + G;
+    }
+    float last = 0.0f, diag_in = (float)j0 * G;
+    for (int g = 0; g < nblk; g++) {
+      const int beta = g - 2 * warp;
+      if (beta >= 0 && beta < nblk_local) {
+        for (int t = 32 * beta + 1; t <= 32 * beta + 32; t++) {
+          float left = __shfl_up_sync(0xffffffffu, last, 1);
+          const int i = t - lane;
+          const bool live = i >= 1 && i <= m;
+          if (lane == 0) {
+            if (warp == 0) left = (float)i * G;  // column 0
+            else if (live) left = ring[(warp - 1) * 128 + (i & 127)];
+          }
+          if (live) {
+            const int jlo = (i <= w0) ? 1 : i - w0 + 1;
+            const int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
+            const float ax = nw_sA[3 * (i - 1)], ay = nw_sA[3 * (i - 1) + 1], az = nw_sA[3 * (i - 1) + 2];
+            float diag = diag_in;
+            diag_in = left;
+            float leftg = left + G;
+            const bool inside = (j0 + 1 >= jlo) && (j0 + CPL <= jhi);
+#pragma unroll
+            for (int c = 0; c < CPL; c++) {
+              const int j = j0 + 1 + c;
+              float cc = mr_d2(ax, ay, az, bx[c], by[c], bz[c]);
+              if (cc > cutoff) cc = MR_UB;
+              float best = fminf(fminf(upg[c], leftg), diag + cc);
+              if (!inside && (j < jlo || j > jhi)) best = (float)(i + j) * G;
+              diag = up[c];
+              up[c] = best;
+              leftg = best + G;
+              upg[c] = leftg;
+              left = best;
+            }
+            last = left;
+            if (lane == 31 && warp + 1 < nwarps) ring[warp * 128 + (i & 127)] = last;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // the thread that owns column nB holds A(m, nB): its row-m value of that column
+    if (warp * 32 + lane == (nB - 1) / CPL) {
+      float result = 0.0f;
+#pragma unroll
+      for (int c = 0; c < CPL; c++)
+        if (c == (nB - 1) - ((nB - 1) / CPL) * CPL) result = up[c];
+      if (result <= thr) surv[atomicAdd(surv_count, 1)] = o;
+    }
+  }
+}
+
 __global__ void k_set_int(int* __restrict__ p, int v) { *p = v; }
 
 // Refine batch set-up in one launch: identity survivor list of `count` items and zeroed

@@ -1,21 +1,25 @@
-"""NW filter timing: python scratch/time_nw.py m nB count"""
-import sys, time, numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
-import oracle_ctypes as oc
-from helpers import *
-from minrms_b200 import SearchOrCuda, OrientationGenerator
-m, nB, count = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-rng = np.random.default_rng(7 * m + nB)
-A = random_chain(rng, m); B = related_chain(rng, A, nB, noise=1.2)
-of_min = int(0.33 * min(m, nB))
-p = oc.make_params(n_min=1, m=m, nB=nB, use_filter=True, of_dist=8.0, of_min=of_min)
-s = SearchOrCuda(A, B, settings_from_params(p, 4))
-og = OrientationGenerator(s)
-pick = og.orientations[np.linspace(0, og.size() - 1, count).astype(int)]
-s.upload_orientations(pick)
-for rep in range(2):
-    s.reset_best(); s.stats(reset=True)
-    s.search_resident(0, count, 0); s.fetch_keys()
-    st = s.stats()
-print('m %d nB %d count %d: nw %.2f ms (%d cells, %.1f GCUPS) survivors %d dp %.2f ms' % (
-    m, nB, count, st['nw_kernel_ms'], st['nw_cells'], st['nw_cells'] / st['nw_kernel_ms'] / 1e6, st['orientations_dp'], st['dp_kernel_ms']))
+"""NW filter alone: decision-only (cost) kernels against the counting kernels.
+python scratch/time_nw.py m nB n_orientations of_frac"""
+import os, sys, time, numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from minrms_b200 import OrientationGenerator, SearchOrCuda, Settings
+from minrms_b200.synth import random_chain, related_chain
+m, nB, n_or, frac = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4])
+rng = np.random.default_rng(4000)
+A = random_chain(rng, m); B = related_chain(np.random.default_rng(4001), A, nB)
+k = int(frac * min(m, nB))
+st = Settings(orientation_filter_nw=True, orientation_filter_nw_max_dist=8.0, orientation_filter_nw_min_num_matches=k)
+for by_cost in (1, 0):
+    s = SearchOrCuda(A, B, st)
+    s.set_option("nw_cost_filter", by_cost)
+    og = OrientationGenerator(s)
+    n = min(n_or, og.size())
+    s.upload_orientations(og.orientations[:n])
+    for rep in range(2):
+        s.reset_best(); s.stats(reset=True)
+        s.search_resident(0, n, 0)
+        stt = s.stats()
+    print("%dx%d of_min %d, %d orientations, by_cost=%d: nw %.2f ms = %.0f GCUPS, survivors %d" % (
+        m, nB, k, n, by_cost, stt["nw_kernel_ms"], stt["nw_cells"] / stt["nw_kernel_ms"] / 1e6, stt["orientations_dp"]))
+    s.close()

@@ -564,3 +564,38 @@ def test_nw_filter_with_more_than_4096_rows():
         assert res["n_last"] == ref["n_last"]
     assert s.eval_one(T_fit)["n_last"] > 0 and s.eval_one(IDENT)["n_last"] == 0
     s.close()
+
+
+@pytest.mark.parametrize("shape", [(120, 130, 2000), (141, 151, 3000), (400, 300, 600), (700, 600, 300)])
+def test_nw_filter_decided_by_cost_equals_counting_filter(shape):
+    """FirstPass only needs NumMatches >= of_min (orientation_filter.cc:129).  The decision-only
+    kernels (k_nw_cost_*) take it from the optimal NW cost, whose intervals for of_min and
+    of_min - 1 matches do not touch (bound in mr_create).  Thresholds all over the distribution
+    of match counts -- also where many orientations sit one match away from of_min -- must give
+    the survivor count of the oracle's DynNW and the tables of the counting kernels."""
+    from minrms_b200 import OrientationGenerator
+    m, nB, n_or = shape
+    rng = np.random.default_rng(5 * m + nB)
+    A = random_chain(rng, m)
+    B = related_chain(rng, A, nB, noise=1.2)
+    p0 = oc.make_params(n_min=1, m=m, nB=nB, use_filter=True, of_dist=8.0, of_min=1)
+    s0 = make_search(A, B, settings_from_params(p0, 4))
+    og = OrientationGenerator(s0)
+    orient = og.orientations[:n_or]
+    s0.close()
+    counts = np.array([oc.nw_num_matches(A, oc.apply_transform(T, B), 1, 8.0, 1) for T in orient])
+    # thresholds at quantiles of the counts: plenty of orientations at of_min and of_min - 1
+    for of_min in sorted(set(int(q) for q in np.quantile(counts, [0.5, 0.9, 0.99]) if q >= 1)):
+        p = oc.make_params(n_min=1, m=m, nB=nB, use_filter=True, of_dist=8.0, of_min=of_min)
+        tabs = []
+        for by_cost in (1, 0):
+            s = make_search(A, B, settings_from_params(p, 4))
+            s.set_option("nw_cost_filter", by_cost)
+            s.stats(reset=True)
+            s.Search(orient)
+            assert s.stats()["orientations_dp"] == int((counts >= of_min).sum()), (of_min, by_cost)
+            tabs.append(s.best_table())
+            s.close()
+        a, b = tabs
+        assert np.array_equal(bits(a["ssd"]), bits(b["ssd"])) and np.array_equal(a["o_id"], b["o_id"])
+        assert np.sum(counts == of_min) + np.sum(counts == of_min - 1) > 0
