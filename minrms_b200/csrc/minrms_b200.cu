@@ -108,6 +108,7 @@ struct mr_ctx {
   float nw_cost_thr = 0.0f;     // pass <=> A(m, nB) <= thr
   double nw_cost_margin = 0.0;
   int64_t opt_nw_cost = 1;      // 0: FirstPass filters with the counting kernels
+  int64_t opt_dp_form = 0;      // 0: min-with-predicate kernels where a bucket exists, 1: two-min / ping-pong forms only
   int64_t opt_dp_only = 0;      // experiments: skip traceback/select (results invalid)
   int64_t opt_costs_only_off = 0;  // tests / measurements: -IR FirstPass through the full kernel
   mr_stats st;
@@ -368,7 +369,14 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count, bool latency = 
   if (!ev) MR_FAIL(c, "cudaEventCreate failed");
   CU(c, cudaEventRecord(ev->a, c->stream));
   const int path = dp_path(c);
-  if (path == 1) {
+  if (path == 1 && !costs_only && c->tiled.vp_bucket && c->opt_dp_form == 0) {
+    // min-with-predicate form, from the patched cubin (mr_dp_vp.cu); there is no silent fallback:
+    // a library that carries the cubin and cannot launch it reports the error
+    std::string why;
+    if (mr_launch_dp_tiles_vp(c->tiled, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb,
+                              c->d_cost, count, c->stream, c->device, &why) != 0)
+      MR_FAIL(c, "tiled DP launch (min-with-predicate kernel) failed: %s", why.c_str());
+  } else if (path == 1) {
     if (mr_launch_dp_tiled(c->tiled, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
                            c->d_tb, c->d_cost, count, c->stream, costs_only) != 0)
       MR_FAIL(c, "tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -876,6 +884,7 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "dp_kernel")) c->opt_dp_kernel = value;
   else if (!strcmp(name, "budget_mb")) { c->opt_budget_mb = std::max<int64_t>(64, value); c->budget_is_default = false; }
   else if (!strcmp(name, "chunk")) c->opt_chunk = value;
+  else if (!strcmp(name, "dp_form")) c->opt_dp_form = value;
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
   else if (!strcmp(name, "ir_costs_only")) c->opt_costs_only_off = value == 0;
   else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);

@@ -41,6 +41,9 @@
 #include <vector>
 #include "mr_device.cuh"
 #include "mr_tile_step.cuh"
+#ifndef MR_DP_TILED_DEVICE_ONLY
+#include "mr_vp_module.h"
+#endif
 
 // Traceback storage of the tiled kernel.  Each tile (thread t of the CTA) writes, every
 // second column, one 32-bit word per layer of the tile: 2 columns x R=8 rows x 2 bits,
@@ -133,6 +136,8 @@ struct MrTiledPlan {
   int ctas_per_sm = 1;
   int grid_cap = 0;
   int grid_cap_costs = 0;  // costs-only kernel (fewer registers: two CTAs per SM up to 384 threads)
+  int vp_bucket = 0;       // CTA-size bucket of the min-with-predicate kernel (mr_dp_vp.cu), 0: none
+  int grid_cap_vp = 0;
   size_t tb_words = 0;
   double lane_efficiency = 0.0;
   TbTiled layout;
@@ -206,12 +211,14 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
 #else
 #define MR_DP_ATTR(MAXT, MINB) __launch_bounds__(MAXT, MINB)
 #endif
-template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP, bool COSTS = false>
-__global__ void MR_DP_ATTR(MAXT, MINB)
-k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
-           const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
-           const int* __restrict__ surv, const int* __restrict__ surv_count,
-           uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
+// the kernel body (a device function so that the min-with-predicate form can be instantiated
+// under extern "C" names in its own translation unit, mr_dp_vp.cu)
+template <int K, int R, bool NB1, bool WINDOWED, bool PP, bool COSTS, bool VP>
+__device__ __forceinline__ void
+mr_dp_tiles_body(const MrDevParams& P, const TbTiled& L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
+                 const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
+                 const int* __restrict__ surv, const int* __restrict__ surv_count,
+                 uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
   static_assert(R == MR_TR && K == MR_TK, "traceback word packing assumes 4 x 8 tiles");
   extern __shared__ float4 smem4[];
   const int m = P.m, nB = P.nB, nb = P.nb;
@@ -276,7 +283,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
 
     // tile state: the ping-pong form keeps two copies (read one, write the other), the in-place
     // form one; bprev = upper boundary A(n, i_lo-1, .) of the previous column (and, ping-pong, this one)
-    static_assert(!(COSTS && PP), "the costs-only update is in place");
+    static_assert(!(COSTS && PP) && !(VP && (PP || COSTS)), "the costs-only and min-with-predicate updates are in place");
     constexpr int NC = PP ? 2 : 1;
     float st[NC][K][R], bprev[NC][K];
     uint32_t acc[K];
@@ -317,6 +324,7 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
       } else {
         const float bin[K] = {ub.x, ub.y, ub.z, ub.w};
         if constexpr (COSTS) mr_tile_update_costs(st[0], bprev[0], bin, cv, dsh);
+        else if constexpr (VP) mr_tile_update_vp(st[0], bprev[0], bin, acc, cv, dsh);
         else mr_tile_update_ip(st[0], bprev[0], bin, acc, cv, dsh);
       }
       mr_tile_publish(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
@@ -367,8 +375,20 @@ k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __res
   }
 }
 
+#ifndef MR_DP_TILED_DEVICE_ONLY   // mr_dp_vp.cu takes the kernel body only
+template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP, bool COSTS = false>
+__global__ void MR_DP_ATTR(MAXT, MINB)
+k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
+           const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
+           const int* __restrict__ surv, const int* __restrict__ surv_count,
+           uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
+  mr_dp_tiles_body<K, R, NB1, WINDOWED, PP, COSTS, false>(P, L, nslots, nsteps, tiles, A, B, orient, surv, surv_count, tb, cost_out);
+}
+
 // ---------------------------------------------------------------------------------- host
 static inline int mr_dp_tiles_minb(int threads);
+static inline int mr_dp_vp_bucket(int threads);
+static inline int mr_dp_vp_minb(int bucket);
 static inline int mr_dp_tiles_minb_costs(int threads);
 static inline bool mr_dp_tiles_pp(int threads);
 static inline void mr_free_dp_tiled(MrTiledPlan* p) {
@@ -467,6 +487,8 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   p->ctas_per_sm = std::max(1, std::min(by_smem, want));
   p->grid_cap = prop.multiProcessorCount * p->ctas_per_sm;
   p->grid_cap_costs = prop.multiProcessorCount * std::max(1, std::min(by_smem, mr_dp_tiles_minb_costs(threads)));
+  p->vp_bucket = mr_dp_vp_bucket(threads);
+  p->grid_cap_vp = prop.multiProcessorCount * std::max(1, std::min(by_smem, mr_dp_vp_minb(p->vp_bucket)));
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
   p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = threads;
   p->layout.tile_of = p->d_tile_of;
@@ -527,6 +549,44 @@ static inline bool mr_dp_tiles_pp(int threads) {
   return false;
 }
 
+// Buckets of the min-with-predicate kernels: the (MAXT, MINB) pairs MR_VP_BUCKET instantiates in
+// mr_dp_vp.cu, by name k_dp_vp_<MAXT>_{g,gw,c,cw} (general / one atom per residue, windowed).
+#define MR_VP_BUCKETS(X) X(320, 2) X(352, 2) X(384, 2)
+static inline int mr_dp_vp_bucket(int threads) {
+#if MR_HAVE_VP_CUBIN
+  if (threads <= 256) return 0;   // small CTAs keep the two-min form (several CTAs per SM)
+#define MR_X(MAXT, MINB) if (threads <= MAXT) return MAXT;
+  MR_VP_BUCKETS(MR_X)
+#undef MR_X
+#endif
+  (void)threads;
+  return 0;
+}
+static inline int mr_dp_vp_minb(int bucket) {
+#define MR_X(MAXT, MINB) if (bucket == MAXT) return MINB;
+  MR_VP_BUCKETS(MR_X)
+#undef MR_X
+  return 1;
+}
+// 0 launched, 1 failed (*why says what)
+static inline int mr_launch_dp_tiles_vp(const MrTiledPlan& p, const MrDevParams& P, const float* A, const float* B,
+                                        const float* orient, const int* surv, const int* surv_count, uint32_t* tb,
+                                        float* cost, int count, cudaStream_t stream, int device, std::string* why) {
+  char name[64];
+  snprintf(name, sizeof name, "k_dp_vp_%d_%s%s", p.vp_bucket, P.nb == 1 ? "c" : "g", P.n_min > 1 ? "w" : "");
+  CUfunction f = mr_vp_function(device, name, p.smem, why);
+  if (!f) return 1;
+  MrDevParams Pv = P;
+  TbTiled Lv = p.layout;
+  int nslots = p.nslots, nsteps = p.steps;
+  const MrTile* tiles = p.d_tiles;
+  void* args[] = {&Pv, &Lv, &nslots, &nsteps, &tiles, &A, &B, &orient, &surv, &surv_count, &tb, &cost};
+  const int grid = std::min(count, p.grid_cap_vp);
+  const CUresult r = mr_vp_driver().LaunchKernel(f, grid, 1, 1, p.threads, 1, 1, (unsigned)p.smem, (CUstream)stream, args, nullptr);
+  if (r != CUDA_SUCCESS) { *why = std::string("cuLaunchKernel(") + name + "): " + mr_vp_errstr(r); return 1; }
+  return 0;
+}
+
 static inline int mr_launch_dp_tiled(const MrTiledPlan& p, const MrDevParams& P, const float* A,
                                      const float* B, const float* orient, const int* surv,
                                      const int* surv_count, uint32_t* tb, float* cost, int count,
@@ -537,3 +597,4 @@ static inline int mr_launch_dp_tiled(const MrTiledPlan& p, const MrDevParams& P,
 #undef MR_X
   return mr_launch_dp_tiles_t<1024, 1, false>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream, costs_only);
 }
+#endif  // MR_DP_TILED_DEVICE_ONLY
