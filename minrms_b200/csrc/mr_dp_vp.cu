@@ -6,8 +6,11 @@
 #define MR_DP_TILED_DEVICE_ONLY
 #include "mr_dp_tiled.cuh"
 
+// launch bounds: registers are allocated per warp in units of 512, so two CTAs of 352 threads
+// (11 warps) get 80 registers per thread (88 measured: one CTA per SM)
+#define MR_VP_ATTR(MAXT, MINB) __launch_bounds__(MAXT, MINB)
 #define MR_VP_KERNEL(NAME, MAXT, MINB, NB1, WINDOWED)                                                               \
-  extern "C" __global__ void __launch_bounds__(MAXT, MINB)                                                            \
+  extern "C" __global__ void MR_VP_ATTR(MAXT, MINB)                                                            \
   NAME(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,                            \
        const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,                    \
        const int* __restrict__ surv, const int* __restrict__ surv_count, uint32_t* __restrict__ tb,                   \

@@ -165,25 +165,34 @@ __device__ __forceinline__ uint32_t mr_vmin_p(uint32_t a, uint32_t b, bool& a_le
 __device__ __forceinline__ void mr_tile_update_vp(float (&st)[MR_TK][MR_TR], float (&bprev)[MR_TK],
                                                   const float (&bin)[MR_TK], uint32_t (&hold)[MR_TK],
                                                   const float (&cv)[MR_TR], const float (&dsh)[MR_TR]) {
+  // Cells in skewed waves: wave t = {(k, r) : r = t - (K-1-k)}, upper layers first.  The four
+  // cells of a wave are independent (instruction-level parallelism in source order), (k, r)
+  // reads the old value of (k-1, r-1) in the same wave before that cell overwrites it, and its
+  // `up` (k, r-1) is one wave old: every cell is updated in place, nothing is copied.
+  uint32_t up[MR_TK];
+  float acc[MR_TK];
 #pragma unroll
-  for (int k = MR_TK - 1; k >= 0; k--) {
-    uint32_t up = __float_as_uint(bin[k]);
-    float acc = MR_VP_MAGIC;
+  for (int k = 0; k < MR_TK; k++) { up[k] = __float_as_uint(bin[k]); acc[k] = MR_VP_MAGIC; }
 #pragma unroll
-    for (int r = 0; r < MR_TR; r++) {
+  for (int t = 0; t < MR_TR + MR_TK - 1; t++) {
+#pragma unroll
+    for (int k = MR_TK - 1; k >= 0; k--) {
+      const int r = t - (MR_TK - 1 - k);
+      if (r < 0 || r >= MR_TR) continue;
       const float dg = (k > 0) ? ((r > 0) ? st[k - 1][r - 1] : bprev[k - 1]) : dsh[r];
       const float d = dg + cv[r];
       bool up_le_d, left_le_t;
-      const uint32_t t = mr_vmin_p(up, __float_as_uint(d), up_le_d);
-      const uint32_t best = mr_vmin_p(__float_as_uint(st[k][r]), t, left_le_t);
-      if (!up_le_d) acc += (float)(1u << (15 - 2 * r));     // s1: NOT (up <= d)
-      if (!left_le_t) acc += (float)(1u << (14 - 2 * r));   // s2: NOT (left <= min(d, up))
+      const uint32_t tt = mr_vmin_p(up[k], __float_as_uint(d), up_le_d);
+      const uint32_t best = mr_vmin_p(__float_as_uint(st[k][r]), tt, left_le_t);
+      if (!up_le_d) acc[k] += (float)(1u << (15 - 2 * r));     // s1: NOT (up <= d)
+      if (!left_le_t) acc[k] += (float)(1u << (14 - 2 * r));   // s2: NOT (left <= min(d, up))
       st[k][r] = __uint_as_float(best);
-      up = best;
+      up[k] = best;
     }
-    // shift this column's 16 bits in below the previous column's
-    hold[k] = __byte_perm(__float_as_uint(acc), hold[k], 0x5410);
   }
+  // shift this column's 16 bits in below the previous column's
+#pragma unroll
+  for (int k = 0; k < MR_TK; k++) hold[k] = __byte_perm(__float_as_uint(acc[k]), hold[k], 0x5410);
 #pragma unroll
   for (int k = 0; k < MR_TK; k++) bprev[k] = bin[k];
 }
@@ -218,6 +227,24 @@ __device__ __forceinline__ void mr_tile_publish(uint32_t a_wr, float btop, const
   mr_sts128(a_wr, btop, top[0], top[1], top[2]);
   mr_sts128(a_wr + 16u, top[3], top[4], top[5], top[6]);
   mr_sts128(a_wr + 32u, b0, b1, b2, b3);
+}
+
+// the same 48 bytes as twelve 4-byte stores: for the in-place forms, whose state registers stay
+// where they are from step to step and are not allocated as aligned quads (ptxas then copies
+// twelve values per step into a quad for the 16-byte stores; the shared-memory wavefronts are the
+// same either way: a 16-byte store of a warp takes four)
+__device__ __forceinline__ void mr_sts32(uint32_t a, float x) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+}
+__device__ __forceinline__ void mr_tile_publish32(uint32_t a_wr, float btop, const float (&top)[MR_TR], float b0, float b1,
+                                                  float b2, float b3) {
+  mr_sts32(a_wr, btop);
+#pragma unroll
+  for (int r = 0; r < MR_TR - 1; r++) mr_sts32(a_wr + 4u + 4u * r, top[r]);
+  mr_sts32(a_wr + 32u, b0);
+  mr_sts32(a_wr + 36u, b1);
+  mr_sts32(a_wr + 40u, b2);
+  mr_sts32(a_wr + 44u, b3);
 }
 
 // n < n_min: the reference reports the corner of the layer's window, A(n, n+wA-1, n+wB-1)

@@ -97,6 +97,8 @@ static inline CUfunction mr_vp_function(int device, const char* name, size_t sme
     CUfunction f = nullptr;
     const CUresult r = d.ModuleGetFunction(&f, m.mod, name);
     if (r != CUDA_SUCCESS) { *why = std::string("cuModuleGetFunction(") + name + "): " + mr_vp_errstr(r); return nullptr; }
+    // two CTAs per SM need the large shared-memory carve-out (the driver's default picked one CTA's worth)
+    d.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
     it = m.fn.emplace(name, f).first;
   }
   size_t& have = m.smem[name];
