@@ -498,7 +498,7 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   p->ctas_per_sm = std::max(1, std::min(by_smem, want));
   p->grid_cap = prop.multiProcessorCount * p->ctas_per_sm;
   p->grid_cap_costs = prop.multiProcessorCount * std::max(1, std::min(by_smem, mr_dp_tiles_minb_costs(threads)));
-  p->vp_bucket = pp ? mr_dp_vp_bucket(threads) : 0;  // the min-with-predicate kernels step in pairs, like ping-pong
+  p->vp_bucket = (!MR_VP_PAIRED || pp) ? mr_dp_vp_bucket(threads) : 0;
   p->grid_cap_vp = prop.multiProcessorCount * std::max(1, std::min(by_smem, mr_dp_vp_minb(p->vp_bucket)));
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
   p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = threads;
@@ -562,10 +562,10 @@ static inline bool mr_dp_tiles_pp(int threads) {
 
 // Buckets of the min-with-predicate kernels: the (MAXT, MINB) pairs MR_VP_BUCKET instantiates in
 // mr_dp_vp.cu, by name k_dp_vp_<MAXT>_{g,gw,c,cw} (general / one atom per residue, windowed).
-#define MR_VP_BUCKETS(X) X(320, 2) X(352, 2) X(384, 2)
+// (80 registers per thread, allocated per warp in units of 512: 2560 per warp, 25 warps per SM)
+#define MR_VP_BUCKETS(X) X(64, 12) X(128, 6) X(192, 4) X(256, 3) X(320, 2) X(352, 2) X(384, 2)
 static inline int mr_dp_vp_bucket(int threads) {
 #if MR_HAVE_VP_CUBIN
-  if (threads <= 256) return 0;   // small CTAs keep the two-min form (several CTAs per SM)
 #define MR_X(MAXT, MINB) if (threads <= MAXT) return MAXT;
   MR_VP_BUCKETS(MR_X)
 #undef MR_X

@@ -23,6 +23,10 @@
   MR_VP_KERNEL(k_dp_vp_##MAXT##_gw, MAXT, MINB, false, true)       \
   MR_VP_KERNEL(k_dp_vp_##MAXT##_c, MAXT, MINB, true, false)        \
   MR_VP_KERNEL(k_dp_vp_##MAXT##_cw, MAXT, MINB, true, true)
+MR_VP_BUCKET(64, 12)
+MR_VP_BUCKET(128, 6)
+MR_VP_BUCKET(192, 4)
+MR_VP_BUCKET(256, 3)
 MR_VP_BUCKET(320, 2)
 MR_VP_BUCKET(352, 2)
 MR_VP_BUCKET(384, 2)
