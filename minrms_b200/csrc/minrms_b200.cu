@@ -108,7 +108,7 @@ struct mr_ctx {
   float nw_cost_thr = 0.0f;     // pass <=> A(m, nB) <= thr
   double nw_cost_margin = 0.0;
   int64_t opt_nw_cost = 1;      // 0: FirstPass filters with the counting kernels
-  int64_t opt_dp_form = 0;      // 0: min-with-predicate kernels where a bucket exists, 1: two-min / ping-pong forms only
+  int64_t opt_dp_form = 0;      // 0: min-with-predicate kernels for single-pass problems, 1: two-min / ping-pong forms only, 2: min-with-predicate also for multi-pass problems
   int64_t opt_dp_only = 0;      // experiments: skip traceback/select (results invalid)
   int64_t opt_costs_only_off = 0;  // tests / measurements: -IR FirstPass through the full kernel
   mr_stats st;
@@ -118,6 +118,9 @@ struct mr_ctx {
   std::string err;
   MrTiledPlan tiled;
   MrTiledMpPlan tiled_mp;
+  MrTiledMpPlan tiled_mp_vp;               // plan of the min-with-predicate multi-pass kernels (384 or 320 threads x 2 CTAs per SM)
+  const TbTiled* cur_mp_layout = nullptr;  // layout of the multi-pass plan that wrote the traceback table of the current chunk
+  int64_t opt_mp_vp_threads = 384;
   int64_t opt_mp_threads = 0;   // tests: threads per CTA of the multi-pass kernel (forces more passes)
   cudaEvent_t user_ev[16] = {};
 };
@@ -236,7 +239,31 @@ int dp_path(const mr_ctx* c) {
   return c->tiled_mp.ok ? 2 : (c->tiled.ok ? 1 : 0);
 }
 bool use_tiled(const mr_ctx* c) { return dp_path(c) != 0; }
-const TbTiled& tiled_layout(const mr_ctx* c) { return dp_path(c) == 2 ? c->tiled_mp.layout : c->tiled.layout; }
+const TbTiled& tiled_layout(const mr_ctx* c) {
+  if (dp_path(c) != 2) return c->tiled.layout;
+  return c->cur_mp_layout ? *c->cur_mp_layout : c->tiled_mp.layout;
+}
+// multi-pass plans: the 512-thread ping-pong plan (also the split mode of Refine batches) and, when
+// the library carries the patched cubin, the plan of the min-with-predicate kernels
+void plan_mp(mr_ctx* c, int max_threads = 0) {
+  mr_plan_dp_tiled_mp(&c->tiled_mp, c->P, c->prop, c->NP, max_threads);
+  mr_free_dp_tiled_mp(&c->tiled_mp_vp);
+  c->tiled_mp_vp.ok = false;
+  c->cur_mp_layout = nullptr;
+#if MR_HAVE_VP_CUBIN
+  if (c->tiled_mp.ok && max_threads == 0 && c->opt_dp_form == 2) {
+    mr_plan_dp_tiled_mp(&c->tiled_mp_vp, c->P, c->prop, c->NP, (int)c->opt_mp_vp_threads);
+    if (c->tiled_mp_vp.ok && c->tiled_mp_vp.threads != (int)c->opt_mp_vp_threads) {  // a row strip wider than the CTA
+      mr_free_dp_tiled_mp(&c->tiled_mp_vp);
+      c->tiled_mp_vp.ok = false;
+    }
+  }
+#endif
+}
+// (measured slower than the 512-thread ping-pong kernel: at 80 registers the multi-pass step -- carry
+// prefetch, carry store, pass bookkeeping on top of the tile -- spills inside the column loop, 5
+// local loads per warp-step: 0.9 against 2.1 TCUPS at 300 x 300; kept behind dp_form = 2)
+bool mp_vp_in_use(const mr_ctx* c) { return c->tiled_mp_vp.ok && c->opt_dp_form == 2; }
 
 // The per-chunk work space (tens of GB; ~100 GB for long chains) is ONE device allocation, the
 // arena, carved up by ensure_chunk.  A destroyed context parks its arena in a per-device cache
@@ -297,7 +324,8 @@ static int arena_reserve(mr_ctx* c, size_t bytes) {
 int ensure_chunk(mr_ctx* c, int64_t want) {
   const size_t words_c = c->Lc.words(c->nB);
   const int path = dp_path(c);
-  const size_t words = path == 2 ? c->tiled_mp.tb_words : path == 1 ? c->tiled.tb_words : words_c;
+  const size_t words = path == 2 ? std::max(c->tiled_mp.tb_words, mp_vp_in_use(c) ? c->tiled_mp_vp.tb_words : (size_t)0)
+                                 : path == 1 ? c->tiled.tb_words : words_c;
   const size_t per_thread_scr = (size_t)c->N * sizeof(short2);
   const int per = std::max(1, c->hp.n_max - std::max(2, c->hp.n_min) + 1);
   // bytes per orientation in a chunk
@@ -369,7 +397,7 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count, bool latency = 
   if (!ev) MR_FAIL(c, "cudaEventCreate failed");
   CU(c, cudaEventRecord(ev->a, c->stream));
   const int path = dp_path(c);
-  if (path == 1 && !costs_only && c->tiled.vp_bucket && c->opt_dp_form == 0) {
+  if (path == 1 && !costs_only && c->tiled.vp_bucket && c->opt_dp_form != 1) {
     // min-with-predicate form, from the patched cubin (mr_dp_vp.cu); there is no silent fallback:
     // a library that carries the cubin and cannot launch it reports the error
     std::string why;
@@ -380,7 +408,15 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count, bool latency = 
     if (mr_launch_dp_tiled(c->tiled, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
                            c->d_tb, c->d_cost, count, c->stream, costs_only) != 0)
       MR_FAIL(c, "tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  } else if (path == 2 && !costs_only && mp_vp_in_use(c) &&
+             !(latency && c->opt_refine_split && count <= c->tiled_mp.split_cap)) {
+    std::string why;
+    c->cur_mp_layout = &c->tiled_mp_vp.layout;
+    if (mr_launch_dp_tiles_mp_vp(c->tiled_mp_vp, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb,
+                                 c->d_cost, count, c->stream, c->device, &why) != 0)
+      MR_FAIL(c, "multi-pass tiled DP launch (min-with-predicate kernel) failed: %s", why.c_str());
   } else if (path == 2) {
+    c->cur_mp_layout = &c->tiled_mp.layout;
     if (mr_launch_dp_tiled_mp(c->tiled_mp, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
                               c->d_tb, c->d_cost, count, c->stream,
                               latency && c->opt_refine_split && count <= c->tiled_mp.split_cap, costs_only) != 0)
@@ -834,7 +870,7 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   if (mr_ensure_smem(k_dp_columns, c->dp_smem)) return bail("smem attribute");
   tick("general kernel setup");
   mr_plan_dp_tiled(&c->tiled, P, c->prop, c->NP);
-  if (!c->tiled.ok || c->tiled.threads > 512) mr_plan_dp_tiled_mp(&c->tiled_mp, P, c->prop, c->NP);
+  if (!c->tiled.ok || c->tiled.threads > 512) plan_mp(c);
   tick("tiled plan");
   const int RR = std::max(c->R, 1), slots = std::max(RR, c->NP);
   if (cudaMalloc(&c->d_keys, 8 * (size_t)RR) != cudaSuccess) return bail("malloc");
@@ -868,6 +904,7 @@ void mr_destroy(mr_ctx* c) {
   if (c->h_ref) cudaFreeHost(c->h_ref);
   mr_free_dp_tiled(&c->tiled);
   mr_free_dp_tiled_mp(&c->tiled_mp);
+  mr_free_dp_tiled_mp(&c->tiled_mp_vp);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -884,7 +921,15 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   if (!strcmp(name, "dp_kernel")) c->opt_dp_kernel = value;
   else if (!strcmp(name, "budget_mb")) { c->opt_budget_mb = std::max<int64_t>(64, value); c->budget_is_default = false; }
   else if (!strcmp(name, "chunk")) c->opt_chunk = value;
-  else if (!strcmp(name, "dp_form")) c->opt_dp_form = value;
+  else if (!strcmp(name, "dp_form")) {
+    if (value < 0 || value > 2) MR_FAIL(c, "mr_set_option: dp_form is 0, 1 or 2");
+    c->opt_dp_form = value;
+    if (c->tiled_mp.ok && value == 2 && !c->tiled_mp_vp.ok) {
+      if (cudaSetDevice(c->device) != cudaSuccess) MR_FAIL(c, "cudaSetDevice failed");
+      cudaStreamSynchronize(c->stream);
+      plan_mp(c, (int)c->opt_mp_threads);
+    }
+  }
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
   else if (!strcmp(name, "ir_costs_only")) c->opt_costs_only_off = value == 0;
   else if (!strcmp(name, "nw_kernel")) c->opt_nw_general = (value == 1);
@@ -897,13 +942,20 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
     c->opt_mp_threads = value;
     if (cudaSetDevice(c->device) != cudaSuccess) MR_FAIL(c, "cudaSetDevice failed");
     cudaStreamSynchronize(c->stream);
-    if (c->tiled_mp.ok || c->opt_dp_kernel == 3) mr_plan_dp_tiled_mp(&c->tiled_mp, c->P, c->prop, c->NP, (int)c->opt_mp_threads);
+    if (c->tiled_mp.ok || c->opt_dp_kernel == 3) plan_mp(c, (int)c->opt_mp_threads);
+  }
+  else if (!strcmp(name, "mp_vp_threads")) {
+    if (value != 320 && value != 384) MR_FAIL(c, "mr_set_option: mp_vp_threads is 320 or 384");
+    c->opt_mp_vp_threads = value;
+    if (cudaSetDevice(c->device) != cudaSuccess) MR_FAIL(c, "cudaSetDevice failed");
+    cudaStreamSynchronize(c->stream);
+    if (c->tiled_mp.ok) plan_mp(c, (int)c->opt_mp_threads);
   }
   else MR_FAIL(c, "mr_set_option: unknown option %s", name);
   if (c->opt_dp_kernel == 2 && !c->tiled.ok) MR_FAIL(c, "tiled DP kernel not available for this problem: %s", c->tiled.why);
   if (c->opt_dp_kernel == 3) {
     if (cudaSetDevice(c->device) != cudaSuccess) MR_FAIL(c, "cudaSetDevice failed");
-    if (!c->tiled_mp.ok) mr_plan_dp_tiled_mp(&c->tiled_mp, c->P, c->prop, c->NP, (int)c->opt_mp_threads);
+    if (!c->tiled_mp.ok) plan_mp(c, (int)c->opt_mp_threads);
     if (!c->tiled_mp.ok) MR_FAIL(c, "multi-pass tiled DP kernel not available for this problem: %s", c->tiled_mp.why);
   }
   return 0;

@@ -1,5 +1,6 @@
-"""Single-pass DP kernel by chain length: min-with-predicate form (dp_form 0) against the two-min /
-ping-pong forms (dp_form 1).  python scratch/time_forms.py 40 60 100 141x151 170"""
+"""DP kernel by chain length: min-with-predicate form (dp_form 0; multi-pass: 384- and 320-thread
+buckets) against the two-min / ping-pong forms (dp_form 1).
+python scratch/time_forms.py 40 60 100 141x151 170 300 600"""
 import os, sys, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,11 +12,15 @@ for arg in sys.argv[1:]:
     rng = np.random.default_rng(7 * m + nB)
     A = random_chain(rng, m); B = related_chain(rng, A, nB)
     cells = dp_cells_per_orientation(m, nB, 1, min(m, nB))
-    count = int(min(60000, max(2000, 2.0e10 / cells)))
+    count = int(min(60000, max(592, 2.0e10 / cells)))
+    variants = [("vp", {"dp_form": 0}), ("legacy", {"dp_form": 1})]
+    if min(m, nB) > 190:
+        variants = [("vp mp 384", {"dp_form": 2}), ("vp mp 320", {"dp_form": 2, "mp_vp_threads": 320}), ("legacy", {"dp_form": 1})]
     keys = []
-    for form in (0, 1):
+    for label, opts in variants:
         s = SearchOrCuda(A, B, Settings())
-        s.set_option("dp_form", form)
+        for k, v in opts.items():
+            s.set_option(k, v)
         og = OrientationGenerator(s)
         pick = og.orientations[np.arange(count) % og.size()]
         s.upload_orientations(pick)
@@ -25,7 +30,7 @@ for arg in sys.argv[1:]:
             keys_now = s.fetch_keys().copy()
             st = s.stats()
         keys.append(keys_now)
-        print("%dx%d x%d dp_form %d: dp %.2f ms = %.0f GCUPS, traceback %.2f ms" % (
-            m, nB, count, form, st["dp_kernel_ms"], cells * count / st["dp_kernel_ms"] / 1e6, st["tb_kernel_ms"]), flush=True)
+        print("%dx%d x%d %-10s: dp %.2f ms = %.0f GCUPS, traceback %.2f ms" % (
+            m, nB, count, label, st["dp_kernel_ms"], cells * count / st["dp_kernel_ms"] / 1e6, st["tb_kernel_ms"]), flush=True)
         s.close()
-    print("   keys identical:", np.array_equal(keys[0], keys[1]))
+    print("   keys identical:", all(np.array_equal(keys[0], k) for k in keys[1:]))
