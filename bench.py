@@ -465,7 +465,7 @@ def main():
     launches = max(stats["dp_kernel_launches"], 1)
     tb_bytes = 0.25 * stats["dp_cells"] / launches          # 2-bit traceback, algorithmic
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath) and w["cfg"] == 2:              # dram bytes from one ncu --set full capture
         tj = json.load(open(tpath))
         per_o = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["orientations_in_launch"]
@@ -478,14 +478,17 @@ def main():
                 "avg_launch_ms": dp_ms / launches,
                 "cells_per_launch": stats["dp_cells"] / launches,
                 "traffic": traffic,
+                "kernel_form": "k_dp_vp_* (single-pass problems): 1 FADD + 2 VIMNMX.U32 with predicate outputs + 2 predicated FADD per "
+                               "cell, cubin patched after ptxas (minrms_b200/sass_patch.py); multi-pass problems: ping-pong form "
+                               "(3 FADD + FMNMX3 + 2 SHF)",
                 "measured_ceilings": {
                     "unit": "GCUPS",
-                    "cell_update_all_lanes_live": 4700.0,
-                    "with_exchange_and_barrier": 3700.0,
-                    "def": "scratch/ubench/cell_ubench.cu on B200: the kernel's 6-instruction cell update (3 FADD, FMNMX3, 2 SHF) "
-                           "alone in registers, 12 warps/SM, every lane live; and with the per-column shared-memory exchange and "
-                           "CTA barrier.  The register file delivers 2 operands/clk/sub-partition (op_ubench.cu: FADD2 2 clk, "
-                           "FFMA2 3 clk) and a cell reads 13: profiles/README.md"},
+                    "alu_pipe_two_ops_per_cell": sms * 64 * f_mhz * 1e6 / 2 / 1e9,
+                    "issue_five_slots_per_cell": sms * 128 * f_mhz * 1e6 / 5 / 1e9,
+                    "def": "every ALU-pipe instruction (VIMNMX, FMNMX, SHF, LOP3, MOV, ISETP) issues at 2 clk per warp "
+                           "instruction per SM sub-partition, FADD at 1 (profiles/r02/sass_probe_vimnmx_predicates.log): the "
+                           "min-with-predicate cell (2 ALU-pipe ops, 5 issue slots) is bounded by the issue rate, the round-1 "
+                           "ping-pong cell (3 ALU-pipe ops, 6 slots) by the ALU pipe at 148 x 64 / 3 x f_SM"},
                 "hbm": {"bound": "hbm", "achieved": tb_bytes / (dp_ms / launches * 1e-3) / 1e9 if dp_ms else 0.0,
                         "peak": pk["hbm_gbs"], "unit": "GB/s", "peak_kind": pk_kind,
                         "algorithmic_bytes_per_launch": tb_bytes,
