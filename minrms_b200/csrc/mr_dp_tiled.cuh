@@ -99,11 +99,10 @@ struct TbTiled {
       }
       const int a = (jm & 1) * 16 + 2 * (rho & 7);
       const uint32_t bits = (word >> (30 - a)) & 3u;      // (s1 << 1) | s2
-      const uint32_t code = (0x0212u >> (4 * bits)) & 3u;  // 0 match, 1 skip-i, 2 skip-j
-      if (code == 0) emit(cn - 1, rho - pad, jm);
-      cn -= (code == 0);
-      rho -= (code != 2);
-      jm -= (code != 1);
+      // s2 = 0: skip-j;  s2 = 1: s1 ? match : skip-i  (decode() below spells the codes out)
+      if (bits == 3u) { emit(cn - 1, rho - pad, jm); cn--; }
+      rho -= (int)(bits & 1u);    // match or skip-i
+      jm -= (bits != 1u);         // match or skip-j
     }
   }
   __device__ __forceinline__ size_t addr(const int* __restrict__ tab, int n, int i, int j) const {
