@@ -158,25 +158,48 @@ def ref_bench(w, procs, per_proc, repeat):
 
 def ref_sample_size(w):
     """orientations per process and step for about a second of reference work per step"""
-    from minrms_b200.search import dp_cells_per_orientation
     m, nB = w["A"].shape[0], w["B"].shape[0]
     if w["cfg"] == 1:
         return 1100          # NW filter on all, DP on 15 %: the whole list in ~1 s on 16 cores
-    cells = dp_cells_per_orientation(m, nB, 1, min(m, nB))
+    cells = dp_cells_closed_form(m, nB, 1, min(m, nB))
     return max(1, int(CPU_CELLS_PER_S_PER_CORE / cells))
 
 
-def common_config(w, args, per_step):
-    """the keys both arms print (the driver compares the two `config` objects)"""
-    return {"workload": w["name"], "config": w["cfg"], "scaling": args.scaling,
-            "orientations_in_list": per_step}
+def dp_cells_closed_form(m, nB, n_min, n_max):
+    """DP cells of one orientation: layer n covers rows n..min(m, n + wA - 1) and
+    columns n..min(nB, n + wB - 1) with wA = m - n_min + 1, wB = nB - n_min + 1.  Plain Python, so that
+    the reference arm does not load the CUDA library for it."""
+    wA, wB = m - n_min + 1, nB - n_min + 1
+    return sum((min(m, n + wA - 1) - n + 1) * (min(nB, n + wB - 1) - n + 1) for n in range(1, n_max + 1))
+
+
+def common_config(w, args, count):
+    """the `config` object: both arms print exactly this (the driver compares them); everything
+    in it follows from the workload and the launch, nothing from what a run measured"""
+    m, nB = w["A"].shape[0], w["B"].shape[0]
+    st = w["settings"]
+    n_min = int(getattr(st, "n_min", 1) or 1)
+    n_max = min(m, nB)
+    cells = dp_cells_closed_form(m, nB, n_min, n_max)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    strong = args.scaling == "strong" and world > 1
+    per_gpu = (count + world - 1) // world if strong else count
+    return {"workload": w["name"], "config": w["cfg"], "scaling": args.scaling if world > 1 else "weak",
+            "orientations_in_list": int(count), "orientations_per_gpu_per_step": int(per_gpu),
+            "dp_cells_per_orientation": cells, "alignment_sizes": int(n_max - max(2, n_min) + 1),
+            "l2": "no explicit flush: the traceback tables of a step (0.25 B per DP cell of every orientation that reaches "
+                  "the DP, up to %.1f GB per GPU for this list) are written and re-read, >> 126 MB L2" % (0.25 * cells * per_gpu / 1e9),
+            "parallelism": ("one list partitioned over %d ranks (contiguous ranges, global ids)" % world if strong else
+                            "%d rank(s), each its own copy of the list under its own ids" % world) +
+                           "; per step: NCCL all_reduce(MIN) of the 64-bit per-size keys in device memory (reduction_ms); "
+                           "the winners' payload from the owning ranks + one all_gather once per search "
+                           "(payload_ms_once_per_search; inside every step of e2e)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from minrms_b200.search import dp_cells_per_orientation
     w = workload(args.config)
     m, nB = w["A"].shape[0], w["B"].shape[0]
     cores = os.cpu_count() or 1
@@ -196,14 +219,15 @@ def run_reference(args):
     n = sum(r[0] for r in res)
     t = sum(r[1] for r in res)
     v = n / t
-    cells = dp_cells_per_orientation(m, nB, w["settings"].n_min, min(m, nB))
+    cells = dp_cells_closed_form(m, nB, w["settings"].n_min, min(m, nB))
+    count = min(total, args.orientations) if args.orientations > 0 else total
     sample = ("%d orientations/step (%d per process x %d processes) of the %d, Search(og,start,stop) of the unmodified "
               "reference, shipped flags -O3 -ffast-math" % (res[0][0], res[0][0] // cores, cores, total))
     line = {"metric": "orientations_per_sec", "value": v, "unit": "orientations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(res),
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": w["data"], "impl": "reference", "dp_gcups": v * cells / 1e9,
-            "config": common_config(w, args, total),
+            "config": common_config(w, args, count),
             "cpu_baseline": {"value": v, "unit": "orientations/s", "cores": cores, "kind": "reference",
                              "sample": sample},
             "e2e": {"value": v, "unit": "orientations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -498,15 +522,7 @@ def main():
                                   "nw_filter": stats["nw_kernel_ms"] / (dev_s * 1e3) if dev_s else None}}
 
     cfgd = common_config(w, args, count)
-    cfgd.update({"orientations_per_gpu_per_step": mine, "dp_cells_per_orientation": int(cells_per),
-                 "alignment_sizes": int(s.n_max - max(2, s.n_min) + 1),
-                 "l2": "no explicit flush: each step writes and re-reads >= %.1f GB of traceback tables per GPU (>> 126 MB L2)" % (
-                     0.25 * cells_per * stats["orientations_dp"] / max(args.steps, 1) / 1e9),
-                 "parallelism": ("one list partitioned over %d ranks (contiguous ranges, global ids)" % world if strong else
-                                 "%d rank(s), each its own copy of the list under its own ids" % world) +
-                                "; per step: NCCL all_reduce(MIN) of the 64-bit per-size keys in device memory (reduction_ms); "
-                                "the winners' payload from the owning ranks + one all_gather once per search "
-                                "(payload_ms_once_per_search; inside every step of e2e)"})
+    assert cfgd["dp_cells_per_orientation"] == int(cells_per), (cfgd["dp_cells_per_orientation"], cells_per)
     line = {"metric": "orientations_per_sec", "value": value, "unit": "orientations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
             "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
