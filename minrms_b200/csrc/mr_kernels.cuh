@@ -367,6 +367,30 @@ k_nw_filter_cta(MrDevParams P, const float* __restrict__ A, const float* __restr
 //   (best + G is formed once per cell for both of its uses.)
 // Same thread mapping as k_nw_filter_warp / k_nw_filter_cta.
 // ---------------------------------------------------------------------------
+// one row of a lane's CPL columns.  BAND: with the per-cell band test (cells outside the band take
+// the border value (i + j) G); without it when every lane of the warp sits fully inside the band
+// at its row (a warp-uniform decision: __all_sync in the callers) -- half the instructions.
+template <int CPL, bool BAND>
+__device__ __forceinline__ float mr_nw_cost_row(float (&up)[CPL], float (&upg)[CPL], const float (&bx)[CPL],
+                                                const float (&by)[CPL], const float (&bz)[CPL], float ax, float ay, float az,
+                                                float left, float diag, float G, float cutoff, int i, int j0, int jlo, int jhi) {
+  float leftg = left + G;
+#pragma unroll
+  for (int c = 0; c < CPL; c++) {
+    const int j = j0 + 1 + c;
+    float cc = mr_d2(ax, ay, az, bx[c], by[c], bz[c]);
+    if (cc > cutoff) cc = MR_UB;
+    float best = fminf(fminf(upg[c], leftg), diag + cc);
+    if (BAND && (j < jlo || j > jhi)) best = (float)(i + j) * G;
+    diag = up[c];
+    up[c] = best;
+    leftg = best + G;
+    upg[c] = leftg;
+    left = best;
+  }
+  return left;
+}
+
 template <int CPL>
 __global__ void __launch_bounds__(128)
 k_nw_cost_warp(MrDevParams P, float thr, const float* __restrict__ A, const float* __restrict__ B,
@@ -398,28 +422,18 @@ k_nw_cost_warp(MrDevParams P, float thr, const float* __restrict__ A, const floa
     float left = __shfl_up_sync(0xffffffffu, last, 1);
     const int i = t - lane;
     if (lane == 0) left = (float)i * G;  // column 0
-    if (i >= 1 && i <= m) {
-      const int jlo = (i <= w0) ? 1 : i - w0 + 1;
-      const int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
+    const bool live = i >= 1 && i <= m;
+    const int jlo = (i <= w0) ? 1 : i - w0 + 1;
+    const int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
+    // fully inside the band (columns beyond nB do not count: nothing in the band ever reads them)
+    const bool inside = (j0 + 1 >= jlo) && (min(j0 + CPL, nB) <= jhi);
+    const bool no_edge = __all_sync(0xffffffffu, !live || inside || j0 + 1 > nB);
+    if (live) {
       const float ax = nw_sA[3 * (i - 1)], ay = nw_sA[3 * (i - 1) + 1], az = nw_sA[3 * (i - 1) + 2];
-      float diag = diag_in;
+      const float diag = diag_in;
       diag_in = left;  // A[i][j0] is the diagonal input of my first column at the next row
-      float leftg = left + G;
-      const bool inside = (j0 + 1 >= jlo) && (j0 + CPL <= jhi);
-#pragma unroll
-      for (int c = 0; c < CPL; c++) {
-        const int j = j0 + 1 + c;
-        float cc = mr_d2(ax, ay, az, bx[c], by[c], bz[c]);
-        if (cc > cutoff) cc = MR_UB;
-        float best = fminf(fminf(upg[c], leftg), diag + cc);
-        if (!inside && (j < jlo || j > jhi)) best = (float)(i + j) * G;
-        diag = up[c];
-        up[c] = best;
-        leftg = best + G;
-        upg[c] = leftg;
-        left = best;
-      }
-      last = left;
+      if (no_edge) last = mr_nw_cost_row<CPL, false>(up, upg, bx, by, bz, ax, ay, az, left, diag, G, cutoff, i, j0, jlo, jhi);
+      else last = mr_nw_cost_row<CPL, true>(up, upg, bx, by, bz, ax, ay, az, left, diag, G, cutoff, i, j0, jlo, jhi);
     }
   }
   // the lane that owns column nB holds A(m, nB): its row-m value of that column
@@ -472,28 +486,16 @@ k_nw_cost_cta(MrDevParams P, float thr, const float* __restrict__ A, const float
             if (warp == 0) left = (float)i * G;  // column 0
             else if (live) left = ring[(warp - 1) * 128 + (i & 127)];
           }
+          const int jlo = (i <= w0) ? 1 : i - w0 + 1;
+          const int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
+          const bool inside = (j0 + 1 >= jlo) && (min(j0 + CPL, nB) <= jhi);
+          const bool no_edge = __all_sync(0xffffffffu, !live || inside || j0 + 1 > nB);
           if (live) {
-            const int jlo = (i <= w0) ? 1 : i - w0 + 1;
-            const int jhi = (i + w1 <= nB) ? i + w1 - 1 : nB;
             const float ax = nw_sA[3 * (i - 1)], ay = nw_sA[3 * (i - 1) + 1], az = nw_sA[3 * (i - 1) + 2];
-            float diag = diag_in;
+            const float diag = diag_in;
             diag_in = left;
-            float leftg = left + G;
-            const bool inside = (j0 + 1 >= jlo) && (j0 + CPL <= jhi);
-#pragma unroll
-            for (int c = 0; c < CPL; c++) {
-              const int j = j0 + 1 + c;
-              float cc = mr_d2(ax, ay, az, bx[c], by[c], bz[c]);
-              if (cc > cutoff) cc = MR_UB;
-              float best = fminf(fminf(upg[c], leftg), diag + cc);
-              if (!inside && (j < jlo || j > jhi)) best = (float)(i + j) * G;
-              diag = up[c];
-              up[c] = best;
-              leftg = best + G;
-              upg[c] = leftg;
-              left = best;
-            }
-            last = left;
+            if (no_edge) last = mr_nw_cost_row<CPL, false>(up, upg, bx, by, bz, ax, ay, az, left, diag, G, cutoff, i, j0, jlo, jhi);
+            else last = mr_nw_cost_row<CPL, true>(up, upg, bx, by, bz, ax, ay, az, left, diag, G, cutoff, i, j0, jlo, jhi);
             if (lane == 31 && warp + 1 < nwarps) ring[warp * 128 + (i & 127)] = last;
           }
         }
