@@ -273,15 +273,18 @@ static std::mutex g_arena_mu;
 constexpr int kArenaSlots = 4;  // per device: contexts of concurrent host threads (all-vs-all workers) each park one
 static Arena g_arena_cache[64][kArenaSlots];
 
+static const bool g_arena_dbg = getenv("MR_DEBUG_PLAN") != nullptr;
+#define MR_ARENA_DBG(...) do { if (g_arena_dbg) fprintf(stderr, __VA_ARGS__); } while (0)
 static void arena_release(mr_ctx* c) {  // stream must be idle
   if (!c->arena.base) return;
+  MR_ARENA_DBG("[mr] arena_release: %zu MB\n", c->arena.size >> 20);
   std::lock_guard<std::mutex> lk(g_arena_mu);
   Arena* slots = g_arena_cache[c->device & 63];
   Arena* smallest = &slots[0];
   for (int k = 1; k < kArenaSlots; k++)
     if (slots[k].size < smallest->size) smallest = &slots[k];
   if (smallest->size < c->arena.size) std::swap(*smallest, c->arena);
-  if (c->arena.base) cudaFree(c->arena.base);
+  if (c->arena.base) { MR_ARENA_DBG("[mr] arena_release: cudaFree %zu MB\n", c->arena.size >> 20); cudaFree(c->arena.base); }
   c->arena = Arena();
 }
 static size_t arena_cached_bytes(const mr_ctx* c) {
@@ -302,6 +305,7 @@ static int arena_reserve(mr_ctx* c, size_t bytes) {
       if (slots[k].size >= bytes && (!fit || slots[k].size < fit->size)) fit = &slots[k];
     if (fit) {
       std::swap(*fit, c->arena);  // ours (smaller or none) is parked instead
+      MR_ARENA_DBG("[mr] arena_reserve %zu MB: took a parked arena of %zu MB%s\n", bytes >> 20, c->arena.size >> 20, fit->base ? ", cudaFree of ours" : "");
       if (fit->base) { cudaFree(fit->base); *fit = Arena(); }
       return 0;
     }
@@ -312,6 +316,7 @@ static int arena_reserve(mr_ctx* c, size_t bytes) {
   if (c->arena.base) cudaFree(c->arena.base);
   c->arena = Arena();
   bytes = (bytes + ((size_t)256 << 20) - 1) & ~(((size_t)256 << 20) - 1);
+  MR_ARENA_DBG("[mr] arena_reserve: cudaMalloc %zu MB\n", bytes >> 20);
   if (cudaMalloc(&c->arena.base, bytes) != cudaSuccess) {
     cudaGetLastError();
     MR_FAIL(c, "out of device memory: %zu MB of chunk work space", bytes >> 20);

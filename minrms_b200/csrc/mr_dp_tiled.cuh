@@ -144,12 +144,6 @@ struct MrTiledPlan {
   int* d_tile_of = nullptr;
 };
 
-#ifndef MR_VP_PAIRED
-#define MR_VP_PAIRED 0   // 1: the min-with-predicate kernel steps in pairs (two copies of the step, measured slower: ptxas rotates the state between the copies)
-#endif
-#ifndef MR_VP_PUBLISH32
-#define MR_VP_PUBLISH32 0  // 1: twelve 4-byte stores instead of three 16-byte ones (measured: 4-way bank conflicts on the 48-byte slot stride)
-#endif
 #define MR_CRING 32  // columns in the C ring (>= strips + MR_CBATCH)
 #define MR_CBATCH 8  // columns of C produced at a time
 __host__ __device__ inline int mr_ring_stride(int WR) { return WR + ((36 - (WR & 31)) & 31); }
@@ -332,12 +326,8 @@ mr_dp_tiles_body(const MrDevParams& P, const TbTiled& L, int nslots, int nsteps,
         else if constexpr (VP) mr_tile_update_vp(st[0], bprev[0], bin, acc, cv, dsh);
         else mr_tile_update_ip(st[0], bprev[0], bin, acc, cv, dsh);
       }
-      if constexpr (VP && MR_VP_PUBLISH32)
-        mr_tile_publish32(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
-                          st[D][3][R - 1]);
-      else
-        mr_tile_publish(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
-                        st[D][3][R - 1]);
+      mr_tile_publish(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
+                      st[D][3][R - 1]);
       // traceback: the K words of this tile every second column (j = s - w even)
       if (!COSTS && s == tb_next) {
         MR_ASSERT(tbp >= reinterpret_cast<uint4*>(tb + (size_t)sv * L.words(nB)) &&
@@ -362,9 +352,8 @@ mr_dp_tiles_body(const MrDevParams& P, const TbTiled& L, int nslots, int nsteps,
     };
     // parity of the exchange set written at step s: s & 1
     const uint32_t off_a = (s & 1) ? 0u : par_bytes, off_b = par_bytes - off_a;
-    if constexpr (PP || (VP && MR_VP_PAIRED)) {
-      // the plan makes every warp window an even number of steps (VP: two copies of the step let
-      // ptxas alternate the registers of the loop-carried boundary values instead of copying them)
+    if constexpr (PP) {
+      // the plan makes every warp window an even number of steps
       for (; s < warp_hi; s += 2) {
         step(std::integral_constant<int, 0>(), s, off_a, off_b);
         step(std::integral_constant<int, 1>(), s + 1, off_b, off_a);
@@ -497,7 +486,7 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   p->ctas_per_sm = std::max(1, std::min(by_smem, want));
   p->grid_cap = prop.multiProcessorCount * p->ctas_per_sm;
   p->grid_cap_costs = prop.multiProcessorCount * std::max(1, std::min(by_smem, mr_dp_tiles_minb_costs(threads)));
-  p->vp_bucket = (!MR_VP_PAIRED || pp) ? mr_dp_vp_bucket(threads) : 0;
+  p->vp_bucket = mr_dp_vp_bucket(threads);
   p->grid_cap_vp = prop.multiProcessorCount * std::max(1, std::min(by_smem, mr_dp_vp_minb(p->vp_bucket)));
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
   p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = threads;

@@ -229,24 +229,6 @@ __device__ __forceinline__ void mr_tile_publish(uint32_t a_wr, float btop, const
   mr_sts128(a_wr + 32u, b0, b1, b2, b3);
 }
 
-// the same 48 bytes as twelve 4-byte stores: for the in-place forms, whose state registers stay
-// where they are from step to step and are not allocated as aligned quads (ptxas then copies
-// twelve values per step into a quad for the 16-byte stores; the shared-memory wavefronts are the
-// same either way: a 16-byte store of a warp takes four)
-__device__ __forceinline__ void mr_sts32(uint32_t a, float x) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
-}
-__device__ __forceinline__ void mr_tile_publish32(uint32_t a_wr, float btop, const float (&top)[MR_TR], float b0, float b1,
-                                                  float b2, float b3) {
-  mr_sts32(a_wr, btop);
-#pragma unroll
-  for (int r = 0; r < MR_TR - 1; r++) mr_sts32(a_wr + 4u + 4u * r, top[r]);
-  mr_sts32(a_wr + 32u, b0);
-  mr_sts32(a_wr + 36u, b1);
-  mr_sts32(a_wr + 40u, b2);
-  mr_sts32(a_wr + 44u, b3);
-}
-
 // n < n_min: the reference reports the corner of the layer's window, A(n, n+wA-1, n+wB-1)
 // (dyn3d.cc:385, dyn3d.h:407-408): one layer per column.  j = column of this step.
 __device__ __forceinline__ void mr_tile_window_cost(const MrDevParams& P, const float (&st)[MR_TK][MR_TR], int j, int w, int c,
