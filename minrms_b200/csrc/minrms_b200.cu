@@ -108,7 +108,7 @@ struct mr_ctx {
   float nw_cost_thr = 0.0f;     // pass <=> A(m, nB) <= thr
   double nw_cost_margin = 0.0;
   int64_t opt_nw_cost = 1;      // 0: FirstPass filters with the counting kernels
-  int64_t opt_dp_form = 0;      // 0: min-with-predicate kernels for single-pass problems, 1: two-min / ping-pong forms only, 2: min-with-predicate also for multi-pass problems
+  int64_t opt_dp_form = 0;      // 0: min-with-predicate kernels where a CTA bucket exists (single-pass problems), 1: two-min / ping-pong forms only
   int64_t opt_dp_only = 0;      // experiments: skip traceback/select (results invalid)
   int64_t opt_costs_only_off = 0;  // tests / measurements: -IR FirstPass through the full kernel
   mr_stats st;
@@ -118,9 +118,6 @@ struct mr_ctx {
   std::string err;
   MrTiledPlan tiled;
   MrTiledMpPlan tiled_mp;
-  MrTiledMpPlan tiled_mp_vp;               // plan of the min-with-predicate multi-pass kernels (384 or 320 threads x 2 CTAs per SM)
-  const TbTiled* cur_mp_layout = nullptr;  // layout of the multi-pass plan that wrote the traceback table of the current chunk
-  int64_t opt_mp_vp_threads = 384;
   int64_t opt_mp_threads = 0;   // tests: threads per CTA of the multi-pass kernel (forces more passes)
   cudaEvent_t user_ev[16] = {};
 };
@@ -239,31 +236,8 @@ int dp_path(const mr_ctx* c) {
   return c->tiled_mp.ok ? 2 : (c->tiled.ok ? 1 : 0);
 }
 bool use_tiled(const mr_ctx* c) { return dp_path(c) != 0; }
-const TbTiled& tiled_layout(const mr_ctx* c) {
-  if (dp_path(c) != 2) return c->tiled.layout;
-  return c->cur_mp_layout ? *c->cur_mp_layout : c->tiled_mp.layout;
-}
-// multi-pass plans: the 512-thread ping-pong plan (also the split mode of Refine batches) and, when
-// the library carries the patched cubin, the plan of the min-with-predicate kernels
-void plan_mp(mr_ctx* c, int max_threads = 0) {
-  mr_plan_dp_tiled_mp(&c->tiled_mp, c->P, c->prop, c->NP, max_threads);
-  mr_free_dp_tiled_mp(&c->tiled_mp_vp);
-  c->tiled_mp_vp.ok = false;
-  c->cur_mp_layout = nullptr;
-#if MR_HAVE_VP_CUBIN
-  if (c->tiled_mp.ok && max_threads == 0 && c->opt_dp_form == 2) {
-    mr_plan_dp_tiled_mp(&c->tiled_mp_vp, c->P, c->prop, c->NP, (int)c->opt_mp_vp_threads);
-    if (c->tiled_mp_vp.ok && c->tiled_mp_vp.threads != (int)c->opt_mp_vp_threads) {  // a row strip wider than the CTA
-      mr_free_dp_tiled_mp(&c->tiled_mp_vp);
-      c->tiled_mp_vp.ok = false;
-    }
-  }
-#endif
-}
-// (measured slower than the 512-thread ping-pong kernel: at 80 registers the multi-pass step -- carry
-// prefetch, carry store, pass bookkeeping on top of the tile -- spills inside the column loop, 5
-// local loads per warp-step: 0.9 against 2.1 TCUPS at 300 x 300; kept behind dp_form = 2)
-bool mp_vp_in_use(const mr_ctx* c) { return c->tiled_mp_vp.ok && c->opt_dp_form == 2; }
+const TbTiled& tiled_layout(const mr_ctx* c) { return dp_path(c) == 2 ? c->tiled_mp.layout : c->tiled.layout; }
+static void plan_mp(mr_ctx* c, int max_threads = 0) { mr_plan_dp_tiled_mp(&c->tiled_mp, c->P, c->prop, c->NP, max_threads); }
 
 // The per-chunk work space (tens of GB; ~100 GB for long chains) is ONE device allocation, the
 // arena, carved up by ensure_chunk.  A destroyed context parks its arena in a per-device cache
@@ -329,8 +303,7 @@ static int arena_reserve(mr_ctx* c, size_t bytes) {
 int ensure_chunk(mr_ctx* c, int64_t want) {
   const size_t words_c = c->Lc.words(c->nB);
   const int path = dp_path(c);
-  const size_t words = path == 2 ? std::max(c->tiled_mp.tb_words, mp_vp_in_use(c) ? c->tiled_mp_vp.tb_words : (size_t)0)
-                                 : path == 1 ? c->tiled.tb_words : words_c;
+  const size_t words = path == 2 ? c->tiled_mp.tb_words : path == 1 ? c->tiled.tb_words : words_c;
   const size_t per_thread_scr = (size_t)c->N * sizeof(short2);
   const int per = std::max(1, c->hp.n_max - std::max(2, c->hp.n_min) + 1);
   // bytes per orientation in a chunk
@@ -413,15 +386,7 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count, bool latency = 
     if (mr_launch_dp_tiled(c->tiled, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
                            c->d_tb, c->d_cost, count, c->stream, costs_only) != 0)
       MR_FAIL(c, "tiled DP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-  } else if (path == 2 && !costs_only && mp_vp_in_use(c) &&
-             !(latency && c->opt_refine_split && count <= c->tiled_mp.split_cap)) {
-    std::string why;
-    c->cur_mp_layout = &c->tiled_mp_vp.layout;
-    if (mr_launch_dp_tiles_mp_vp(c->tiled_mp_vp, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb,
-                                 c->d_cost, count, c->stream, c->device, &why) != 0)
-      MR_FAIL(c, "multi-pass tiled DP launch (min-with-predicate kernel) failed: %s", why.c_str());
   } else if (path == 2) {
-    c->cur_mp_layout = &c->tiled_mp.layout;
     if (mr_launch_dp_tiled_mp(c->tiled_mp, c->P, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count,
                               c->d_tb, c->d_cost, count, c->stream,
                               latency && c->opt_refine_split && count <= c->tiled_mp.split_cap, costs_only) != 0)
@@ -909,7 +874,6 @@ void mr_destroy(mr_ctx* c) {
   if (c->h_ref) cudaFreeHost(c->h_ref);
   mr_free_dp_tiled(&c->tiled);
   mr_free_dp_tiled_mp(&c->tiled_mp);
-  mr_free_dp_tiled_mp(&c->tiled_mp_vp);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -927,13 +891,8 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "budget_mb")) { c->opt_budget_mb = std::max<int64_t>(64, value); c->budget_is_default = false; }
   else if (!strcmp(name, "chunk")) c->opt_chunk = value;
   else if (!strcmp(name, "dp_form")) {
-    if (value < 0 || value > 2) MR_FAIL(c, "mr_set_option: dp_form is 0, 1 or 2");
+    if (value < 0 || value > 1) MR_FAIL(c, "mr_set_option: dp_form is 0 or 1");
     c->opt_dp_form = value;
-    if (c->tiled_mp.ok && value == 2 && !c->tiled_mp_vp.ok) {
-      if (cudaSetDevice(c->device) != cudaSuccess) MR_FAIL(c, "cudaSetDevice failed");
-      cudaStreamSynchronize(c->stream);
-      plan_mp(c, (int)c->opt_mp_threads);
-    }
   }
   else if (!strcmp(name, "exp_dp_only")) c->opt_dp_only = value;
   else if (!strcmp(name, "ir_costs_only")) c->opt_costs_only_off = value == 0;
@@ -948,13 +907,6 @@ int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
     if (cudaSetDevice(c->device) != cudaSuccess) MR_FAIL(c, "cudaSetDevice failed");
     cudaStreamSynchronize(c->stream);
     if (c->tiled_mp.ok || c->opt_dp_kernel == 3) plan_mp(c, (int)c->opt_mp_threads);
-  }
-  else if (!strcmp(name, "mp_vp_threads")) {
-    if (value != 320 && value != 384) MR_FAIL(c, "mr_set_option: mp_vp_threads is 320 or 384");
-    c->opt_mp_vp_threads = value;
-    if (cudaSetDevice(c->device) != cudaSuccess) MR_FAIL(c, "cudaSetDevice failed");
-    cudaStreamSynchronize(c->stream);
-    if (c->tiled_mp.ok) plan_mp(c, (int)c->opt_mp_threads);
   }
   else MR_FAIL(c, "mr_set_option: unknown option %s", name);
   if (c->opt_dp_kernel == 2 && !c->tiled.ok) MR_FAIL(c, "tiled DP kernel not available for this problem: %s", c->tiled.why);

@@ -67,15 +67,16 @@ struct MrTileMp {
   int pad_;
 };
 
-// the kernel body (a device function: mr_dp_vp.cu instantiates its min-with-predicate form, VP,
-// under extern "C" names, see mr_dp_tiled.cuh)
-template <int K, int R, bool NB1, bool WINDOWED, bool PP, bool SPLIT, bool COSTS, bool VP>
-__device__ __forceinline__ void
-mr_dp_tiles_mp_body(const MrDevParams& P, const TbTiled& L, int nslots, int npasses, int wl_max, const MrPass* __restrict__ passes,
-                    const MrTileMp* __restrict__ tiles, const float* __restrict__ A, const float* __restrict__ B,
-                    const float* __restrict__ orient, const int* __restrict__ surv,
-                    const int* __restrict__ surv_count, float4* carry_all, size_t carry_pitch,
-                    uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
+// (The min-with-predicate tile update of the single-pass kernel was tried here at 384 x 2 and
+// 320 x 2 CTAs per SM and lost against 512 x 1 ping-pong: more, thinner passes, and spills in the
+// column loop at 80 registers -- 0.9-1.4 against 2.0 TCUPS, profiles/README.md.)
+template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP, bool SPLIT = false, bool COSTS = false>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, const MrPass* __restrict__ passes,
+              const MrTileMp* __restrict__ tiles, const float* __restrict__ A, const float* __restrict__ B,
+              const float* __restrict__ orient, const int* __restrict__ surv,
+              const int* __restrict__ surv_count, float4* carry_all, size_t carry_pitch,
+              uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
   static_assert(R == MR_TR && K == MR_TK, "traceback word packing assumes 4 x 8 tiles");
   extern __shared__ float4 smem4[];
   const int m = P.m, nB = P.nB, nb = P.nb;
@@ -165,7 +166,7 @@ mr_dp_tiles_mp_body(const MrDevParams& P, const TbTiled& L, int nslots, int npas
       // tile state and step: as in k_dp_tiles (mr_tile_step.cuh); the upper boundary of a pass's
       // first strip comes from the carry buffer (fetched one column ahead into a register), and
       // the bottom row of its last strip goes there
-      static_assert(!(COSTS && PP) && !(VP && (PP || COSTS || SPLIT)), "the costs-only and min-with-predicate updates are in place");
+      static_assert(!(COSTS && PP), "the costs-only update is in place");
       constexpr int NC = PP ? 2 : 1;
       float st[NC][K][R], bprev[NC][K];
       uint32_t acc[K];
@@ -208,7 +209,6 @@ mr_dp_tiles_mp_body(const MrDevParams& P, const TbTiled& L, int nslots, int npas
         } else {
           const float bin[K] = {ub.x, ub.y, ub.z, ub.w};
           if constexpr (COSTS) mr_tile_update_costs(st[0], bprev[0], bin, cv, dsh);
-          else if constexpr (VP) mr_tile_update_vp(st[0], bprev[0], bin, acc, cv, dsh);
           else mr_tile_update_ip(st[0], bprev[0], bin, acc, cv, dsh);
         }
         mr_tile_publish(a_me + wr_off, bprev[D][K - 1], st[D][K - 1], st[D][0][R - 1], st[D][1][R - 1], st[D][2][R - 1],
@@ -262,18 +262,6 @@ mr_dp_tiles_mp_body(const MrDevParams& P, const TbTiled& L, int nslots, int npas
     }
   }
 #undef MR_MP_SYNC
-}
-
-#ifndef MR_DP_TILED_DEVICE_ONLY
-template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP, bool SPLIT = false, bool COSTS = false>
-__global__ void __launch_bounds__(MAXT, MINB)
-k_dp_tiles_mp(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, const MrPass* __restrict__ passes,
-              const MrTileMp* __restrict__ tiles, const float* __restrict__ A, const float* __restrict__ B,
-              const float* __restrict__ orient, const int* __restrict__ surv,
-              const int* __restrict__ surv_count, float4* carry_all, size_t carry_pitch,
-              uint32_t* __restrict__ tb, float* __restrict__ cost_out) {
-  mr_dp_tiles_mp_body<K, R, NB1, WINDOWED, PP, SPLIT, COSTS, false>(P, L, nslots, npasses, wl_max, passes, tiles, A, B, orient,
-                                                                    surv, surv_count, carry_all, carry_pitch, tb, cost_out);
 }
 
 // ---------------------------------------------------------------------------------- host
@@ -548,30 +536,6 @@ static inline int mr_launch_dp_tiles_mp_t(const MrTiledMpPlan& p, const MrDevPar
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-// min-with-predicate form of the multi-pass kernel (k_dp_vp_mp_384_*, mr_dp_vp.cu): a plan made
-// with max_threads = MR_VP_MP_THREADS (two CTAs per SM).  0 launched, 1 failed (*why says what)
-#define MR_VP_MP_THREADS 384
-static inline int mr_launch_dp_tiles_mp_vp(const MrTiledMpPlan& p, const MrDevParams& P, const float* A, const float* B,
-                                           const float* orient, const int* surv, const int* surv_count, uint32_t* tb,
-                                           float* cost, int count, cudaStream_t stream, int device, std::string* why) {
-  char name[64];
-  snprintf(name, sizeof name, "k_dp_vp_mp_%d_%s%s", p.threads, P.nb == 1 ? "c" : "g", P.n_min > 1 ? "w" : "");
-  CUfunction f = mr_vp_function(device, name, p.smem, why);
-  if (!f) return 1;
-  MrDevParams Pv = P;
-  TbTiled Lv = p.layout;
-  int nslots = p.nslots, npasses = p.npasses, wl_max = p.wl_max;
-  const MrPass* passes = p.d_passes;
-  const MrTileMp* tiles = p.d_tiles;
-  float4* carry = p.d_carry;
-  size_t pitch = p.carry_pitch;
-  void* args[] = {&Pv, &Lv, &nslots, &npasses, &wl_max, &passes, &tiles, &A, &B, &orient, &surv, &surv_count, &carry, &pitch, &tb, &cost};
-  const int grid = std::min(count, p.grid_cap);
-  const CUresult r = mr_vp_driver().LaunchKernel(f, grid, 1, 1, p.threads, 1, 1, (unsigned)p.smem, (CUstream)stream, args, nullptr);
-  if (r != CUDA_SUCCESS) { *why = std::string("cuLaunchKernel(") + name + "): " + mr_vp_errstr(r); return 1; }
-  return 0;
-}
-
 static inline int mr_launch_dp_tiled_mp(const MrTiledMpPlan& p, const MrDevParams& P, const float* A,
                                         const float* B, const float* orient, const int* surv,
                                         const int* surv_count, uint32_t* tb, float* cost, int count,
@@ -584,4 +548,3 @@ static inline int mr_launch_dp_tiled_mp(const MrTiledMpPlan& p, const MrDevParam
 #undef MR_TRY
   return mr_launch_dp_tiles_mp_t<1024, 1, false>(p, P, A, B, orient, surv, surv_count, tb, cost, count, stream, false, costs_only);
 }
-#endif  // MR_DP_TILED_DEVICE_ONLY

@@ -4,7 +4,7 @@
 // predicate destinations stay) and embedded in the library, which loads it through the driver
 // API (mr_vp_module.h).  Nothing in here is ever launched unpatched.
 #define MR_DP_TILED_DEVICE_ONLY
-#include "mr_dp_tiled_mp.cuh"
+#include "mr_dp_tiled.cuh"
 
 // launch bounds: registers are allocated per warp in units of 512, so two CTAs of 352 threads
 // (11 warps) get 80 registers per thread (88 measured: one CTA per SM)
@@ -31,22 +31,3 @@ MR_VP_BUCKET(320, 2)
 MR_VP_BUCKET(352, 2)
 MR_VP_BUCKET(384, 2)
 
-// multi-pass form (chains beyond one CTA), 384 threads x 2 CTAs per SM
-#define MR_VP_MP_KERNEL(NAME, MAXT, MINB, NB1, WINDOWED)                                                                     \
-  extern "C" __global__ void MR_VP_ATTR(MAXT, MINB)                                                                          \
-  NAME(MrDevParams P, TbTiled L, int nslots, int npasses, int wl_max, const MrPass* __restrict__ passes,                     \
-       const MrTileMp* __restrict__ tiles, const float* __restrict__ A, const float* __restrict__ B,                         \
-       const float* __restrict__ orient, const int* __restrict__ surv, const int* __restrict__ surv_count,                   \
-       float4* carry_all, size_t carry_pitch, uint32_t* __restrict__ tb, float* __restrict__ cost_out) {                     \
-    mr_dp_tiles_mp_body<4, 8, NB1, WINDOWED, false, false, false, true>(P, L, nslots, npasses, wl_max, passes, tiles, A, B,  \
-                                                                        orient, surv, surv_count, carry_all, carry_pitch,    \
-                                                                        tb, cost_out);                                       \
-  }
-MR_VP_MP_KERNEL(k_dp_vp_mp_384_g, 384, 2, false, false)
-MR_VP_MP_KERNEL(k_dp_vp_mp_384_gw, 384, 2, false, true)
-MR_VP_MP_KERNEL(k_dp_vp_mp_384_c, 384, 2, true, false)
-MR_VP_MP_KERNEL(k_dp_vp_mp_384_cw, 384, 2, true, true)
-MR_VP_MP_KERNEL(k_dp_vp_mp_320_g, 320, 2, false, false)
-MR_VP_MP_KERNEL(k_dp_vp_mp_320_gw, 320, 2, false, true)
-MR_VP_MP_KERNEL(k_dp_vp_mp_320_c, 320, 2, true, false)
-MR_VP_MP_KERNEL(k_dp_vp_mp_320_cw, 320, 2, true, true)

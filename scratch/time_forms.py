@@ -7,18 +7,17 @@ sys.path.insert(0, ROOT)
 from minrms_b200 import OrientationGenerator, SearchOrCuda, Settings
 from minrms_b200.search import dp_cells_per_orientation
 from minrms_b200.synth import random_chain, related_chain
+NMIN = int(os.environ.get("NMIN", "1"))   # > 1: the windowed kernel variants
 for arg in sys.argv[1:]:
     m, nB = (int(x) for x in arg.split("x")) if "x" in arg else (int(arg), int(arg))
     rng = np.random.default_rng(7 * m + nB)
     A = random_chain(rng, m); B = related_chain(rng, A, nB)
-    cells = dp_cells_per_orientation(m, nB, 1, min(m, nB))
+    cells = dp_cells_per_orientation(m, nB, NMIN, min(m, nB))
     count = int(min(60000, max(592, 2.0e10 / cells)))
     variants = [("vp", {"dp_form": 0}), ("legacy", {"dp_form": 1})]
-    if min(m, nB) > 190:
-        variants = [("vp mp 384", {"dp_form": 2}), ("vp mp 320", {"dp_form": 2, "mp_vp_threads": 320}), ("legacy", {"dp_form": 1})]
     keys = []
     for label, opts in variants:
-        s = SearchOrCuda(A, B, Settings())
+        s = SearchOrCuda(A, B, Settings(n_min=NMIN))
         for k, v in opts.items():
             s.set_option(k, v)
         og = OrientationGenerator(s)

@@ -24,12 +24,6 @@ def make_search(A, B, settings, kernel=None):
         # the two-min / ping-pong tile updates (the library's default is the min-with-predicate
         # form from the patched cubin wherever a CTA bucket exists)
         s.set_option("dp_form", 1)
-    elif kernel == 5:
-        # min-with-predicate form also for the multi-pass kernel (off by default: slower), 320-thread bucket
-        s.set_option("dp_form", 2)
-        s.set_option("mp_vp_threads", 320)
-    elif kernel == 6:
-        s.set_option("dp_form", 2)   # the same, 384-thread bucket
     elif kernel is not None:
         s.set_option("dp_kernel", kernel)
     return s
@@ -46,7 +40,7 @@ def test_orientation_generation_matches_reference(cfg, request):
     assert np.array_equal(sha(og.orientations), g["orient_sha256"])
 
 
-@pytest.mark.parametrize("kernel", [1, 0, 3, 4, 5, 6])
+@pytest.mark.parametrize("kernel", [1, 0, 3, 4])
 @pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv", "golden_maxn"])
 def test_single_orientation_values_match_reference(cfg, kernel, request):
     g = request.getfixturevalue(cfg)
@@ -57,7 +51,7 @@ def test_single_orientation_values_match_reference(cfg, kernel, request):
                           g["sample_ssd"][k], g["sample_T"][k], g["sample_pairs"][k], "o=%d" % o)
 
 
-@pytest.mark.parametrize("kernel", [1, 0, 3, 4, 5, 6])
+@pytest.mark.parametrize("kernel", [1, 0, 3, 4])
 @pytest.mark.parametrize("cfg", ["golden_c1", "golden_c2", "golden_mid", "golden_long", "golden_bb", "golden_bb_of", "golden_ir_off", "golden_iv", "golden_maxn"])
 def test_full_search_and_refine_match_reference(cfg, kernel, request):
     """configs 1 and 2 (and the 230 x 250 pair of the multi-pass kernel) end to end:
