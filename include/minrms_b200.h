@@ -184,7 +184,10 @@ int mr_event_elapsed_ms(mr_ctx *ctx, int32_t slot_a, int32_t slot_b, float *ms);
  * "refine_batch" = 0 all flagged sizes per Refine batch / k at most k (1 = sequential);
  * "refine_split" = 0 keeps one CTA per orientation in the DP of Refine batches (default 1: the
  * passes of the multi-pass kernel run on a cluster of CTAs); "nw_kernel" = 1
- * thread-per-orientation filter; "mp_threads" (tests). */
+ * thread-per-orientation filter; "mp_threads" (tests); "dp_form" = 1 runs the two-min / ping-pong
+ * tile updates instead of the min-with-predicate kernels of the patched cubin (default 0);
+ * "nw_cost_filter" = 0 keeps the counting NW kernels where the optimal cost would decide the
+ * filter (default 1); "ir_costs_only" = 0 sends -IR searches through the full DP kernel. */
 int mr_set_option(mr_ctx *ctx, const char *name, int64_t value);
 
 /* number of Dyn3d cells per orientation for all layers 1..n_max */
