@@ -778,6 +778,9 @@ int mr_create(mr_ctx** out, const float* A, int32_t m, const float* B, int32_t n
   }
   tick("device properties");
   c->hp = *p;
+  // MINRMS_B200_DP_FORM=1: the two-min / ping-pong tile updates for every context of the process
+  // (field debugging and A/B runs without touching the caller; mr_set_option("dp_form") overrides)
+  if (const char* e = getenv("MINRMS_B200_DP_FORM")) c->opt_dp_form = atoi(e) == 1 ? 1 : 0;
   c->m = m; c->nB = nB; c->N = N; c->R = p->n_max - p->n_min + 1;
   c->NP = ((p->n_max + 31) / 32) * 32;
   memset(&c->st, 0, sizeof c->st);

@@ -603,3 +603,31 @@ def test_nw_filter_decided_by_cost_equals_counting_filter(shape):
         a, b = tabs
         assert np.array_equal(bits(a["ssd"]), bits(b["ssd"])) and np.array_equal(a["o_id"], b["o_id"])
         assert np.sum(counts == of_min) + np.sum(counts == of_min - 1) > 0
+
+
+def test_dp_form_switches_give_identical_tables(monkeypatch):
+    """The min-with-predicate DP kernels (patched cubin, the default) against the two-min /
+    ping-pong forms, selected per context (dp_form) and per process (MINRMS_B200_DP_FORM):
+    every per-size key (score bits and orientation id) must be the same, on CTA buckets of
+    64, 128, 256 and 352 threads."""
+    from minrms_b200 import OrientationGenerator
+    for m, nB, n_or in ((30, 34, 900), (62, 58, 700), (110, 100, 400), (141, 151, 300)):
+        rng = np.random.default_rng(11 * m + nB)
+        A = random_chain(rng, m)
+        B = related_chain(rng, A, nB, noise=1.0)
+        p = oc.make_params(n_min=1, m=m, nB=nB)
+        keys = []
+        for mode in ("default", "option", "env"):
+            if mode == "env":
+                monkeypatch.setenv("MINRMS_B200_DP_FORM", "1")
+            s = make_search(A, B, settings_from_params(p, 4))
+            if mode == "option":
+                s.set_option("dp_form", 1)
+            og = OrientationGenerator(s)
+            s.Search(og.orientations[:n_or])
+            t = s.best_table()
+            keys.append((bits(t["ssd"]).copy(), t["o_id"].copy(), t["pairs"].copy()))
+            s.close()
+            monkeypatch.delenv("MINRMS_B200_DP_FORM", raising=False)
+        for k in keys[1:]:
+            assert np.array_equal(keys[0][0], k[0]) and np.array_equal(keys[0][1], k[1]) and np.array_equal(keys[0][2], k[2])
