@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of runtime switches: scratch/ab_env.sh "MR_TB_FUSED=1" "MR_TB_FUSED=0" ...
+# A/B of runtime switches: scratch/ab_env.sh "MINRMS_B200_TB_PAIRS=0" "MINRMS_B200_TB_PAIRS=1" ...
 for v in "$@"; do
   env $v python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras 2>/dev/null | tail -1 | python -c "
 import sys,json; d=json.loads(sys.stdin.read()); r=d['roofline']; sh=r['share_of_step']
