@@ -142,7 +142,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", [1, 0, 3])
+@pytest.mark.parametrize("kernel", [1, 0, 3, 4])
 @pytest.mark.parametrize("case", CASES)
 def test_synthetic_pairs_match_oracle(case, kernel):
     from minrms_b200 import OrientationGenerator
@@ -631,3 +631,57 @@ def test_dp_form_switches_give_identical_tables(monkeypatch):
             monkeypatch.delenv("MINRMS_B200_DP_FORM", raising=False)
         for k in keys[1:]:
             assert np.array_equal(keys[0][0], k[0]) and np.array_equal(keys[0][1], k[1]) and np.array_equal(keys[0][2], k[2])
+
+
+def _random_cases(count, seed=20261019):
+    """seeded random option mixes on small pairs: sizes, atoms per residue, -minN / -maxN, -max-dist,
+    -max-rmsd, the NW filter, -IR, fragment length"""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        m, nB = int(rng.integers(4, 73)), int(rng.integers(4, 73))
+        lo = min(m, nB)
+        nb = 2 if rng.random() < 0.2 else 1
+        frag = int(rng.integers(2, min(6, lo) + 1))
+        n_min = int(rng.integers(1, max(2, lo // 2) + 1)) if rng.random() < 0.6 else 1
+        n_max = int(rng.integers(max(n_min, 2), lo + 1)) if rng.random() < 0.3 else lo
+        max_dist = float(rng.uniform(6.0, 14.0)) if rng.random() < 0.3 else -1.0
+        max_rmsd = float(rng.uniform(2.0, 7.0)) if rng.random() < 0.4 else -1.0
+        filt = (float(rng.uniform(6.0, 11.0)), int(rng.integers(1, max(2, lo // 3) + 1))) if rng.random() < 0.35 else None
+        ir = 0 if rng.random() < 0.2 else 1
+        out.append((m, nB, nb, n_min, n_max, max_dist, max_rmsd, filt, ir, frag))
+    return out
+
+
+@pytest.mark.parametrize("case", _random_cases(24), ids=lambda c: "%dx%d_nb%d_min%d_max%d" % (c[0], c[1], c[2], c[3], c[4]))
+def test_random_option_mixes_match_oracle(case):
+    """The default kernels (min-with-predicate DP from the patched cubin, decision-only NW filter,
+    costs-only -IR pass) on seeded random option mixes: FirstPass over the first 250 orientations
+    and Refine against the oracle, bit for bit."""
+    from minrms_b200 import OrientationGenerator
+    m, nB, nb, n_min, n_max, max_dist, max_rmsd, filt, ir, frag = case
+    rng = np.random.default_rng(77 * m + nB + 1000 * nb)
+    A = random_chain(rng, m, nb)
+    B = related_chain(rng, A, nB, nb, noise=0.9)
+    p = oc.make_params(nb=nb, n_min=n_min, n_max=n_max, max_dist=max_dist, max_rmsd=max_rmsd,
+                       use_filter=filt is not None, of_dist=filt[0] if filt else 0.0,
+                       of_min=filt[1] if filt else 0, refine_while_searching=bool(ir))
+    og_ref = oc.gen_orientations(A, B, nb, frag, n_min)
+    if og_ref.shape[0] == 0:
+        pytest.skip("no fragment pair inside the band")
+    s = make_search(A, B, settings_from_params(p, frag))
+    og = OrientationGenerator(s)
+    assert np.array_equal(bits(og.orientations), bits(og_ref))
+    k = min(250, og_ref.shape[0])
+    ws = oc.Workspace(A, B, p)
+    best = ws.search(og_ref[:k])
+    s.Search(og.orientations[:k])
+    t = s.best_table()
+    assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "search")
+    assert np.array_equal(t["o_id"], best["o_id"])
+    if np.any(best["ssd"] < 1e26):
+        ws.refine(best)
+        s.Refine()
+        t = s.best_table()
+        assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "refine")
+    s.close()
