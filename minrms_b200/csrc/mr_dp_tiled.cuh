@@ -137,6 +137,7 @@ struct MrTiledPlan {
   int grid_cap_costs = 0;  // costs-only kernel (fewer registers: two CTAs per SM up to 384 threads)
   int vp_bucket = 0;       // CTA-size bucket of the min-with-predicate kernel (mr_dp_vp.cu), 0: none
   int grid_cap_vp = 0;
+  mutable void* vp_fn = nullptr;       // CUfunction, looked up at the first launch (per plan: one context, one device)
   size_t tb_words = 0;
   double lane_efficiency = 0.0;
   TbTiled layout;
@@ -487,6 +488,7 @@ static inline void mr_plan_dp_tiled(MrTiledPlan* p, const MrDevParams& P, const 
   p->grid_cap = prop.multiProcessorCount * p->ctas_per_sm;
   p->grid_cap_costs = prop.multiProcessorCount * std::max(1, std::min(by_smem, mr_dp_tiles_minb_costs(threads)));
   p->vp_bucket = mr_dp_vp_bucket(threads);
+  p->vp_fn = nullptr;
   p->grid_cap_vp = prop.multiProcessorCount * std::max(1, std::min(by_smem, mr_dp_vp_minb(p->vp_bucket)));
   p->layout.K = K; p->layout.R = R; p->layout.W = W; p->layout.JP = nBe / 2;
   p->layout.pad = pad; p->layout.NP = NP; p->layout.CN = CN; p->layout.T = threads;
@@ -573,7 +575,8 @@ static inline int mr_launch_dp_tiles_vp(const MrTiledPlan& p, const MrDevParams&
                                         float* cost, int count, cudaStream_t stream, int device, std::string* why) {
   char name[64];
   snprintf(name, sizeof name, "k_dp_vp_%d_%s%s", p.vp_bucket, P.nb == 1 ? "c" : "g", P.n_min > 1 ? "w" : "");
-  CUfunction f = mr_vp_function(device, name, p.smem, why);
+  if (!p.vp_fn) p.vp_fn = mr_vp_function(device, name, p.smem, why);
+  CUfunction f = static_cast<CUfunction>(p.vp_fn);
   if (!f) return 1;
   MrDevParams Pv = P;
   TbTiled Lv = p.layout;
