@@ -470,12 +470,20 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
       }
 #undef MR_NWC
     } else if (by_cost && c->nB <= 8192) {
-      const int nw = (c->nB + 255) / 256, cp = (c->nB + 32 * nw - 1) / (32 * nw);
+      // columns per lane: up to 16 (a warp spans 512 columns) beyond 512 columns -- the per-row work of
+      // a lane (shuffle, band bounds, coordinates of the row) is spread over more cells: 600x600 801 ->
+      // 1000 GCUPS, 1000x900 909 -> 1183, 2000x1500 1104 -> 1227 -- up to 8 below (two warps at least)
+      const int wcols = c->nB > 512 ? 512 : 256;
+      const int nw = (c->nB + wcols - 1) / wcols, cp = (c->nB + 32 * nw - 1) / (32 * nw);
       const size_t sm = 4 * (size_t)((3 * c->m + 3) & ~3) + 4 * 128 * (size_t)(nw - 1);
       const int grid = std::min(count, c->prop.multiProcessorCount * 16);
       typedef void (*nwk_t)(MrDevParams, float, const float*, const float*, const float*, int, int*, int*);
-      static const nwk_t ks[2][4] = {{k_nw_cost_cta<5, 256>, k_nw_cost_cta<6, 256>, k_nw_cost_cta<7, 256>, k_nw_cost_cta<8, 256>},
-                                     {k_nw_cost_cta<5, 1024>, k_nw_cost_cta<6, 1024>, k_nw_cost_cta<7, 1024>, k_nw_cost_cta<8, 1024>}};
+      static const nwk_t ks[2][12] = {{k_nw_cost_cta<5, 256>, k_nw_cost_cta<6, 256>, k_nw_cost_cta<7, 256>, k_nw_cost_cta<8, 256>,
+                                       k_nw_cost_cta<9, 256>, k_nw_cost_cta<10, 256>, k_nw_cost_cta<11, 256>, k_nw_cost_cta<12, 256>,
+                                       k_nw_cost_cta<13, 256>, k_nw_cost_cta<14, 256>, k_nw_cost_cta<15, 256>, k_nw_cost_cta<16, 256>},
+                                      {k_nw_cost_cta<5, 1024>, k_nw_cost_cta<6, 1024>, k_nw_cost_cta<7, 1024>, k_nw_cost_cta<8, 1024>,
+                                       k_nw_cost_cta<9, 1024>, k_nw_cost_cta<10, 1024>, k_nw_cost_cta<11, 1024>, k_nw_cost_cta<12, 1024>,
+                                       k_nw_cost_cta<13, 1024>, k_nw_cost_cta<14, 1024>, k_nw_cost_cta<15, 1024>, k_nw_cost_cta<16, 1024>}};
       const nwk_t k = ks[nw > 8 ? 1 : 0][std::max(cp, 5) - 5];
       if (mr_ensure_smem(k, sm)) MR_FAIL(c, "NW filter: shared memory attribute failed");
       k<<<grid, 32 * nw, sm, c->stream>>>(c->P, c->nw_cost_thr, c->dA, c->dB, d_orient_chunk, count, surv, c->d_surv_count);
