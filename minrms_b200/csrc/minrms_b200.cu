@@ -460,15 +460,22 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
     const int cpl = (c->nB + 31) / 32;
     const bool by_cost = decision_only && c->nw_cost_ok && c->opt_nw_cost && c->hp.nb == 1 && !c->opt_nw_general;
     if (by_cost && cpl <= 8) {
-      const int grid = (count + 3) / 4;
+      // up to 256 columns: 8 lanes per orientation up to 128 columns, 16 beyond (k_nw_cost_warp)
+      const int sw = c->nB <= 128 ? 8 : 16;
+      const int cp = (c->nB + sw - 1) / sw;   // 1..16
+      const int grid = (count + 4 * (32 / sw) - 1) / (4 * (32 / sw));
       const size_t sm = 4 * 3 * (size_t)c->m;
-#define MR_NWC(CPL) if (mr_ensure_smem(k_nw_cost_warp<CPL>, sm)) MR_FAIL(c, "NW filter: shared memory attribute failed"); \
-      k_nw_cost_warp<CPL><<<grid, 128, sm, c->stream>>>(c->P, c->nw_cost_thr, c->dA, c->dB, d_orient_chunk, count, surv, c->d_surv_count)
-      switch (cpl) {
-        case 1: MR_NWC(1); break; case 2: MR_NWC(2); break; case 3: MR_NWC(3); break; case 4: MR_NWC(4); break;
-        case 5: MR_NWC(5); break; case 6: MR_NWC(6); break; case 7: MR_NWC(7); break; default: MR_NWC(8); break;
-      }
-#undef MR_NWC
+      typedef void (*nwk_t)(MrDevParams, float, const float*, const float*, const float*, int, int*, int*);
+#define MR_NWC8(CPL) k_nw_cost_warp<CPL, 8>
+#define MR_NWC16(CPL) k_nw_cost_warp<CPL, 16>
+      static const nwk_t k8[16] = {MR_NWC8(1), MR_NWC8(2), MR_NWC8(3), MR_NWC8(4), MR_NWC8(5), MR_NWC8(6), MR_NWC8(7), MR_NWC8(8),
+                                   MR_NWC8(9), MR_NWC8(10), MR_NWC8(11), MR_NWC8(12), MR_NWC8(13), MR_NWC8(14), MR_NWC8(15), MR_NWC8(16)};
+      static const nwk_t k16[8] = {MR_NWC16(9), MR_NWC16(10), MR_NWC16(11), MR_NWC16(12), MR_NWC16(13), MR_NWC16(14), MR_NWC16(15), MR_NWC16(16)};
+#undef MR_NWC8
+#undef MR_NWC16
+      const nwk_t k = sw == 8 ? k8[cp - 1] : k16[cp - 9];
+      if (mr_ensure_smem(k, sm)) MR_FAIL(c, "NW filter: shared memory attribute failed");
+      k<<<grid, 128, sm, c->stream>>>(c->P, c->nw_cost_thr, c->dA, c->dB, d_orient_chunk, count, surv, c->d_surv_count);
     } else if (by_cost && c->nB <= 8192) {
       // columns per lane: up to 16 (a warp spans 512 columns) beyond 512 columns -- the per-row work of
       // a lane (shuffle, band bounds, coordinates of the row) is spread over more cells: 600x600 801 ->

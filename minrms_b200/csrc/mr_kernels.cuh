@@ -391,7 +391,11 @@ __device__ __forceinline__ float mr_nw_cost_row(float (&up)[CPL], float (&upg)[C
   return left;
 }
 
-template <int CPL>
+// SW lanes per orientation (32, 16 or 8): short chains put 2 or 4 orientations into a warp, each
+// lane then owns up to 16 columns -- the per-row work of a lane (shuffle, band bounds, the row's
+// coordinates) is spread over more cells and the wavefront fills and drains in SW - 1 steps
+// instead of 31.
+template <int CPL, int SW = 32>
 __global__ void __launch_bounds__(128)
 k_nw_cost_warp(MrDevParams P, float thr, const float* __restrict__ A, const float* __restrict__ B,
                const float* __restrict__ orient, int count, int* __restrict__ surv,
@@ -400,9 +404,13 @@ k_nw_cost_warp(MrDevParams P, float thr, const float* __restrict__ A, const floa
   const int m = P.m, nB = P.nB, w0 = P.w0, w1 = P.w1;
   for (int k = threadIdx.x; k < m * 3; k += blockDim.x) nw_sA[k] = A[k];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (o >= count) return;
+  static_assert(SW == 32 || SW == 16 || SW == 8, "lanes per orientation");
+  const int lane = threadIdx.x & (SW - 1);            // lane within the orientation's group
+  const int sub = (threadIdx.x & 31) / SW;
+  const int o_first = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / SW);
+  if (o_first >= count) return;                        // the whole warp is beyond the list
+  const bool valid = o_first + sub < count;            // a group beyond the list runs along (shuffles, votes) on the last orientation
+  const int o = valid ? o_first + sub : count - 1;
   const float G = P.nw_gap, cutoff = P.nw_cutoff;
   float T[12];
 #pragma unroll
@@ -418,8 +426,8 @@ k_nw_cost_warp(MrDevParams P, float thr, const float* __restrict__ A, const floa
     upg[c] = up[c] + G;
   }
   float last = 0.0f, diag_in = (float)j0 * G;  // my last column at my current row; A[i-1][j0]
-  for (int t = 1; t <= m + 31; t++) {
-    float left = __shfl_up_sync(0xffffffffu, last, 1);
+  for (int t = 1; t <= m + SW - 1; t++) {
+    float left = __shfl_up_sync(0xffffffffu, last, 1, SW);
     const int i = t - lane;
     if (lane == 0) left = (float)i * G;  // column 0
     const bool live = i >= 1 && i <= m;
@@ -442,8 +450,8 @@ k_nw_cost_warp(MrDevParams P, float thr, const float* __restrict__ A, const floa
 #pragma unroll
   for (int c = 0; c < CPL; c++)
     if (c == (nB - 1) - owner * CPL) result = up[c];
-  result = __shfl_sync(0xffffffffu, result, owner);
-  if (lane == 0 && result <= thr) surv[atomicAdd(surv_count, 1)] = o;
+  result = __shfl_sync(0xffffffffu, result, owner, SW);
+  if (lane == 0 && valid && result <= thr) surv[atomicAdd(surv_count, 1)] = o;
 }
 
 template <int CPL, int MAXT>
