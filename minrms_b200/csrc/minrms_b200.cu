@@ -459,10 +459,11 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
     CU(c, cudaEventRecord(ev->a, c->stream));
     const int cpl = (c->nB + 31) / 32;
     const bool by_cost = decision_only && c->nw_cost_ok && c->opt_nw_cost && c->hp.nb == 1 && !c->opt_nw_general;
-    if (by_cost && cpl <= 8) {
-      // up to 256 columns: 8 lanes per orientation up to 128 columns, 16 beyond (k_nw_cost_warp)
-      const int sw = c->nB <= 128 ? 8 : 16;
-      const int cp = (c->nB + sw - 1) / sw;   // 1..16
+    if (by_cost && cpl <= 16) {
+      // up to 512 columns (k_nw_cost_warp, up to 16 columns per lane): 8 lanes per orientation up to 128
+      // columns, 16 up to 256, a whole warp beyond
+      const int sw = c->nB <= 128 ? 8 : c->nB <= 256 ? 16 : 32;
+      const int cp = (c->nB + sw - 1) / sw;   // 1..16 (9..16 for 16 and 32 lanes)
       const int grid = (count + 4 * (32 / sw) - 1) / (4 * (32 / sw));
       const size_t sm = 4 * 3 * (size_t)c->m;
       typedef void (*nwk_t)(MrDevParams, float, const float*, const float*, const float*, int, int*, int*);
@@ -471,9 +472,11 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
       static const nwk_t k8[16] = {MR_NWC8(1), MR_NWC8(2), MR_NWC8(3), MR_NWC8(4), MR_NWC8(5), MR_NWC8(6), MR_NWC8(7), MR_NWC8(8),
                                    MR_NWC8(9), MR_NWC8(10), MR_NWC8(11), MR_NWC8(12), MR_NWC8(13), MR_NWC8(14), MR_NWC8(15), MR_NWC8(16)};
       static const nwk_t k16[8] = {MR_NWC16(9), MR_NWC16(10), MR_NWC16(11), MR_NWC16(12), MR_NWC16(13), MR_NWC16(14), MR_NWC16(15), MR_NWC16(16)};
+      static const nwk_t k32[8] = {k_nw_cost_warp<9, 32>, k_nw_cost_warp<10, 32>, k_nw_cost_warp<11, 32>, k_nw_cost_warp<12, 32>,
+                                   k_nw_cost_warp<13, 32>, k_nw_cost_warp<14, 32>, k_nw_cost_warp<15, 32>, k_nw_cost_warp<16, 32>};
 #undef MR_NWC8
 #undef MR_NWC16
-      const nwk_t k = sw == 8 ? k8[cp - 1] : k16[cp - 9];
+      const nwk_t k = sw == 8 ? k8[cp - 1] : sw == 16 ? k16[cp - 9] : k32[cp - 9];
       if (mr_ensure_smem(k, sm)) MR_FAIL(c, "NW filter: shared memory attribute failed");
       k<<<grid, 128, sm, c->stream>>>(c->P, c->nw_cost_thr, c->dA, c->dB, d_orient_chunk, count, surv, c->d_surv_count);
     } else if (by_cost && c->nB <= 8192) {
