@@ -461,7 +461,9 @@ def main():
         reps = 3 if cells_per * total < 5e11 else 1
         evals = 0
         f0 = time.perf_counter()
-        for _ in range(reps):
+        for rep in range(reps + (1 if reps > 1 else 0)):
+            if rep == 1 and reps > 1:
+                f0 = time.perf_counter()     # the first pass allocated this context's work space (cudaMalloc of GBs): warm from here
             s2 = SearchOrCuda(A, B, st, device=local)
             og2 = OrientationGenerator(s2)
             s2.Search(og2, 0, count)
@@ -470,7 +472,7 @@ def main():
         f_s = (time.perf_counter() - f0) / reps
         full_run = {"value": count / f_s, "unit": "orientations/s", "ms": 1e3 * f_s, "refine_evaluations": int(evals),
                     "what": "context + orientation generation (GPU) + FirstPass + Refine + tables on the host, "
-                            "through SearchOrCuda (the calls bin/minrms/main.cc:123-173 makes), warm process"}
+                            "through SearchOrCuda (the calls bin/minrms/main.cc:123-173 makes), warm process (work space of a previous context re-used)"}
         nw_filter = measure_nw_filter(local, clocks)
 
     if rank != 0:
