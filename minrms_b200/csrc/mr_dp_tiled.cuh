@@ -206,11 +206,6 @@ __device__ __forceinline__ void mr_produce_c(float* __restrict__ Cr, const float
   }
 }
 
-#ifdef MR_EXP_MAXNREG   // measurement builds only: a register cap of our choosing instead of the launch bounds
-#define MR_DP_ATTR(MAXT, MINB) __maxnreg__(MR_EXP_MAXNREG)
-#else
-#define MR_DP_ATTR(MAXT, MINB) __launch_bounds__(MAXT, MINB)
-#endif
 // the kernel body (a device function so that the min-with-predicate form can be instantiated
 // under extern "C" names in its own translation unit, mr_dp_vp.cu)
 template <int K, int R, bool NB1, bool WINDOWED, bool PP, bool COSTS, bool VP>
@@ -377,7 +372,7 @@ mr_dp_tiles_body(const MrDevParams& P, const TbTiled& L, int nslots, int nsteps,
 
 #ifndef MR_DP_TILED_DEVICE_ONLY   // mr_dp_vp.cu takes the kernel body only
 template <int K, int R, int MAXT, int MINB, bool NB1, bool WINDOWED, bool PP, bool COSTS = false>
-__global__ void MR_DP_ATTR(MAXT, MINB)
+__global__ void __launch_bounds__(MAXT, MINB)
 k_dp_tiles(MrDevParams P, TbTiled L, int nslots, int nsteps, const MrTile* __restrict__ tiles,
            const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ orient,
            const int* __restrict__ surv, const int* __restrict__ surv_count,
@@ -524,13 +519,7 @@ static inline int mr_launch_dp_tiles_t(const MrTiledPlan& p, const MrDevParams& 
 // ping-pong form (one FMNMX3 per cell) ~150.  Small pairs have few tiles: several CTAs
 // (orientations) per SM keep the pipes fed; from 320 threads on, one CTA per SM in the
 // ping-pong form is faster than two in the two-min form (config 2: 2.07 vs 2.01 TCUPS).
-#ifndef MR_DP_BIG_MINB
-#define MR_DP_BIG_MINB 1
-#endif
-#ifndef MR_DP_BIG_PP
-#define MR_DP_BIG_PP true
-#endif
-#define MR_DP_BIG_BUCKETS(X) X(320, MR_DP_BIG_MINB, MR_DP_BIG_PP) X(352, MR_DP_BIG_MINB, MR_DP_BIG_PP) X(384, MR_DP_BIG_MINB, MR_DP_BIG_PP)
+#define MR_DP_BIG_BUCKETS(X) X(320, 1, true) X(352, 1, true) X(384, 1, true)
 #define MR_DP_BUCKETS(X) \
   X(64, 10, false) X(128, 5, false) X(192, 3, false) X(256, 2, false) MR_DP_BIG_BUCKETS(X) X(512, 1, true)
 static inline int mr_dp_tiles_minb(int threads) {
