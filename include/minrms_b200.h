@@ -190,6 +190,12 @@ int mr_event_elapsed_ms(mr_ctx *ctx, int32_t slot_a, int32_t slot_b, float *ms);
  * filter (default 1); "ir_costs_only" = 0 sends -IR searches through the full DP kernel. */
 int mr_set_option(mr_ctx *ctx, const char *name, int64_t value);
 
+/* What the context will run, by name: "dp_path" (0 general kernel, 1 tiled single-pass, 2 tiled
+ * multi-pass), "dp_threads" (CTA size), "dp_vp_bucket" (CTA bucket of the min-with-predicate
+ * kernel that FirstPass will launch, 0: the two-min / ping-pong forms), "dp_ctas_per_sm",
+ * "dp_passes", "nw_decided_by_cost" (1: FirstPass filters with the decision-only kernels). */
+int mr_get_info(mr_ctx *ctx, const char *name, int64_t *value);
+
 /* number of Dyn3d cells per orientation for all layers 1..n_max */
 int64_t mr_dp_cells_per_orientation(int32_t m, int32_t nB, int32_t n_min, int32_t n_max);
 

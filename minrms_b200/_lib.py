@@ -32,7 +32,7 @@ class MrStats(C.Structure):
 EXPORTS = ["mr_create", "mr_destroy", "mr_last_error", "mr_best_init", "mr_search",
            "mr_upload_orientations", "mr_search_resident", "mr_reset_best", "mr_fetch_best",
            "mr_fetch_keys", "mr_device_keys", "mr_fetch_rows_device", "mr_eval_one", "mr_refine", "mr_gen_orientations",
-           "mr_superimpose_batch", "mr_plot_stats", "mr_get_stats", "mr_reset_stats", "mr_set_option",
+           "mr_superimpose_batch", "mr_plot_stats", "mr_get_stats", "mr_reset_stats", "mr_set_option", "mr_get_info",
            "mr_dp_cells_per_orientation", "mr_event_record", "mr_event_elapsed_ms"]
 
 _lib = None
@@ -75,6 +75,7 @@ def load():
     L.mr_event_record.argtypes = [vp, C.c_int32]
     L.mr_event_elapsed_ms.argtypes = [vp, C.c_int32, C.c_int32, fp]
     L.mr_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.mr_get_info.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     L.mr_dp_cells_per_orientation.restype = C.c_int64
     L.mr_dp_cells_per_orientation.argtypes = [C.c_int32] * 4
     for name in EXPORTS:

@@ -906,6 +906,22 @@ int mr_best_init(const mr_ctx* c, mr_best* best) {
   return 0;
 }
 
+// read-only view of what a context will run (tests, logs): see include/minrms_b200.h
+int mr_get_info(mr_ctx* c, const char* name, int64_t* value) {
+  if (!c || !name || !value) return 1;
+  const int path = dp_path(c);
+  if (!strcmp(name, "dp_path")) *value = path;   // 0 general, 1 tiled single-pass, 2 tiled multi-pass
+  else if (!strcmp(name, "dp_threads")) *value = path == 1 ? c->tiled.threads : path == 2 ? c->tiled_mp.threads : std::min(c->NP, 1024);
+  else if (!strcmp(name, "dp_vp_bucket")) *value = (path == 1 && c->opt_dp_form != 1) ? c->tiled.vp_bucket : 0;
+  else if (!strcmp(name, "dp_ctas_per_sm"))
+    *value = path == 1 ? ((c->tiled.vp_bucket && c->opt_dp_form != 1) ? c->tiled.grid_cap_vp : c->tiled.grid_cap) / c->prop.multiProcessorCount
+                       : path == 2 ? c->tiled_mp.grid_cap / c->prop.multiProcessorCount : c->dp_grid_cap / c->prop.multiProcessorCount;
+  else if (!strcmp(name, "dp_passes")) *value = path == 2 ? c->tiled_mp.npasses : 1;
+  else if (!strcmp(name, "nw_decided_by_cost")) *value = (c->hp.use_filter && c->nw_cost_ok && c->opt_nw_cost && c->hp.nb == 1 && !c->opt_nw_general) ? 1 : 0;
+  else MR_FAIL(c, "mr_get_info: unknown name %s", name);
+  return 0;
+}
+
 int mr_set_option(mr_ctx* c, const char* name, int64_t value) {
   if (!c || !name) return 1;
   if (!strcmp(name, "dp_kernel")) c->opt_dp_kernel = value;

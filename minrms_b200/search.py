@@ -140,6 +140,13 @@ class SearchOrCuda:
     def set_option(self, name, value):
         self._check(self.lib.mr_set_option(self.ctx, name.encode(), int(value)))
 
+    def info(self, name):
+        """what the context will run (mr_get_info): dp_path, dp_threads, dp_vp_bucket, dp_ctas_per_sm, ..."""
+        import ctypes as C
+        v = C.c_int64(0)
+        self._check(self.lib.mr_get_info(self.ctx, name.encode(), C.byref(v)))
+        return int(v.value)
+
     # -- SearchOr interface -----------------------------------------------------
     def Search(self, og, start=0, stop=None, first_id=None):
         """SearchOr::Search(og, start, stop) (search_or.h:87-104): FirstPass over

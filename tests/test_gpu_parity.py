@@ -685,3 +685,23 @@ def test_random_option_mixes_match_oracle(case):
         t = s.best_table()
         assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], n_min, "refine")
     s.close()
+
+
+def test_default_kernels_are_the_round2_ones(golden_c1, golden_c2, golden_mid):
+    """What a context runs by default (mr_get_info): the reference's test pair goes through the
+    min-with-predicate DP kernel of the patched cubin (352-thread bucket, two CTAs per SM) and,
+    with -of, through the decision-only NW filter; chains beyond one CTA through the multi-pass
+    kernel; dp_form = 1 falls back to the two-min / ping-pong forms."""
+    s = make_search(golden_c2["A"], golden_c2["B"], settings_from_golden(golden_c2))
+    assert s.info("dp_path") == 1 and s.info("dp_threads") == 352
+    assert s.info("dp_vp_bucket") == 352 and s.info("dp_ctas_per_sm") == 2
+    assert s.info("nw_decided_by_cost") == 0
+    s.set_option("dp_form", 1)
+    assert s.info("dp_vp_bucket") == 0 and s.info("dp_ctas_per_sm") == 1
+    s.close()
+    s = make_search(golden_c1["A"], golden_c1["B"], settings_from_golden(golden_c1))
+    assert s.info("dp_vp_bucket") > 0 and s.info("nw_decided_by_cost") == 1
+    s.close()
+    s = make_search(golden_mid["A"], golden_mid["B"], settings_from_golden(golden_mid))
+    assert s.info("dp_path") == 2 and s.info("dp_passes") >= 2 and s.info("dp_vp_bucket") == 0
+    s.close()
