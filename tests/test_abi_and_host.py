@@ -101,3 +101,27 @@ def test_all_vs_all_schedule_covers_every_pair_once_and_balances():
     assert pair_cost(3, 200, st) == 0                                     # shorter than the fragment
     ps = pair_settings(st, 141, 151, min_n=0.33, of_min=0.33)
     assert ps.n_min == 47 and ps.orientation_filter_nw_min_num_matches == 47 and st.n_min == 1
+
+
+def test_bench_config_is_the_same_object_in_both_arms():
+    """bench.py: the `config` both arms print comes from one function of the workload and the launch
+    alone (the driver compares the two), and its closed-form cell count is the library's."""
+    import argparse
+    import importlib.util
+    import os
+    from minrms_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    L = _lib.load()
+    for m, nB, n_min in ((141, 151, 1), (141, 151, 47), (600, 600, 1), (2000, 1500, 1), (40, 46, 10), (7, 2, 2)):
+        n_max = min(m, nB)
+        assert bench.dp_cells_closed_form(m, nB, n_min, n_max) == int(L.mr_dp_cells_per_orientation(m, nB, n_min, n_max))
+    args = argparse.Namespace(scaling="weak")
+    for cfg in (1, 2):
+        w = bench.workload(cfg)
+        a = bench.common_config(w, args, 20424)
+        b = bench.common_config(w, args, 20424)
+        assert a == b and a["config"] == cfg and a["dp_cells_per_orientation"] in (794770, 1044481)
+        assert set(a) >= {"workload", "orientations_in_list", "orientations_per_gpu_per_step", "alignment_sizes", "l2", "parallelism"}
