@@ -84,6 +84,18 @@ int mr_best_init(const mr_ctx *ctx, mr_best *best);
 int mr_search(mr_ctx *ctx, const float *orient12, int64_t count, int64_t first_id,
               mr_best *best);
 
+/* mr_search that also returns every score FirstPass compares: the input of the reference's
+ * alternate-solutions bookkeeping (-alt-o / -alt-o-orig).  scores[(o - first_id) * R + r] is the
+ * sum_sqd_dist handed to SearchOrDyn3d::KeepTrackOfAltSolutions for orientation o and size
+ * n_min + r (bin/minrms/search_or_dyn3d.cc:477-542, called at :1897-1904), MR_UPPER_BOUND
+ * where the reference does not get there (orientation rejected by the -of filter, n-loop left
+ * early at :1714-1721 / :1810-1811).  The temp files the reference writes (one record per
+ * kept score, :523-540) follow from this array and the running minimum over o; the
+ * 3x4 matrix of a record is mr_eval_one's T for that orientation and size.  Host memory,
+ * count * R floats, copied inside the call. */
+int mr_search_scores(mr_ctx *ctx, const float *orient12, int64_t count, int64_t first_id,
+                     mr_best *best, float *scores);
+
 /* Same search with the orientation list already resident in device memory
  * (uploaded once with mr_upload_orientations); nothing is copied to the host until
  * mr_fetch_best.  Used to time the kernels alone. */

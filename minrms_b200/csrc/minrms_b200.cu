@@ -66,6 +66,10 @@ struct mr_ctx {
   int use_gcol = 0;
   size_t dp_smem = 0;
   unsigned long long* d_keys = nullptr;
+  // mr_search_scores: every compared score of the running search, [count][R], grow-only
+  float* d_scores = nullptr;
+  int64_t scores_cap = 0;       // floats
+  float* scores_out = nullptr;  // non-null while mr_search_scores runs: search_device records into it
   // multi-GPU reduction on the device (mr_keys_snapshot / mr_fetch_rows_device)
   unsigned long long* d_keys_local = nullptr;  // this context's keys before the cross-rank MIN
   int32_t* d_rows = nullptr;                   // [R][2 + 12 + N] int32: key, transform, pairs of the sizes this context owns
@@ -581,7 +585,7 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
       if (!costs_only && launch_tb<false>(c, d_orient, cnt, nullptr, 0)) return 1;
       k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->surv, c->d_surv_count, c->d_cost,
                                                         costs_only ? c->d_cost : c->d_ssd, (long long)first_id, c->d_keys,
-                                                        nullptr, nullptr);
+                                                        nullptr, nullptr, c->scores_out);
       CU(c, cudaGetLastError());
       c->st.kernel_launches += 2;
     }
@@ -606,7 +610,8 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
     if (!costs_only && launch_tb<false>(c, oc, cnt, nullptr, 0)) return 1;
     k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->surv, c->d_surv_count,
                                                       c->d_cost, costs_only ? c->d_cost : c->d_ssd,
-                                                      (long long)(first_id + start), c->d_keys, nullptr, nullptr);
+                                                      (long long)(first_id + start), c->d_keys, nullptr, nullptr,
+                                                      c->scores_out ? c->scores_out + (size_t)start * c->R : nullptr);
     CU(c, cudaGetLastError());
     c->st.kernel_launches++;
     c->st.orientations += cnt;
@@ -888,7 +893,7 @@ void mr_destroy(mr_ctx* c) {
   arena_release(c);
   cudaFree(c->dA); cudaFree(c->dB); cudaFree(c->d_orient); cudaFree(c->d_surv_count);
   cudaFree(c->d_surv_all); cudaFree(c->d_nw_all);
-  cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w);
+  cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w); cudaFree(c->d_scores);
   cudaFree(c->d_keys_local); cudaFree(c->d_rows); cudaFree(c->d_item_row); cudaFree(c->d_misc);
   cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
   cudaFree(c->d_ref_pairs_in); cudaFree(c->d_ref_n); cudaFree(c->d_ref_orient); cudaFree(c->d_ref_T);
@@ -1116,6 +1121,38 @@ static int eval_w0(mr_ctx* c, bool apply_filter, int32_t* n_last, int32_t* nw_ma
       for (int k = 0; k < 2 * N; k++)
         pairs[(size_t)(n - 1) * 2 * N + k] = (v && k < 2 * n) ? hp[(size_t)(n - 1) * 2 * N + k] : 0;
   }
+  return 0;
+}
+
+// FirstPass that also returns what KeepTrackOfAltSolutions is handed for every (orientation,
+// size) it is called on (search_or_dyn3d.cc:1795-1811, 1897-1904): the compared score, or
+// MR_UPPER_BOUND where the reference never gets there (filtered orientation, early exit).
+int mr_search_scores(mr_ctx* c, const float* orient12, int64_t count, int64_t first_id, mr_best* best,
+                     float* scores) {
+  if (!c || !best || !scores) return 1;
+  CU(c, cudaSetDevice(c->device));
+  if (count <= 0) return mr_search(c, orient12, count, first_id, best);
+  if (c->opt_dp_only) MR_FAIL(c, "mr_search_scores: dp_only is set");
+  const int64_t need = count * (int64_t)c->R;
+  if (need > ((int64_t)1 << 34)) MR_FAIL(c, "mr_search_scores: orientations x sizes exceeds 2^34 scores; search the list in slices");
+  if (need > c->scores_cap) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_scores);
+    c->d_scores = nullptr;
+    c->scores_cap = 0;
+    CU(c, cudaMalloc(&c->d_scores, 4 * (size_t)need));
+    c->scores_cap = need;
+  }
+  k_fill_f32<<<(int)std::min<int64_t>((need + 255) / 256, 148 * 16), 256, 0, c->stream>>>(c->d_scores, (size_t)need, MR_UPPER_BOUND);
+  CU(c, cudaGetLastError());
+  c->st.kernel_launches++;
+  c->scores_out = c->d_scores;
+  const int rc = mr_search(c, orient12, count, first_id, best);
+  c->scores_out = nullptr;
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(scores, c->d_scores, 4 * (size_t)need, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->st.d2h_bytes += 4 * need;
   return 0;
 }
 

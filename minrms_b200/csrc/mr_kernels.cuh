@@ -522,6 +522,9 @@ k_nw_cost_cta(MrDevParams P, float thr, const float* __restrict__ A, const float
 }
 
 __global__ void k_set_int(int* __restrict__ p, int v) { *p = v; }
+__global__ void k_fill_f32(float* __restrict__ p, size_t n, float v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
 
 // Refine batch set-up in one launch: identity survivor list of `count` items and zeroed
 // per-size outputs (what k_iota + four memsets did)
@@ -899,13 +902,14 @@ __global__ void k_select_warp(MrDevParams P, int NP, const int* __restrict__ sur
 // (search_or_dyn3d.cc:1714-1721 max-dist, 1810-1811 max-rmsd) as a prefix over n, then
 // atomicMin the 64-bit key (float_bits(ssd) << 32 | o_id) per size: strict "<" with the
 // lowest orientation id winning ties is exactly search_or_dyn3d.cc:1825-1835 evaluated
-// in id order.  Optionally writes valid[] / n_last for mr_eval_one.
+// in id order.  Optionally writes valid[] / n_last for mr_eval_one, and every compared score
+// (scores, mr_search_scores) for the alternate-solutions bookkeeping.
 // ---------------------------------------------------------------------------
 __global__ void k_select(MrDevParams P, int NP, const int* __restrict__ surv,
                          const int* __restrict__ surv_count, const float* __restrict__ cost,
                          const float* __restrict__ ssd, long long id_base,
                          unsigned long long* __restrict__ keys, unsigned char* __restrict__ valid,
-                         int* __restrict__ n_last_out) {
+                         int* __restrict__ n_last_out, float* __restrict__ scores = nullptr) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= *surv_count) return;
   const unsigned long long oid = (unsigned long long)(id_base + surv[s]);
@@ -933,6 +937,9 @@ __global__ void k_select(MrDevParams P, int NP, const int* __restrict__ surv,
         const float v = sv8[q];
         if (P.max_rmsd >= 0.0f && v > (float)(n * P.nb) * (P.max_rmsd * P.max_rmsd)) { done = true; continue; }
         if (valid) valid[slot] = 1;
+        // -alt-o: the score KeepTrackOfAltSolutions sees for (orientation, size)
+        // (search_or_dyn3d.cc:1897-1904), row = position of the orientation in the searched list
+        if (scores && v < MR_UB) scores[(size_t)surv[s] * (P.n_max - P.n_min + 1) + (n - P.n_min)] = v;
         if (keys && v < MR_UB) {
           const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | oid;
           // most candidates lose: a plain (possibly stale, only ever too large) read first

@@ -5,11 +5,16 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <algorithm>
+#include <cmath>
 #include <iostream>
+#include <map>
+#include <sstream>
 #include <thread>
 
 #include <distance_metric.h>
 #include <global_utils.h>
+#include <simple_numeric_utils.h>  // SQR
 
 using namespace std;
 
@@ -22,8 +27,11 @@ static void Check(mr_ctx* c, int rc)
 
 SearchOrCuda::SearchOrCuda(SearchOrDyn3d::Settings const& s) : SearchOrDyn3d(s)
 {
-  if (settings.num_solutions != 1)
-    ERR("Error: alternate solutions (-alt-o, -alt-r) are not supported by the CUDA search.");
+  if (settings.num_solutions != 1 && settings.alt_method == Settings::ALT_METHOD_PAIRS)
+    ERR("Error: alternate solutions by common pairs (-alt-r) are not supported by the CUDA search;\n"
+        "       use -alt-o or -alt-o-orig.");
+  if (settings.num_solutions != 1 && settings.refine_method == Settings::REFINE_ALL)
+    ERR("Error: -r-all with alternate solutions is not supported by the CUDA search; use -r.");
   const int nb = Biopolymer::Residue::NumBackboneAtoms();
   N = max_num_matches;
   R = range_of_n;
@@ -93,6 +101,14 @@ void SearchOrCuda::TableFromHost(mr_best const& t)
 void SearchOrCuda::Search(OrientationGenerator const& og, long start, long stop)
 {
   const int G = (int)ctx.size();
+  const bool alt = settings.num_solutions > 1;
+  vector<float> scores;          // [stop - start][R], filled slice by slice by the GPUs
+  vector<Real> lowest_before;    // aaSumSqdDists[0] as KeepTrackOfAltSolutions first sees it
+  if (alt) {
+    scores.resize((size_t)(stop - start) * R);
+    lowest_before.assign(aaSumSqdDists[0], aaSumSqdDists[0] + R);
+    reduced_cache.clear();
+  }
   vector<vector<float> > vs(G), vT(G);
   vector<vector<int16_t> > vp(G);
   vector<vector<int64_t> > vo(G);
@@ -105,7 +121,12 @@ void SearchOrCuda::Search(OrientationGenerator const& og, long start, long stop)
     mr_best_init(ctx[g], &tb[g]);
     const long a = start + (stop - start) * g / G, b = start + (stop - start) * (g + 1) / G;
     const float* first = (b > a) ? &og[a].transform[0][0] : NULL;
-    th.push_back(thread([=, &rc, &tb]() { rc[g] = (b > a) ? mr_search(ctx[g], first, b - a, a, &tb[g]) : 0; }));
+    float* sc = alt && b > a ? &scores[(size_t)(a - start) * R] : NULL;
+    th.push_back(thread([=, &rc, &tb]() {
+      if (b <= a) rc[g] = 0;
+      else if (sc) rc[g] = mr_search_scores(ctx[g], first, b - a, a, &tb[g], sc);
+      else rc[g] = mr_search(ctx[g], first, b - a, a, &tb[g]);
+    }));
   }
   for (int g = 0; g < G; ++g) th[g].join();
   for (int g = 0; g < G; ++g) Check(ctx[g], rc[g]);
@@ -130,6 +151,128 @@ void SearchOrCuda::Search(OrientationGenerator const& og, long start, long stop)
         "       The restrictions you placed on accepting solutions were\n"
         "       too strict.  Try using a lower minimum-number-of-matches,\n"
         "       a larger maximum distance cutoff, for example.");
+  if (alt) CalcAlternates(og, start, stop, scores, lowest_before);
+}
+
+// The optimal-superposition matrices of every size at orientation o_id (what FirstPass hands
+// to KeepTrackOfAltSolutions as orientation_reduced, search_or_dyn3d.cc:1897-1904),
+// evaluated on the GPU the first time a candidate of that orientation is looked at.
+vector<float> const& SearchOrCuda::ReducedOrientations(OrientationGenerator const& og, long o_id)
+{
+  map<long, vector<float> >::iterator it = reduced_cache.find(o_id);
+  if (it != reduced_cache.end()) return it->second;
+  vector<float>& t = reduced_cache[o_id];
+  t.resize((size_t)12 * N);
+  int32_t n_last = 0, nw = 0;
+  Check(ctx[0], mr_eval_one(ctx[0], &og[o_id].transform[0][0], 0, &n_last, &nw, NULL, NULL, NULL, &t[0], NULL));
+  return t;
+}
+
+// ReadAltSolutionFiles + CalcAltSolutionsFromAltSolutionTable (search_or_dyn3d.cc:626-920,
+// 1253-1447) without the temp files.  The file of size n holds one record per orientation
+// whose score was within alt_rmsd_tolerance of the best score SO FAR (KeepTrackOfAltSolutions,
+// :477-542), in search order; that sequence is rebuilt here from the scores of the whole
+// search and a running minimum, then sorted and walked exactly as ReadAltSolutionFile does
+// (same element type, same std::sort, same comparisons in Real).
+void SearchOrCuda::CalcAlternates(OrientationGenerator const& og, long start, long stop,
+                                  vector<float> const& scores, vector<Real> const& lowest_before)
+{
+  const int nb = Biopolymer::Residue::NumBackboneAtoms();
+  const bool m3d = settings.alt_method == Settings::ALT_METHOD_3D;
+  const bool unlimited = settings.alt_rmsd_tolerance == Settings::ALTERNATES_NOT_LIMITED_BY_RMSD;
+  cout << "Choosing the best alternate alignments from the scores of the search." << endl;
+  multimap<long, OrientationOwner> orientation_owners;
+  vector<long> alt_ids(settings.num_solutions);
+  vector<float> alt_mats((size_t)12 * settings.num_solutions);
+  for (int n = n_min; n <= n_max; ++n) {
+    const int row = n - n_min;
+    if (aaSumSqdDists[0][row] == DistanceMetric::UPPER_BOUND) continue;  // :641
+    vector<OrientationUsageInstance> vInstances;
+    OrientationUsageInstance best_orientation;
+    bool best_orientation_found = false;
+    Real lowest_sum_sqd_dist_so_far = lowest_before[row];
+    for (long o = start; o < stop; ++o) {
+      const Real sum_sqd_dist = scores[(size_t)(o - start) * R + row];
+      if (!(sum_sqd_dist < DistanceMetric::UPPER_BOUND)) continue;  // never compared at this size
+      if (sum_sqd_dist < lowest_sum_sqd_dist_so_far) lowest_sum_sqd_dist_so_far = sum_sqd_dist;  // :1825-1835
+      if (!((sum_sqd_dist <= lowest_sum_sqd_dist_so_far * SQR(settings.alt_rmsd_tolerance)) || unlimited))
+        continue;                                                    // :493-501
+      OrientationUsageInstance u;
+      u.orig_orientation_id = o;
+      u.rmsd = sqrt(sum_sqd_dist / (n * nb));                        // :527-529
+      // :722-746: the record of the stored best solution goes first; it is the record of the
+      // winning orientation (the first one, in search order, that reached the best score)
+      if (!best_orientation_found && o == oid[row]) {
+        best_orientation = u;
+        best_orientation_found = true;
+      } else
+        vInstances.push_back(u);
+    }
+    if (!best_orientation_found)
+      ERR_INTERNAL("alternates: the best solution with " << n << " matches was not found in this search range.");
+    sort(vInstances.begin(), vInstances.end());                      // :755
+    vInstances.insert(vInstances.begin(), best_orientation);
+    memcpy(&vInstances[0].orientation_reduced[0][0], &aaTransforms[0][row][0][0], 12 * sizeof(Real));
+    alt_ids[0] = vInstances[0].orig_orientation_id;
+    memcpy(&alt_mats[0], &aaTransforms[0][row][0][0], 12 * sizeof(Real));
+    const Real best_rmsd = vInstances[0].rmsd;
+    int alt_count = 1;
+    for (vector<OrientationUsageInstance>::iterator p = vInstances.begin() + 1;
+         p != vInstances.end() && alt_count < settings.num_solutions &&
+         ((p->rmsd <= best_rmsd * settings.alt_rmsd_tolerance) || unlimited);
+         ++p) {
+      if (m3d)
+        memcpy(&p->orientation_reduced[0][0], &ReducedOrientations(og, p->orig_orientation_id)[(size_t)12 * (n - 1)],
+               12 * sizeof(Real));
+      int r;
+      for (r = 0; r < alt_count &&
+                  SufficientlyDifferentOrientationFromRthAlternate(
+                      *p, &alt_ids[0], reinterpret_cast<Matrix3x4*>(&alt_mats[0]), r, og);
+           ++r) {}
+      if (r != alt_count) continue;                                  // :858
+      OrientationOwner entry;
+      entry.n = n;
+      entry.r = alt_count;
+      orientation_owners.insert(make_pair(p->orig_orientation_id, entry));
+      alt_ids[alt_count] = p->orig_orientation_id;
+      if (m3d) memcpy(&alt_mats[(size_t)12 * alt_count], &p->orientation_reduced[0][0], 12 * sizeof(Real));
+      ++alt_count;
+    }
+  }
+  // :1253-1447: every owning orientation is evaluated once more (on the GPU) and the sizes it
+  // owns are stored at their rank
+  cout << "Recalculating the candidates for alternate alignments on the GPU." << endl;
+  vector<float> cost(N), ssd_n(N), T_n((size_t)12 * N);
+  vector<int16_t> pairs_n((size_t)2 * N * N);
+  vector<uint8_t> valid_n(N);
+  int orientation_counter = 0, alignment_counter = 0;
+  multimap<long, OrientationOwner>::iterator q = orientation_owners.begin();
+  while (q != orientation_owners.end()) {
+    const long o_id = q->first;
+    int32_t n_last = 0, nw = 0;
+    Check(ctx[0], mr_eval_one(ctx[0], &og[o_id].transform[0][0], 0, &n_last, &nw, &cost[0], &valid_n[0], &ssd_n[0],
+                              &T_n[0], &pairs_n[0]));
+    for (; q != orientation_owners.end() && q->first == o_id; ++q) {
+      const int n = q->second.n, r = q->second.r, row = n - n_min;
+      if (!valid_n[n - 1]) ERR_INTERNAL("alternates: orientation " << o_id << " has no alignment with " << n << " matches.");
+      // :1404-1423
+      aaSumSqdDists[r][row] = settings.refine_while_searching ? ssd_n[n - 1] : cost[n - 1];
+      if (settings.refine_while_searching)
+        memcpy(&aaTransforms[r][row][0][0], &T_n[(size_t)12 * (n - 1)], 12 * sizeof(Real));
+      else
+        CopyMatrix3x4(og[o_id].transform, aaTransforms[r][row]);
+      aaAlignments[r][row].resize(n);
+      for (int k = 0; k < n; ++k) {
+        aaAlignments[r][row][k][0] = pairs_n[(size_t)2 * N * (n - 1) + 2 * k];
+        aaAlignments[r][row][k][1] = pairs_n[(size_t)2 * N * (n - 1) + 2 * k + 1];
+      }
+      ++alignment_counter;
+    }
+    ++orientation_counter;
+  }
+  cout << "During re-calculation to find the alternate alignments,\n"
+       << orientation_counter << " orientations were tried, and\n"
+       << alignment_counter << " alternate alignments were found\n" << flush;
 }
 
 // search_or_dyn3d.cc:2261-2658 (REFINE_BEST)
@@ -144,6 +287,9 @@ void SearchOrCuda::Refine()
   Check(ctx[0], mr_refine(ctx[0], &mine, (int32_t)iters, &evals));
   TableFromHost(mine);
   cout << "(During refinement, " << evals + 1 << " new orientations were tested on the GPU.)" << endl;
+  // :2648-2654: the refined best solutions may have moved next to an alternate (the
+  // reference's own table bookkeeping, a handful of O(numRes2) comparisons per size)
+  if (settings.num_solutions > 1) CheckAlternatesForConsistency();
 }
 
 // search_or_dyn3d.cc:2942-2996.  The rows of the plot (WritePlotFile, 2662-2760: longest
@@ -159,36 +305,45 @@ void SearchOrCuda::WriteChimeraInfo() const
     SearchOrDyn3d::WriteChimeraInfo();
     return;
   }
-  WritePlotFileCuda(ca);
-  string info_name = string(SearchOrDyn3d::BASE_FILE_NAME) + "_chimera.info";
-  ofstream info_file(info_name.c_str(), ios::out);
-  if (!info_file) ERR_INTERNAL("Cannot open file \"" << info_name << "\" for writing.  Exiting...");
-  info_file << "fixed pdb:" << settings.vPdbFileNames[0] << "\n";
-  info_file << "moveable pdb:" << settings.vPdbFileNames[1] << "\n";
-  info_file << "rmsd:" << SearchOrDyn3d::BASE_FILE_NAME << "_chimera.plot\n";
-  info_file << "base:" << SearchOrDyn3d::BASE_FILE_NAME << "\n";
-  info_file << "number of atoms used:" << nb << "\n";
-  for (int q = 0; q < nb; ++q) info_file << Biopolymer::Residue::LookupBackboneAtomSymbol(q) << "\n";
+  // one pair of files per rank, named align_ / align<r+1>_ as at :2682-2688, 2968-2990
+  for (int r = 0; r < settings.num_solutions; ++r) {
+    WritePlotFileCuda(ca, r);
+    stringstream base, rank;
+    base << SearchOrDyn3d::BASE_FILE_NAME;
+    if (settings.num_solutions != 1) base << r + 1;
+    string info_name = base.str() + "_chimera.info";
+    ofstream info_file(info_name.c_str(), ios::out);
+    if (!info_file) ERR_INTERNAL("Cannot open file \"" << info_name << "\" for writing.  Exiting...");
+    info_file << "fixed pdb:" << settings.vPdbFileNames[0] << "\n";
+    info_file << "moveable pdb:" << settings.vPdbFileNames[1] << "\n";
+    info_file << "rmsd:" << base.str() << "_chimera.plot\n";
+    info_file << "base:" << base.str() << (settings.num_solutions != 1 ? "_" : "") << "\n";
+    info_file << "number of atoms used:" << nb << "\n";
+    for (int q = 0; q < nb; ++q) info_file << Biopolymer::Residue::LookupBackboneAtomSymbol(q) << "\n";
+  }
 }
 
-void SearchOrCuda::WritePlotFileCuda(int ca_index) const
+void SearchOrCuda::WritePlotFileCuda(int ca_index, int rank) const
 {
   vector<float> vs(R), vT(12 * R);
   vector<int16_t> vp((size_t)2 * N * R, 0);
   for (int r = 0; r < R; ++r) {
-    vs[r] = aaSumSqdDists[0][r];
-    memcpy(&vT[12 * r], &aaTransforms[0][r][0][0], 12 * sizeof(float));
+    vs[r] = aaSumSqdDists[rank][r];
+    memcpy(&vT[12 * r], &aaTransforms[rank][r][0][0], 12 * sizeof(float));
     if (!(vs[r] < DistanceMetric::UPPER_BOUND)) continue;
     for (int k = 0; k < n_min + r; ++k) {
-      vp[(size_t)2 * N * r + 2 * k] = aaAlignments[0][r][k][0];
-      vp[(size_t)2 * N * r + 2 * k + 1] = aaAlignments[0][r][k][1];
+      vp[(size_t)2 * N * r + 2 * k] = aaAlignments[rank][r][k][0];
+      vp[(size_t)2 * N * r + 2 * k + 1] = aaAlignments[rank][r][k][1];
     }
   }
   mr_best t;
   t.ssd = &vs[0]; t.T = &vT[0]; t.pairs = &vp[0]; t.o_id = NULL;
   vector<double> rows((size_t)9 * R);
   Check(ctx[0], mr_plot_stats(ctx[0], &t, ca_index, &rows[0]));
-  string plot_name = string(SearchOrDyn3d::BASE_FILE_NAME) + "_chimera.plot";
+  stringstream plot_base;
+  plot_base << SearchOrDyn3d::BASE_FILE_NAME;
+  if (settings.num_solutions != 1) plot_base << rank + 1;
+  string plot_name = plot_base.str() + "_chimera.plot";
   ofstream plot_file(plot_name.c_str(), ios::out);
   if (!plot_file) ERR_INTERNAL("WritePlotFile() cannot create file \"" << plot_name << "\" for writing.");
   plot_file << "# Matches,RMSD,Longest Distance" << ",-log(probability)\n";

@@ -15,6 +15,7 @@
 // (their include guards then skip them), so that the redefinition reaches the declaration
 // of SearchOrDyn3d and nothing else -- no standard or library header is parsed with it.
 #include <fstream>
+#include <map>
 #include <set>
 #include <string>
 #include <vector>
@@ -51,7 +52,13 @@ class SearchOrCuda : public SearchOrDyn3d {
   SearchOrCuda& operator=(SearchOrCuda const&);
   void TableToHost(mr_best& t);   // reference tables -> flat C-ABI table
   void TableFromHost(mr_best const& t);
-  void WritePlotFileCuda(int ca_index) const;
+  void WritePlotFileCuda(int ca_index, int r) const;
+  // -alt-o / -alt-o-orig (ALT_METHOD_3D / ALT_METHOD_3D_ORIG): the reference's bookkeeping
+  // of search_or_dyn3d.cc:477-542, 626-952, 1253-1447 from the scores of mr_search_scores
+  void CalcAlternates(OrientationGenerator const& og, long start, long stop,
+                      std::vector<float> const& scores, std::vector<Real> const& lowest_before);
+  std::vector<float> const& ReducedOrientations(OrientationGenerator const& og, long o_id);
+  std::map<long, std::vector<float> > reduced_cache;  // o_id -> mr_eval_one's T, [N][12]
   std::vector<mr_ctx*> ctx;       // one per GPU ($MINRMS_CUDA_GPUS, default 1)
   std::vector<float> ssd, T;
   std::vector<int16_t> pairs;
