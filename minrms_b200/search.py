@@ -159,6 +159,21 @@ class SearchOrCuda:
         self._check(self.lib.mr_search(self.ctx, _fp(part), part.shape[0], start if first_id is None else first_id,
                                        C.byref(self._best)))
 
+    def SearchScores(self, og, start=0, stop=None, first_id=None):
+        """Search() that also returns the [stop - start, R] float32 array of every score FirstPass
+        compares (mr_search_scores): what SearchOrDyn3d::KeepTrackOfAltSolutions is handed
+        (search_or_dyn3d.cc:477-542, 1897-1904), UPPER_BOUND where the reference never gets to
+        that size.  The alternate-solutions bookkeeping (-alt-o) starts from it."""
+        orient = og.orientations if hasattr(og, "orientations") else np.asarray(og, np.float32)
+        orient = np.ascontiguousarray(orient, np.float32).reshape(-1, 12)
+        stop = orient.shape[0] if stop is None else stop
+        part = np.ascontiguousarray(orient[start:stop])
+        scores = np.full((part.shape[0], max(self.R, 1)), UPPER_BOUND, np.float32)
+        self._check(self.lib.mr_search_scores(self.ctx, _fp(part), part.shape[0],
+                                              start if first_id is None else first_id,
+                                              C.byref(self._best), _fp(scores)))
+        return scores[:, :self.R]
+
     def check_solutions(self):
         """the reference's final check in FirstPass (search_or_dyn3d.cc:1929-1941)"""
         if not np.any(self.aSumSqdDists[:self.R] < UPPER_BOUND):

@@ -20,14 +20,27 @@ CONFIGS = {
     # cut-off (multi-pass DP, CTA NW filter), and 60 x 66 with four backbone atoms per residue
     "long": ["-fm", "4,0.6", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "4.0", "-ir", "-r"],
     "bb": ["-fm", "4", "-HS", "-ir", "-r"],
+    # alternate solutions (bin/minrms/minrms_parser.cc:755-840): three ranks on config 1 with an
+    # RMSD tolerance; four ranks, no tolerance, four backbone atoms; -alt-o-orig (implies -IR);
+    # no refinement with a distance cut-off
+    "alt": ["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.5", "-ir", "-r",
+            "-alt-o", "3,2.0,1.5"],
+    "alt_bb": ["-fm", "4", "-HS", "-ir", "-r", "-alt-o", "4,1.0"],
+    "alt_orig": ["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.5", "-r",
+                 "-alt-o-orig", "3,1.5,1.6"],
+    "alt_bbnr": ["-fm", "4", "-HS", "-ir", "-alt-o", "3,0.5,1.3", "-max-dist", "6.0"],
 }
-MOLS = {"long": ("synth_c.pdb", "synth_d.pdb"), "bb": ("synth_bb1.pdb", "synth_bb2.pdb")}
+MOLS = {"long": ("synth_c.pdb", "synth_d.pdb"), "bb": ("synth_bb1.pdb", "synth_bb2.pdb"),
+        "alt_bb": ("synth_bb1.pdb", "synth_bb2.pdb"), "alt_bbnr": ("synth_bb1.pdb", "synth_bb2.pdb")}
 PAIR = ("hemoglobin.pdb,*.A", "myoglobin.pdb")
 
 
 def digest_dir(d):
     out = {}
-    for f in sorted(glob.glob(os.path.join(d, "align*.msf")) + glob.glob(os.path.join(d, "align_chimera.plot"))):
+    # with alternates the files of rank r are align<r>_<n>.msf, align<r>_chimera.plot / .info
+    # (bin/minrms/search_or_dyn3d.cc:2682-2688, 2968-2990)
+    for f in sorted(glob.glob(os.path.join(d, "align*.msf")) + glob.glob(os.path.join(d, "align_chimera.plot")) +
+                    glob.glob(os.path.join(d, "align[0-9]*_chimera.*"))):
         lines = open(f, "rb").read().split(b"\n")
         lines = [b"<MSF header line masked>" if b" MSF: " in ln and b"Check:" in ln else ln for ln in lines]
         out[os.path.basename(f)] = hashlib.sha256(b"\n".join(lines)).hexdigest()
@@ -38,7 +51,7 @@ def run(exe, args, workdir, cfg=None):
     mols = MOLS.get(cfg, PAIR)
     for f in mols:
         subprocess.check_call(["cp", os.path.join(HERE, f.split(",")[0]), workdir])
-    if cfg == "bb":   # the reference reads the atom names from atoms_used.txt in its cwd
+    if cfg in ("bb", "alt_bb"):   # the reference reads the atom names from atoms_used.txt in its cwd
         subprocess.check_call(["cp", os.path.join(HERE, "atoms_used_backbone.txt"), os.path.join(workdir, "atoms_used.txt")])
     subprocess.check_call([exe] + args + list(mols), cwd=workdir,
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)

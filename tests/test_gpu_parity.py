@@ -705,3 +705,65 @@ def test_default_kernels_are_the_round2_ones(golden_c1, golden_c2, golden_mid):
     s = make_search(golden_mid["A"], golden_mid["B"], settings_from_golden(golden_mid))
     assert s.info("dp_path") == 2 and s.info("dp_passes") >= 2 and s.info("dp_vp_bucket") == 0
     s.close()
+
+
+def _oracle_scores(ws, orient, n_min, R):
+    """what KeepTrackOfAltSolutions is handed, orientation by orientation, from the oracle's
+    FirstPass body (search_or_dyn3d.cc:1691-1835, 1897-1904)"""
+    out = np.full((orient.shape[0], R), np.float32(1e26), np.float32)
+    for o, T in enumerate(orient):
+        e = ws.eval(T)
+        if e["n_last"] <= 0:
+            continue
+        for r in range(R):
+            n = n_min + r
+            if e["valid"][n - 1] and e["ssd"][n - 1] < np.float32(1e26):
+                out[o, r] = e["ssd"][n - 1]
+    return out
+
+
+@pytest.mark.parametrize("variant", ["c1_filter", "c1_small_chunks", "c2_dense", "ir_off", "synth_max_rmsd_nb4"])
+def test_search_scores_match_oracle(variant, golden_c1, golden_c2, golden_ir_off):
+    """mr_search_scores (the input of the -alt-o bookkeeping): every compared score of FirstPass,
+    bit for bit, with the -of filter (survivor indices into the whole list), without it over
+    several chunks (chunk-relative indices), through the costs-only -IR pass, and with the
+    max-rmsd exit on a four-atom backbone; the best table of the same call is the usual one."""
+    from minrms_b200 import OrientationGenerator
+    if variant.startswith("c") or variant == "ir_off":
+        g = golden_ir_off if variant == "ir_off" else golden_c2 if variant == "c2_dense" else golden_c1
+        A, B, p = g["A"], g["B"], params_from_golden(g)
+        s = make_search(A, B, settings_from_golden(g))
+        orient = np.ascontiguousarray(OrientationGenerator(s).orientations[:300 if variant == "c2_dense" else 1500])
+        if variant == "c1_small_chunks":
+            p.use_filter = 0
+            s.close()
+            st = settings_from_golden(g)
+            st.orientation_filter_nw = False
+            s = make_search(A, B, st)
+            s.set_option("chunk", 128)
+            orient = np.ascontiguousarray(orient[:700])
+    else:
+        rng = np.random.default_rng(4242)
+        A = random_chain(rng, 48, 4)
+        B = related_chain(rng, A, 55, 4, noise=0.9)
+        p = oc.make_params(nb=4, n_min=12, n_max=40, max_rmsd=2.5)
+        s = make_search(A, B, settings_from_params(p, 4))
+        orient = np.ascontiguousarray(OrientationGenerator(s).orientations[:900])
+    ws = oc.Workspace(A, B, p)
+    R = p.n_max - p.n_min + 1
+    want = _oracle_scores(ws, orient, p.n_min, R)
+    got = s.SearchScores(orient)
+    assert got.shape == want.shape
+    assert np.array_equal(bits(got), bits(want))
+    assert np.any(want < np.float32(1e26)) and (variant == "c2_dense" or np.any(want >= np.float32(1e26)))
+    best = ws.search(orient)
+    t = s.best_table()
+    assert_table_equal(t["ssd"], t["T"], t["pairs"], best["ssd"], best["T"], best["pairs"], p.n_min, variant)
+    # the table is the column minimum of the scores, the winner its first arg-min
+    have = best["ssd"] < np.float32(1e26)
+    assert np.array_equal(bits(got.min(axis=0)[have]), bits(best["ssd"][have]))
+    assert np.array_equal(got.argmin(axis=0)[have], best["o_id"][have])
+    # a second, shorter call reuses the device buffer: rows must not keep scores of the first
+    got2 = s.SearchScores(orient[100:400], first_id=100)
+    assert np.array_equal(bits(got2), bits(want[100:400]))
+    s.close()
