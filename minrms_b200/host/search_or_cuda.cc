@@ -30,8 +30,6 @@ SearchOrCuda::SearchOrCuda(SearchOrDyn3d::Settings const& s) : SearchOrDyn3d(s)
   if (settings.num_solutions != 1 && settings.alt_method == Settings::ALT_METHOD_PAIRS)
     ERR("Error: alternate solutions by common pairs (-alt-r) are not supported by the CUDA search;\n"
         "       use -alt-o or -alt-o-orig.");
-  if (settings.num_solutions != 1 && settings.refine_method == Settings::REFINE_ALL)
-    ERR("Error: -r-all with alternate solutions is not supported by the CUDA search; use -r.");
   const int nb = Biopolymer::Residue::NumBackboneAtoms();
   N = max_num_matches;
   R = range_of_n;
@@ -48,6 +46,8 @@ SearchOrCuda::SearchOrCuda(SearchOrDyn3d::Settings const& s) : SearchOrDyn3d(s)
   int ngpu = 1;
   if (const char* e = getenv("MINRMS_CUDA_GPUS")) ngpu = max(1, atoi(e));
   // the flattened coordinate arrays the reference builds at search_or_dyn3d.cc:186-224
+  coordsA.assign(&aRotateUsingTheseCoords1[0][0], &aRotateUsingTheseCoords1[0][0] + (size_t)3 * nb * numRes1);
+  coordsB.assign(&aRotateUsingTheseCoords2[0][0], &aRotateUsingTheseCoords2[0][0] + (size_t)3 * nb * numRes2);
   for (int g = 0; g < ngpu; ++g) {
     mr_ctx* c = NULL;
     if (mr_create(&c, &aRotateUsingTheseCoords1[0][0], numRes1, &aRotateUsingTheseCoords2[0][0],
@@ -287,9 +287,70 @@ void SearchOrCuda::Refine()
   Check(ctx[0], mr_refine(ctx[0], &mine, (int32_t)iters, &evals));
   TableFromHost(mine);
   cout << "(During refinement, " << evals + 1 << " new orientations were tested on the GPU.)" << endl;
-  // :2648-2654: the refined best solutions may have moved next to an alternate (the
-  // reference's own table bookkeeping, a handful of O(numRes2) comparisons per size)
+  if (settings.num_solutions > 1 && settings.refine_method == Settings::REFINE_ALL) {
+    int num_iterations = 0, num_new_solutions = 0;
+    for (int r = 1; r < settings.num_solutions; ++r) RefineAlternate(r, num_iterations, num_new_solutions);
+    cout << "(Refining the alternates, " << num_iterations << " new orientations were tested on the GPU,\n"
+            " and " << num_new_solutions << " instances of better alignments were found.)" << endl;
+  }
+  // :2648-2654: the refined solutions may have moved next to one another (the reference's
+  // own table bookkeeping, a handful of O(numRes2) comparisons per size)
   if (settings.num_solutions > 1) CheckAlternatesForConsistency();
+}
+
+// Refine() for a rank r > 0 (-r-all, search_or_dyn3d.cc:2344-2640): the size n at the median of
+// the unrefined ones is superimposed on its own alignment (CalcMinRMSD,
+// lib/pair_alignment/pair_alignment.cc:715-820: pairs in order, the nb atoms of a pair
+// consecutively), the DP runs at that orientation, and -- unlike rank 0 -- only the solution of
+// the SAME size may be replaced (:2543-2560; the m-loop stops at m = n, :2415-2421).  A size is
+// done when an evaluation leaves its alignment unchanged.  Both steps run on the GPU
+// (mr_superimpose_batch, mr_eval_one); valid[n-1] says that none of the loop's early exits
+// (max-dist :2424, max-rmsd :2500) fired at or before n.
+void SearchOrCuda::RefineAlternate(int r, int& num_iterations_total, int& num_new_solutions)
+{
+  const int nb = Biopolymer::Residue::NumBackboneAtoms();
+  vector<char> flags(R);
+  bool* aNeed2Refine = reinterpret_cast<bool*>(&flags[0]);
+  for (int row = 0; row < R; ++row) aNeed2Refine[row] = aaSumSqdDists[r][row] < DistanceMetric::UPPER_BOUND;
+  cout << "Currently refining the " << r + 1 << "th-best alignments.\n" << flush;
+  vector<float> fixed((size_t)3 * nb * N), moveable((size_t)3 * nb * N), cost(N), ssd_n(N), T_n((size_t)12 * N);
+  vector<int16_t> pairs_n((size_t)2 * N * N);
+  vector<uint8_t> valid_n(N);
+  PairwiseAlignment oldNthAlignment(max_num_matches);
+  for (int num_iterations = 1;
+       num_iterations <= settings.refine_max_iters || settings.refine_max_iters == Settings::ITERATE_UNTIL_CONVERGENCE;
+       ++num_iterations) {
+    const int n = FindMedian(aNeed2Refine, n_min, n_max);
+    if (n == n_min - 1) break;
+    ++num_iterations_total;
+    const int row = n - n_min;
+    PairwiseAlignment& al = aaAlignments[r][row];
+    for (int k = 0; k < n; ++k)
+      for (int q = 0; q < nb; ++q) {
+        memcpy(&fixed[(size_t)3 * (k * nb + q)], &coordsA[(size_t)3 * (al[k][0] * nb + q)], 3 * sizeof(float));
+        memcpy(&moveable[(size_t)3 * (k * nb + q)], &coordsB[(size_t)3 * (al[k][1] * nb + q)], 3 * sizeof(float));
+      }
+    float T12[12], rmsd = 0.0f;
+    Check(ctx[0], mr_superimpose_batch(ctx[0], 1, n * nb, &fixed[0], &moveable[0], T12, &rmsd));
+    int32_t n_last = 0, nw = 0;
+    Check(ctx[0], mr_eval_one(ctx[0], T12, 0, &n_last, &nw, &cost[0], &valid_n[0], &ssd_n[0], &T_n[0], &pairs_n[0]));
+    oldNthAlignment.resize(n);
+    oldNthAlignment = al;
+    if (valid_n[n - 1]) {
+      const Real sum_sqd_dist = settings.refine_while_searching ? ssd_n[n - 1] : cost[n - 1];
+      if (sum_sqd_dist < aaSumSqdDists[r][row]) {
+        aaSumSqdDists[r][row] = sum_sqd_dist;
+        memcpy(&aaTransforms[r][row][0][0], settings.refine_while_searching ? &T_n[(size_t)12 * (n - 1)] : T12,
+               12 * sizeof(Real));
+        for (int k = 0; k < n; ++k) {
+          al[k][0] = pairs_n[(size_t)2 * N * (n - 1) + 2 * k];
+          al[k][1] = pairs_n[(size_t)2 * N * (n - 1) + 2 * k + 1];
+        }
+        ++num_new_solutions;
+      }
+    }
+    aNeed2Refine[row] = !(oldNthAlignment == al);
+  }
 }
 
 // search_or_dyn3d.cc:2942-2996.  The rows of the plot (WritePlotFile, 2662-2760: longest

@@ -58,6 +58,9 @@ class SearchOrCuda : public SearchOrDyn3d {
   void CalcAlternates(OrientationGenerator const& og, long start, long stop,
                       std::vector<float> const& scores, std::vector<Real> const& lowest_before);
   std::vector<float> const& ReducedOrientations(OrientationGenerator const& og, long o_id);
+  // -r-all: the ranks above the first (search_or_dyn3d.cc:2344-2640 with r > 0)
+  void RefineAlternate(int r, int& num_iterations, int& num_new_solutions);
+  std::vector<float> coordsA, coordsB;  // the constructor's flattened atoms (CalcMinRMSD overwrites the base's arrays)
   std::map<long, std::vector<float> > reduced_cache;  // o_id -> mr_eval_one's T, [N][12]
   std::vector<mr_ctx*> ctx;       // one per GPU ($MINRMS_CUDA_GPUS, default 1)
   std::vector<float> ssd, T;

@@ -137,3 +137,13 @@ int mr_plot_stats(mr_ctx *c, const mr_best *best, int32_t ca_index, double *rows
   orc_plot_stats(c->A, c->m, c->B, c->nB, c->p.nb, ca_index, c->p.n_min, c->R, c->N, &b, rows);
   return 0;
 }
+
+int mr_superimpose_batch(mr_ctx *c, int32_t batch, int32_t np, const float *fixed,
+                         const float *moveable, float *T, float *rmsd)
+{
+  int b;
+  (void)c;
+  for (b = 0; b < batch; b++)
+    rmsd[b] = orc_superimpose(np, fixed + (size_t)3 * np * b, moveable + (size_t)3 * np * b, T + 12 * b);
+  return 0;
+}

@@ -46,7 +46,7 @@ def hostcheck(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("cfg", ["bb", "alt_bb", "alt_bbnr", "alt"])
+@pytest.mark.parametrize("cfg", ["bb", "alt_bb", "alt_bbnr", "alt", "alt_rall", "alt_rall_orig"])
 def test_host_logic_writes_the_reference_files(cfg, hostcheck, tmp_path):
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "msf_digests.json")))[cfg]
     got = run(hostcheck, CONFIGS[cfg], str(tmp_path), cfg)
