@@ -96,6 +96,18 @@ int mr_search(mr_ctx *ctx, const float *orient12, int64_t count, int64_t first_i
 int mr_search_scores(mr_ctx *ctx, const float *orient12, int64_t count, int64_t first_id,
                      mr_best *best, float *scores);
 
+/* Replaces one pass of SearchOrDyn3d::MultiPass (bin/minrms/search_or_dyn3d.cc:1975-2250), the
+ * search for the alternates of -alt-r (ALT_METHOD_PAIRS): mr_search in which an alignment of
+ * size n is recorded only if, for every table q < n_lower, it shares at most
+ * max_pairs_common residue pairs with lower[q]'s alignment of size n
+ * (NotTooManyPairsInCommon, :352-365; NumMatchesInBothAssumingMonotonicity,
+ * lib/pair_alignment/pair_alignment.cc:2529-2555).  Sizes a lower table has no solution for
+ * constrain nothing.  The early exits of the n-loop (:2040, :2078) are those of mr_search.
+ * lower[q].ssd and lower[q].pairs are read (host memory); T and o_id may be NULL. */
+int mr_search_dissimilar(mr_ctx *ctx, const float *orient12, int64_t count, int64_t first_id,
+                         mr_best *best, int32_t n_lower, const mr_best *lower,
+                         int32_t max_pairs_common);
+
 /* Same search with the orientation list already resident in device memory
  * (uploaded once with mr_upload_orientations); nothing is copied to the host until
  * mr_fetch_best.  Used to time the kernels alone. */

@@ -29,7 +29,7 @@ class MrStats(C.Structure):
                 ("refine_batches", C.c_int64), ("refine_evals_launched", C.c_int64)]
 
 
-EXPORTS = ["mr_create", "mr_destroy", "mr_last_error", "mr_best_init", "mr_search", "mr_search_scores",
+EXPORTS = ["mr_create", "mr_destroy", "mr_last_error", "mr_best_init", "mr_search", "mr_search_scores", "mr_search_dissimilar",
            "mr_upload_orientations", "mr_search_resident", "mr_reset_best", "mr_fetch_best",
            "mr_fetch_keys", "mr_device_keys", "mr_fetch_rows_device", "mr_eval_one", "mr_refine", "mr_gen_orientations",
            "mr_superimpose_batch", "mr_plot_stats", "mr_get_stats", "mr_reset_stats", "mr_set_option", "mr_get_info",
@@ -57,6 +57,8 @@ def load():
     L.mr_best_init.argtypes = [vp, C.POINTER(MrBest)]
     L.mr_search.argtypes = [vp, fp, C.c_int64, C.c_int64, C.POINTER(MrBest)]
     L.mr_search_scores.argtypes = [vp, fp, C.c_int64, C.c_int64, C.POINTER(MrBest), fp]
+    L.mr_search_dissimilar.argtypes = [vp, fp, C.c_int64, C.c_int64, C.POINTER(MrBest), C.c_int32,
+                                       C.POINTER(MrBest), C.c_int32]
     L.mr_upload_orientations.argtypes = [vp, fp, C.c_int64]
     L.mr_search_resident.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
     L.mr_reset_best.argtypes = [vp]

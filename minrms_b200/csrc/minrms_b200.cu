@@ -70,6 +70,13 @@ struct mr_ctx {
   float* d_scores = nullptr;
   int64_t scores_cap = 0;       // floats
   float* scores_out = nullptr;  // non-null while mr_search_scores runs: search_device records into it
+  // mr_search_dissimilar: alignments of the lower ranks as residue -> partner tables
+  short* d_excl_partner = nullptr;    // [ranks][R][m]
+  size_t excl_partner_cap = 0;        // shorts
+  unsigned char* d_excl = nullptr;    // [chunk][NP] flags written by the traceback kernel
+  size_t excl_cap = 0;
+  int excl_ranks = 0, excl_max_common = 0;
+  bool excl_on = false;               // true while mr_search_dissimilar runs
   // multi-GPU reduction on the device (mr_keys_snapshot / mr_fetch_rows_device)
   unsigned long long* d_keys_local = nullptr;  // this context's keys before the cross-rank MIN
   int32_t* d_rows = nullptr;                   // [R][2 + 12 + N] int32: key, transform, pairs of the sizes this context owns
@@ -408,7 +415,7 @@ int launch_dp(mr_ctx* c, const float* d_orient_chunk, int count, bool latency = 
   return 0;
 }
 
-template <bool EMIT>
+template <bool EMIT, bool EXCL = false>
 int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* items, int n_items,
               float* d_T = nullptr, short* d_pairs = nullptr, bool pairs_in_scratch = false) {
   if (!d_T) d_T = c->d_Tout;
@@ -431,17 +438,19 @@ int launch_tb(mr_ctx* c, const float* d_orient_chunk, int count, const int2* ite
     if (base + want <= (size_t)c->prop.sharedMemPerBlockOptin) pairs_smem = want;
   }
   if (use_tiled(c)) {
-    auto kern = k_traceback_kabsch<TbTiled, EMIT>;
+    auto kern = k_traceback_kabsch<TbTiled, EMIT, EXCL>;
     if (mr_ensure_smem(kern, base + pairs_smem)) MR_FAIL(c, "traceback kernel: shared memory attribute failed");
     kern<<<grid, 128, base + pairs_smem, c->stream>>>(
         c->P, tiled_layout(c), c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb,
-        c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs, pairs_smem ? 1 : 0);
+        c->d_cost, items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs, pairs_smem ? 1 : 0,
+        EXCL ? c->d_excl_partner : nullptr, c->excl_ranks, c->excl_max_common, EXCL ? c->d_excl : nullptr);
   } else {
-    auto kern = k_traceback_kabsch<TbColumns, EMIT>;
+    auto kern = k_traceback_kabsch<TbColumns, EMIT, EXCL>;
     if (mr_ensure_smem(kern, base + pairs_smem)) MR_FAIL(c, "traceback kernel: shared memory attribute failed");
     kern<<<grid, 128, base + pairs_smem, c->stream>>>(
         c->P, c->Lc, c->dA, c->dB, d_orient_chunk, c->surv, c->d_surv_count, c->d_tb, c->d_cost,
-        items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs, pairs_smem ? 1 : 0);
+        items, n_items, n_lo, c->d_scratch, c->d_ssd, d_T, d_pairs, pairs_smem ? 1 : 0,
+        EXCL ? c->d_excl_partner : nullptr, c->excl_ranks, c->excl_max_common, EXCL ? c->d_excl : nullptr);
   }
   CU(c, cudaGetLastError());
   CU(c, cudaEventRecord(ev->b, c->stream));
@@ -542,6 +551,20 @@ int launch_filter(mr_ctx* c, const float* d_orient_chunk, int count, bool apply_
   return 0;
 }
 
+// flags of mr_search_dissimilar, one byte per (orientation of a chunk, size)
+static int ensure_excl(mr_ctx* c) {
+  if (!c->excl_on) return 0;
+  const size_t need = (size_t)c->chunk_cap * c->NP;
+  if (need <= c->excl_cap) return 0;
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_excl);
+  c->d_excl = nullptr;
+  c->excl_cap = 0;
+  CU(c, cudaMalloc(&c->d_excl, need));
+  c->excl_cap = need;
+  return 0;
+}
+
 // FirstPass over a device-resident list
 int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first_id) {
   if (count <= 0) return 0;
@@ -549,7 +572,8 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
   // (search_or_dyn3d.cc:576-589), so FirstPass needs no alignment: the DP runs without tie
   // predicates / traceback words and the select kernel reads the costs.  The <= R winners get
   // their paths in fetch_payload, which re-evaluates them with the full kernel.
-  const bool costs_only = !c->hp.refine_while_searching && use_tiled(c) && !c->opt_costs_only_off;
+  // (not with mr_search_dissimilar: the exclusion test needs every alignment)
+  const bool costs_only = !c->hp.refine_while_searching && use_tiled(c) && !c->opt_costs_only_off && !c->excl_on;
   if (c->hp.use_filter) {
     // Phase 1: filter the whole list (it needs nothing per orientation but two ints), so that
     // phase 2 runs the DP over full chunks of survivors whatever the pass rate -- at config-4
@@ -575,6 +599,7 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
     c->st.dp_cells += dp_cells(c->m, c->nB, c->hp.n_min, c->hp.n_max) * total;
     c->st.d2h_bytes += 4;
     if (total > 0 && ensure_chunk(c, total)) return 1;
+    if (total > 0 && ensure_excl(c)) return 1;
     for (int64_t s0 = 0; s0 < total; s0 += c->chunk_cap) {
       const int cnt = (int)std::min<int64_t>(c->chunk_cap, total - s0);
       k_set_int<<<1, 1, 0, c->stream>>>(c->d_surv_count, cnt);
@@ -582,10 +607,11 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
       c->surv = c->d_surv_all + s0;  // indices into the whole list
       if (launch_dp(c, d_orient, cnt, false, costs_only)) return 1;
       if (c->opt_dp_only) continue;
-      if (!costs_only && launch_tb<false>(c, d_orient, cnt, nullptr, 0)) return 1;
+      if (!costs_only && (c->excl_on ? launch_tb<false, true>(c, d_orient, cnt, nullptr, 0)
+                                      : launch_tb<false>(c, d_orient, cnt, nullptr, 0))) return 1;
       k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->surv, c->d_surv_count, c->d_cost,
                                                         costs_only ? c->d_cost : c->d_ssd, (long long)first_id, c->d_keys,
-                                                        nullptr, nullptr, c->scores_out);
+                                                        nullptr, nullptr, c->scores_out, c->excl_on ? c->d_excl : nullptr);
       CU(c, cudaGetLastError());
       c->st.kernel_launches += 2;
     }
@@ -593,6 +619,7 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
     return 0;
   }
   if (ensure_chunk(c, count)) return 1;
+  if (ensure_excl(c)) return 1;
   for (int64_t start = 0; start < count; start += c->chunk_cap) {
     const int cnt = (int)std::min<int64_t>(c->chunk_cap, count - start);
     const float* oc = d_orient + 12 * (size_t)start;
@@ -607,11 +634,13 @@ int search_device(mr_ctx* c, const float* d_orient, int64_t count, int64_t first
     c->pending_counts.push_back({slot, cnt});
     if (launch_dp(c, oc, cnt, false, costs_only)) return 1;
     if (c->opt_dp_only) { c->st.orientations += cnt; continue; }
-    if (!costs_only && launch_tb<false>(c, oc, cnt, nullptr, 0)) return 1;
+    if (!costs_only && (c->excl_on ? launch_tb<false, true>(c, oc, cnt, nullptr, 0)
+                                    : launch_tb<false>(c, oc, cnt, nullptr, 0))) return 1;
     k_select<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->P, c->NP, c->surv, c->d_surv_count,
                                                       c->d_cost, costs_only ? c->d_cost : c->d_ssd,
                                                       (long long)(first_id + start), c->d_keys, nullptr, nullptr,
-                                                      c->scores_out ? c->scores_out + (size_t)start * c->R : nullptr);
+                                                      c->scores_out ? c->scores_out + (size_t)start * c->R : nullptr,
+                                                      c->excl_on ? c->d_excl : nullptr);
     CU(c, cudaGetLastError());
     c->st.kernel_launches++;
     c->st.orientations += cnt;
@@ -894,6 +923,7 @@ void mr_destroy(mr_ctx* c) {
   cudaFree(c->dA); cudaFree(c->dB); cudaFree(c->d_orient); cudaFree(c->d_surv_count);
   cudaFree(c->d_surv_all); cudaFree(c->d_nw_all);
   cudaFree(c->d_gcol); cudaFree(c->d_keys); cudaFree(c->d_orient_w); cudaFree(c->d_scores);
+  cudaFree(c->d_excl_partner); cudaFree(c->d_excl);
   cudaFree(c->d_keys_local); cudaFree(c->d_rows); cudaFree(c->d_item_row); cudaFree(c->d_misc);
   cudaFree(c->d_widx); cudaFree(c->d_items); cudaFree(c->d_Tout); cudaFree(c->d_pairs_out);
   cudaFree(c->d_ref_pairs_in); cudaFree(c->d_ref_n); cudaFree(c->d_ref_orient); cudaFree(c->d_ref_T);
@@ -1154,6 +1184,51 @@ int mr_search_scores(mr_ctx* c, const float* orient12, int64_t count, int64_t fi
   CU(c, cudaStreamSynchronize(c->stream));
   c->st.d2h_bytes += 4 * need;
   return 0;
+}
+
+// One pass of SearchOrDyn3d::MultiPass (search_or_dyn3d.cc:1975-2250): FirstPass in which an
+// alignment may be recorded only if it shares at most max_pairs_common pairs with the stored
+// alignment of the same size of EVERY table in lower[] (:2086-2107).  The early exits of the
+// n-loop do not depend on that test, so the only change on the device is a flag per
+// (orientation, size) from the traceback kernel that the select kernel honours.
+int mr_search_dissimilar(mr_ctx* c, const float* orient12, int64_t count, int64_t first_id, mr_best* best,
+                         int32_t n_lower, const mr_best* lower, int32_t max_pairs_common) {
+  if (!c || !best) return 1;
+  CU(c, cudaSetDevice(c->device));
+  if (n_lower < 0 || (n_lower > 0 && !lower) || max_pairs_common < 0) MR_FAIL(c, "mr_search_dissimilar: bad arguments");
+  if (n_lower == 0 || count <= 0) return mr_search(c, orient12, count, first_id, best);
+  if (c->opt_dp_only) MR_FAIL(c, "mr_search_dissimilar: dp_only is set");
+  const size_t need = (size_t)n_lower * c->R * c->m;
+  std::vector<short> partner(need, (short)-1);
+  for (int q = 0; q < n_lower; q++)
+    for (int r = 0; r < c->R; r++) {
+      if (!lower[q].ssd || !lower[q].pairs) MR_FAIL(c, "mr_search_dissimilar: lower table without ssd / pairs");
+      if (!(lower[q].ssd[r] < MR_UPPER_BOUND)) continue;   // no stored alignment: nothing to be similar to
+      const int n = c->hp.n_min + r;
+      const int16_t* pr = lower[q].pairs + (size_t)r * 2 * c->N;
+      for (int k = 0; k < n; k++) {
+        if (pr[2 * k] < 0 || pr[2 * k] >= c->m || pr[2 * k + 1] < 0 || pr[2 * k + 1] >= c->nB)
+          MR_FAIL(c, "mr_search_dissimilar: pair outside the molecules in a lower table");
+        partner[((size_t)q * c->R + r) * c->m + pr[2 * k]] = pr[2 * k + 1];
+      }
+    }
+  if (need > c->excl_partner_cap) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_excl_partner);
+    c->d_excl_partner = nullptr;
+    c->excl_partner_cap = 0;
+    CU(c, cudaMalloc(&c->d_excl_partner, 2 * need));
+    c->excl_partner_cap = need;
+  }
+  CU(c, cudaMemcpyAsync(c->d_excl_partner, partner.data(), 2 * need, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->st.h2d_bytes += 2 * (int64_t)need;
+  c->excl_ranks = n_lower;
+  c->excl_max_common = max_pairs_common;
+  c->excl_on = true;
+  const int rc = mr_search(c, orient12, count, first_id, best);
+  c->excl_on = false;
+  return rc;
 }
 
 int mr_eval_one(mr_ctx* c, const float* T12, int32_t apply_filter, int32_t* n_last,

@@ -640,7 +640,6 @@ k_dp_columns(MrDevParams P, TbColumns L, const float* __restrict__ A, const floa
 // and both coordinate sets sit in shared memory.
 //   items == NULL: dense grid over (s, n in [n_lo, n_max]);  else explicit (s,n) list.
 //   EMIT: also write the transform and the pair list.
-// ---------------------------------------------------------------------------
 #ifndef MR_TB_MINB
 #define MR_TB_MINB 12
 #endif
@@ -649,14 +648,24 @@ k_dp_columns(MrDevParams P, TbColumns L, const float* __restrict__ A, const floa
 #ifndef MR_TB_EMIT_MINB
 #define MR_TB_EMIT_MINB 4
 #endif
-template <class Layout, bool EMIT>
+//   EXCL (-alt-r, SearchOrDyn3d::MultiPass, search_or_dyn3d.cc:2086-2107): also count the
+//         pairs this alignment shares with the stored alignment of the same size of each of
+//         excl_ranks lower ranks (NumMatchesInBothAssumingMonotonicity,
+//         lib/pair_alignment/pair_alignment.cc:2529-2555: both lists are strictly increasing in
+//         i, so the count is the number of pairs k with partner[i_k] == j_k) and flag the
+//         alignment when any count exceeds excl_max_common.  excl_partner: [rank][R][m] shorts,
+//         j matched to residue i or -1; excl_out: [survivor][NP] bytes.
+// ---------------------------------------------------------------------------
+template <class Layout, bool EMIT, bool EXCL = false>
 __global__ void __launch_bounds__(128, EMIT ? MR_TB_EMIT_MINB : MR_TB_MINB)
 k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const float* __restrict__ B,
                    const float* __restrict__ orient, const int* __restrict__ surv,
                    const int* __restrict__ surv_count, const uint32_t* __restrict__ tb,
                    const float* __restrict__ cost, const int2* __restrict__ items, int n_items,
                    int n_lo, short2* __restrict__ scratch, float* __restrict__ ssd_out,
-                   float* __restrict__ T_out, short* __restrict__ pairs_out, int pairs_in_smem) {
+                   float* __restrict__ T_out, short* __restrict__ pairs_out, int pairs_in_smem,
+                   const short* __restrict__ excl_partner = nullptr, int excl_ranks = 0,
+                   int excl_max_common = 0, unsigned char* __restrict__ excl_out = nullptr) {
   extern __shared__ int tb_smem[];
   const int nb = P.nb;
   int* tab = tb_smem;                                              // layout table
@@ -696,6 +705,22 @@ k_traceback_kabsch(MrDevParams P, Layout L, const float* __restrict__ A, const f
     if (EMIT && sp) sp[(size_t)k * 128] = v;
   });
 #define MYR(k) ((EMIT && sp) ? sp[(size_t)(k) * 128] : MY(k))
+  if (EXCL) {
+    bool too_similar = false;
+    if (n >= P.n_min) {
+      const int R = P.n_max - P.n_min + 1;
+      for (int q = 0; q < excl_ranks; q++) {
+        const short* partner = excl_partner + ((size_t)q * R + (n - P.n_min)) * P.m;
+        int common = 0;
+        for (int k = 0; k < n; k++) {
+          const short2 pr = MYR(k);
+          common += (partner[pr.x] == pr.y) ? 1 : 0;
+        }
+        too_similar = too_similar || common > excl_max_common;
+      }
+    }
+    excl_out[slot] = too_similar ? 1 : 0;
+  }
   float T[12];
   float ssd;
   if (P.refine_while_searching) {
@@ -903,13 +928,15 @@ __global__ void k_select_warp(MrDevParams P, int NP, const int* __restrict__ sur
 // atomicMin the 64-bit key (float_bits(ssd) << 32 | o_id) per size: strict "<" with the
 // lowest orientation id winning ties is exactly search_or_dyn3d.cc:1825-1835 evaluated
 // in id order.  Optionally writes valid[] / n_last for mr_eval_one, and every compared score
-// (scores, mr_search_scores) for the alternate-solutions bookkeeping.
+// (scores, mr_search_scores) for the alternate-solutions bookkeeping; excl (mr_search_dissimilar)
+// marks the (survivor, size) alignments that may not be recorded.
 // ---------------------------------------------------------------------------
 __global__ void k_select(MrDevParams P, int NP, const int* __restrict__ surv,
                          const int* __restrict__ surv_count, const float* __restrict__ cost,
                          const float* __restrict__ ssd, long long id_base,
                          unsigned long long* __restrict__ keys, unsigned char* __restrict__ valid,
-                         int* __restrict__ n_last_out, float* __restrict__ scores = nullptr) {
+                         int* __restrict__ n_last_out, float* __restrict__ scores = nullptr,
+                         const unsigned char* __restrict__ excl = nullptr) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= *surv_count) return;
   const unsigned long long oid = (unsigned long long)(id_base + surv[s]);
@@ -940,7 +967,9 @@ __global__ void k_select(MrDevParams P, int NP, const int* __restrict__ surv,
         // -alt-o: the score KeepTrackOfAltSolutions sees for (orientation, size)
         // (search_or_dyn3d.cc:1897-1904), row = position of the orientation in the searched list
         if (scores && v < MR_UB) scores[(size_t)surv[s] * (P.n_max - P.n_min + 1) + (n - P.n_min)] = v;
-        if (keys && v < MR_UB) {
+        // -alt-r: an alignment too similar to a lower rank's still takes part in the early exits
+        // above, it just cannot be recorded (search_or_dyn3d.cc:2080-2107)
+        if (keys && v < MR_UB && !(excl && excl[slot])) {
           const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | oid;
           // most candidates lose: a plain (possibly stale, only ever too large) read first
           // keeps the 64-bit atomics on the ~140 hot addresses rare

@@ -27,9 +27,6 @@ static void Check(mr_ctx* c, int rc)
 
 SearchOrCuda::SearchOrCuda(SearchOrDyn3d::Settings const& s) : SearchOrDyn3d(s)
 {
-  if (settings.num_solutions != 1 && settings.alt_method == Settings::ALT_METHOD_PAIRS)
-    ERR("Error: alternate solutions by common pairs (-alt-r) are not supported by the CUDA search;\n"
-        "       use -alt-o or -alt-o-orig.");
   const int nb = Biopolymer::Residue::NumBackboneAtoms();
   N = max_num_matches;
   R = range_of_n;
@@ -66,84 +63,97 @@ SearchOrCuda::~SearchOrCuda()
   for (size_t g = 0; g < ctx.size(); ++g) mr_destroy(ctx[g]);
 }
 
-void SearchOrCuda::TableToHost(mr_best& t)
+void SearchOrCuda::TableToHost(mr_best& t, int rank)
 {
   t.ssd = &ssd[0]; t.T = &T[0]; t.pairs = &pairs[0]; t.o_id = &oid[0];
   for (int r = 0; r < R; ++r) {
-    ssd[r] = aaSumSqdDists[0][r];
-    memcpy(&T[12 * r], &aaTransforms[0][r][0][0], 12 * sizeof(float));
+    ssd[r] = aaSumSqdDists[rank][r];
+    memcpy(&T[12 * r], &aaTransforms[rank][r][0][0], 12 * sizeof(float));
     const int n = n_min + r;
+    if (rank > 0 && !(ssd[r] < DistanceMetric::UPPER_BOUND)) continue;  // alternates without a solution keep an unsized alignment
     for (int k = 0; k < n; ++k) {
-      pairs[(size_t)2 * N * r + 2 * k] = aaAlignments[0][r][k][0];
-      pairs[(size_t)2 * N * r + 2 * k + 1] = aaAlignments[0][r][k][1];
+      pairs[(size_t)2 * N * r + 2 * k] = aaAlignments[rank][r][k][0];
+      pairs[(size_t)2 * N * r + 2 * k + 1] = aaAlignments[rank][r][k][1];
     }
   }
 }
 
-void SearchOrCuda::TableFromHost(mr_best const& t)
+void SearchOrCuda::TableFromHost(mr_best const& t, int rank)
 {
   for (int r = 0; r < R; ++r) {
-    aaSumSqdDists[0][r] = t.ssd[r];
-    memcpy(&aaTransforms[0][r][0][0], &t.T[12 * r], 12 * sizeof(float));
+    aaSumSqdDists[rank][r] = t.ssd[r];
     const int n = n_min + r;
     if (!(t.ssd[r] < DistanceMetric::UPPER_BOUND)) continue;
+    memcpy(&aaTransforms[rank][r][0][0], &t.T[12 * r], 12 * sizeof(float));
+    aaAlignments[rank][r].resize(n);
     for (int k = 0; k < n; ++k) {
-      aaAlignments[0][r][k][0] = t.pairs[(size_t)2 * N * r + 2 * k];
-      aaAlignments[0][r][k][1] = t.pairs[(size_t)2 * N * r + 2 * k + 1];
+      aaAlignments[rank][r][k][0] = t.pairs[(size_t)2 * N * r + 2 * k];
+      aaAlignments[rank][r][k][1] = t.pairs[(size_t)2 * N * r + 2 * k + 1];
     }
   }
 }
 
-// FirstPass over og[start, stop) (search_or_dyn3d.cc:1643-1946).  vector<OrGenEntry> is a
-// contiguous array of 12-float Matrix3x4 (or_gen.h:73-78), so the range is passed as is;
-// with several GPUs it is cut into contiguous slices, one host thread per GPU, and the
-// per-size tables are merged with the reference's "lower score, then lower id" rule.
-void SearchOrCuda::Search(OrientationGenerator const& og, long start, long stop)
+// One search over `count` transforms (ids id0, id0 + 1, ...) into the tables of `rank`: with
+// several GPUs the list is cut into contiguous slices, one host thread per GPU, and the per-size
+// tables are merged with the reference's "lower score, then lower id" rule
+// (search_or_dyn3d.cc:1825-1835).  scores: mr_search_scores; n_lower > 0: mr_search_dissimilar.
+void SearchOrCuda::SearchRank(int rank, const float* first12, long count, long id0, float* scores,
+                              int n_lower, const mr_best* lower, vector<int64_t>& ids)
 {
   const int G = (int)ctx.size();
-  const bool alt = settings.num_solutions > 1;
-  vector<float> scores;          // [stop - start][R], filled slice by slice by the GPUs
-  vector<Real> lowest_before;    // aaSumSqdDists[0] as KeepTrackOfAltSolutions first sees it
-  if (alt) {
-    scores.resize((size_t)(stop - start) * R);
-    lowest_before.assign(aaSumSqdDists[0], aaSumSqdDists[0] + R);
-    reduced_cache.clear();
-  }
   vector<vector<float> > vs(G), vT(G);
   vector<vector<int16_t> > vp(G);
   vector<vector<int64_t> > vo(G);
   vector<mr_best> tb(G);
   vector<int> rc(G, 0);
   vector<thread> th;
+  const int max_common = settings.alt_max_pairs_common;
   for (int g = 0; g < G; ++g) {
     vs[g].resize(R); vT[g].resize(12 * R); vp[g].assign((size_t)2 * N * R, 0); vo[g].resize(R);
     tb[g].ssd = &vs[g][0]; tb[g].T = &vT[g][0]; tb[g].pairs = &vp[g][0]; tb[g].o_id = &vo[g][0];
     mr_best_init(ctx[g], &tb[g]);
-    const long a = start + (stop - start) * g / G, b = start + (stop - start) * (g + 1) / G;
-    const float* first = (b > a) ? &og[a].transform[0][0] : NULL;
-    float* sc = alt && b > a ? &scores[(size_t)(a - start) * R] : NULL;
+    const long a = count * g / G, b = count * (g + 1) / G;
+    const float* first = (b > a) ? first12 + 12 * a : NULL;
+    float* sc = scores && b > a ? scores + (size_t)a * R : NULL;
     th.push_back(thread([=, &rc, &tb]() {
       if (b <= a) rc[g] = 0;
-      else if (sc) rc[g] = mr_search_scores(ctx[g], first, b - a, a, &tb[g], sc);
-      else rc[g] = mr_search(ctx[g], first, b - a, a, &tb[g]);
+      else if (n_lower > 0) rc[g] = mr_search_dissimilar(ctx[g], first, b - a, id0 + a, &tb[g], n_lower, lower, max_common);
+      else if (sc) rc[g] = mr_search_scores(ctx[g], first, b - a, id0 + a, &tb[g], sc);
+      else rc[g] = mr_search(ctx[g], first, b - a, id0 + a, &tb[g]);
     }));
   }
   for (int g = 0; g < G; ++g) th[g].join();
   for (int g = 0; g < G; ++g) Check(ctx[g], rc[g]);
   mr_best mine;
-  TableToHost(mine);
+  TableToHost(mine, rank);
   for (int g = 0; g < G; ++g)
     for (int r = 0; r < R; ++r) {
       const bool better = tb[g].ssd[r] < mine.ssd[r] ||
                           (tb[g].ssd[r] == mine.ssd[r] && tb[g].ssd[r] < DistanceMetric::UPPER_BOUND &&
-                           oid[r] >= 0 && tb[g].o_id[r] < oid[r]);
+                           ids[r] >= 0 && tb[g].o_id[r] < ids[r]);
       if (!better) continue;
       mine.ssd[r] = tb[g].ssd[r];
-      oid[r] = tb[g].o_id[r];
+      ids[r] = tb[g].o_id[r];
       memcpy(&mine.T[12 * r], &tb[g].T[12 * r], 12 * sizeof(float));
       memcpy(&mine.pairs[(size_t)2 * N * r], &tb[g].pairs[(size_t)2 * N * r], sizeof(int16_t) * 2 * (n_min + r));
     }
-  TableFromHost(mine);
+  TableFromHost(mine, rank);
+}
+
+// FirstPass over og[start, stop) (search_or_dyn3d.cc:283-325, 1643-1946).  vector<OrGenEntry> is
+// a contiguous array of 12-float Matrix3x4 (or_gen.h:73-78), so the range is passed as is.
+void SearchOrCuda::Search(OrientationGenerator const& og, long start, long stop)
+{
+  const bool alt = settings.num_solutions > 1;
+  vector<float> scores;          // [stop - start][R], filled slice by slice by the GPUs
+  vector<Real> lowest_before;    // aaSumSqdDists[0] as KeepTrackOfAltSolutions first sees it
+  if (alt && alt_method_requires_alt_solution_table) {   // :140-149
+    scores.resize((size_t)(stop - start) * R);
+    lowest_before.assign(aaSumSqdDists[0], aaSumSqdDists[0] + R);
+    reduced_cache.clear();
+  }
+  SearchRank(0, stop > start ? &og[start].transform[0][0] : NULL, stop - start, start,
+             scores.empty() ? NULL : &scores[0], 0, NULL, oid);
   int n;
   for (n = n_min; n <= n_max && aaSumSqdDists[0][n - n_min] == DistanceMetric::UPPER_BOUND; ++n) {}
   if (n > n_max)  // search_or_dyn3d.cc:1929-1941
@@ -151,7 +161,70 @@ void SearchOrCuda::Search(OrientationGenerator const& og, long start, long stop)
         "       The restrictions you placed on accepting solutions were\n"
         "       too strict.  Try using a lower minimum-number-of-matches,\n"
         "       a larger maximum distance cutoff, for example.");
-  if (alt) CalcAlternates(og, start, stop, scores, lowest_before);
+  if (alt && settings.alt_method == Settings::ALT_METHOD_PAIRS) CalcAlternatesByPairs(og, start, stop, scores, lowest_before);
+  else if (alt) CalcAlternates(og, start, stop, scores, lowest_before);
+}
+
+// -alt-r (CalcAltSolutionsUsing_ALT_METHOD_PAIRS, search_or_dyn3d.cc:367-416): one more search
+// per rank, in which an alignment is recorded only if it shares at most alt_max_pairs_common
+// pairs with the solutions of the same size of all lower ranks (MultiPass, :1975-2250 -> one
+// mr_search_dissimilar per rank).  With an RMSD tolerance the searches run over the orientations
+// that produced, at some size, an alignment within the tolerance of the best one
+// (GetOrientationsOfLowRmsdFromAltTable, :960-1035, over the records KeepTrackOfAltSolutions
+// keeps: rebuilt from the scores as in CalcAlternates); otherwise over the whole range.
+void SearchOrCuda::CalcAlternatesByPairs(OrientationGenerator const& og, long start, long stop,
+                                         vector<float> const& scores, vector<Real> const& lowest_before)
+{
+  const int nb = Biopolymer::Residue::NumBackboneAtoms();
+  set<long> use_these_orientations;
+  if (settings.alt_rmsd_tolerance != Settings::ALTERNATES_NOT_LIMITED_BY_RMSD) {
+    for (int n = n_min; n <= n_max; ++n) {
+      const int row = n - n_min;
+      if (aaSumSqdDists[0][row] == DistanceMetric::UPPER_BOUND) continue;
+      const Real best_rmsd = sqrt(aaSumSqdDists[0][row] / (n * nb));
+      const Real tolerable_rmsd = settings.alt_rmsd_tolerance * best_rmsd;
+      Real lowest_sum_sqd_dist_so_far = lowest_before[row];
+      for (long o = start; o < stop; ++o) {
+        const Real sum_sqd_dist = scores[(size_t)(o - start) * R + row];
+        if (!(sum_sqd_dist < DistanceMetric::UPPER_BOUND)) continue;
+        if (sum_sqd_dist < lowest_sum_sqd_dist_so_far) lowest_sum_sqd_dist_so_far = sum_sqd_dist;
+        if (!(sum_sqd_dist <= lowest_sum_sqd_dist_so_far * SQR(settings.alt_rmsd_tolerance))) continue;  // :493-497
+        const Real rmsd = sqrt(sum_sqd_dist / (n * nb));
+        if (tolerable_rmsd >= rmsd) use_these_orientations.insert(o);                                    // :1019-1031
+      }
+    }
+    cout << "  ...After the RMSD-filter, the number of orientations\n"
+            "     we have to consider is: " << use_these_orientations.size() << endl;
+  } else
+    for (long o = start; o < stop; ++o) use_these_orientations.insert(o);
+  // the searched list in ascending id order: positions in it break ties like the ids would
+  vector<float> list((size_t)12 * use_these_orientations.size());
+  size_t at = 0;
+  for (set<long>::const_iterator p = use_these_orientations.begin(); p != use_these_orientations.end(); ++p, ++at)
+    memcpy(&list[12 * at], &og[*p].transform[0][0], 12 * sizeof(float));
+  vector<vector<float> > lower_ssd(settings.num_solutions);
+  vector<vector<int16_t> > lower_pairs(settings.num_solutions);
+  vector<mr_best> lower(settings.num_solutions);
+  for (int r = 1; r < settings.num_solutions; ++r) {
+    cout << "----- Searching for the " << r + 1 << "th-best alignments -----" << endl;
+    // rank r - 1 is final now: flatten it next to the lower ones
+    const int q = r - 1;
+    lower_ssd[q].assign(aaSumSqdDists[q], aaSumSqdDists[q] + R);
+    lower_pairs[q].assign((size_t)2 * N * R, 0);
+    for (int row = 0; row < R; ++row) {
+      if (!(lower_ssd[q][row] < DistanceMetric::UPPER_BOUND)) continue;
+      for (int k = 0; k < n_min + row; ++k) {
+        lower_pairs[q][(size_t)2 * N * row + 2 * k] = aaAlignments[q][row][k][0];
+        lower_pairs[q][(size_t)2 * N * row + 2 * k + 1] = aaAlignments[q][row][k][1];
+      }
+    }
+    lower[q].ssd = &lower_ssd[q][0]; lower[q].T = NULL; lower[q].pairs = &lower_pairs[q][0]; lower[q].o_id = NULL;
+    vector<int64_t> ids(R, -1);
+    SearchRank(r, list.empty() ? NULL : &list[0], (long)use_these_orientations.size(), 0, NULL, r, &lower[0], ids);
+    int n;
+    for (n = n_min; n <= n_max && aaSumSqdDists[r][n - n_min] == DistanceMetric::UPPER_BOUND; ++n) {}
+    if (n > n_max) cout << "No " << r + 1 << "th-best alignments were found." << endl;
+  }
 }
 
 // The optimal-superposition matrices of every size at orientation o_id (what FirstPass hands

@@ -2,7 +2,10 @@
 // (bin/minrms/search_or.h:57-130) whose Search() and Refine() run on the GPU through the
 // C ABI of include/minrms_b200.h.  It derives from SearchOrDyn3d only to reuse the
 // reference's own result tables and writers (WriteMSF / WriteChimeraInfo,
-// bin/minrms/search_or_dyn3d.cc:2848-2996) unchanged.
+// bin/minrms/search_or_dyn3d.cc:2848-2996) unchanged.  Alternate solutions: -alt-o / -alt-o-orig
+// (the scores of FirstPass from the GPU, the reference's selection rules on the host), -alt-r
+// (one more GPU search per rank with the common-pairs test inside the traceback kernel) and
+// -r-all (the alternates refined through the GPU as well).
 //
 // SearchOrDyn3d keeps aaSumSqdDists / aaTransforms / aaAlignments private
 // (bin/minrms/search_or_dyn3d.h:228-310).  A maintainer adopting this class changes that
@@ -50,8 +53,13 @@ class SearchOrCuda : public SearchOrDyn3d {
  private:
   SearchOrCuda(SearchOrCuda const&);
   SearchOrCuda& operator=(SearchOrCuda const&);
-  void TableToHost(mr_best& t);   // reference tables -> flat C-ABI table
-  void TableFromHost(mr_best const& t);
+  void TableToHost(mr_best& t, int rank = 0);   // reference tables of a rank -> flat C-ABI table
+  void TableFromHost(mr_best const& t, int rank = 0);
+  void SearchRank(int rank, const float* first12, long count, long id0, float* scores, int n_lower,
+                  const mr_best* lower, std::vector<int64_t>& ids);
+  // -alt-r (ALT_METHOD_PAIRS): search_or_dyn3d.cc:367-416, 960-1035, 1975-2250
+  void CalcAlternatesByPairs(OrientationGenerator const& og, long start, long stop,
+                             std::vector<float> const& scores, std::vector<Real> const& lowest_before);
   void WritePlotFileCuda(int ca_index, int r) const;
   // -alt-o / -alt-o-orig (ALT_METHOD_3D / ALT_METHOD_3D_ORIG): the reference's bookkeeping
   // of search_or_dyn3d.cc:477-542, 626-952, 1253-1447 from the scores of mr_search_scores

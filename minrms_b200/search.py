@@ -174,6 +174,24 @@ class SearchOrCuda:
                                               C.byref(self._best), _fp(scores)))
         return scores[:, :self.R]
 
+    def SearchDissimilar(self, og, lower, max_pairs_common, start=0, stop=None, first_id=None):
+        """One pass of SearchOrDyn3d::MultiPass (-alt-r, search_or_dyn3d.cc:1975-2250) into this
+        object's table: Search() in which an alignment of size n is recorded only if it shares at
+        most max_pairs_common pairs with the size-n alignment of every table in `lower`
+        (dicts with ssd [R] and pairs [R, N, 2], e.g. best_table() of the lower ranks)."""
+        orient = og.orientations if hasattr(og, "orientations") else np.asarray(og, np.float32)
+        orient = np.ascontiguousarray(orient, np.float32).reshape(-1, 12)
+        stop = orient.shape[0] if stop is None else stop
+        part = np.ascontiguousarray(orient[start:stop])
+        keep = [(np.ascontiguousarray(t["ssd"], np.float32), np.ascontiguousarray(t["pairs"], np.int16)) for t in lower]
+        arr = (_lib.MrBest * max(len(keep), 1))()
+        for q, (ssd, pairs) in enumerate(keep):
+            assert ssd.shape[0] >= self.R and pairs.shape == (max(self.R, 1), self.N, 2)
+            arr[q] = _lib.MrBest(_fp(ssd), None, pairs.ctypes.data_as(C.POINTER(C.c_int16)), None)
+        self._check(self.lib.mr_search_dissimilar(self.ctx, _fp(part), part.shape[0],
+                                                  start if first_id is None else first_id,
+                                                  C.byref(self._best), len(keep), arr, int(max_pairs_common)))
+
     def check_solutions(self):
         """the reference's final check in FirstPass (search_or_dyn3d.cc:1929-1941)"""
         if not np.any(self.aSumSqdDists[:self.R] < UPPER_BOUND):

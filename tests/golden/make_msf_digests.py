@@ -32,10 +32,16 @@ CONFIGS = {
     # -r-all: the alternates are refined too (bin/minrms/search_or_dyn3d.cc:2344-2640 with r > 0)
     "alt_rall": ["-fm", "4", "-HS", "-ir", "-r-all", "-alt-o", "3,1.0,1.6"],
     "alt_rall_orig": ["-fm", "4", "-HS", "-r-all", "-alt-o-orig", "3,1.0,1.6", "-max-dist", "7.0"],
+    # -alt-r (ALT_METHOD_PAIRS): one more search per rank, at most K common pairs with the lower ranks
+    "altr": ["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.5", "-ir", "-r",
+             "-alt-r", "3,40,1.5"],
+    "altr_bb": ["-fm", "4", "-HS", "-ir", "-r", "-alt-r", "3,5"],
+    "altr_ir": ["-fm", "4", "-HS", "-IR", "-r-all", "-alt-r", "4,20,1.4", "-max-dist", "7.0"],
 }
 MOLS = {"long": ("synth_c.pdb", "synth_d.pdb"), "bb": ("synth_bb1.pdb", "synth_bb2.pdb"),
         "alt_bb": ("synth_bb1.pdb", "synth_bb2.pdb"), "alt_bbnr": ("synth_bb1.pdb", "synth_bb2.pdb"),
-        "alt_rall": ("synth_bb1.pdb", "synth_bb2.pdb"), "alt_rall_orig": ("synth_bb1.pdb", "synth_bb2.pdb")}
+        "alt_rall": ("synth_bb1.pdb", "synth_bb2.pdb"), "alt_rall_orig": ("synth_bb1.pdb", "synth_bb2.pdb"),
+        "altr_bb": ("synth_bb1.pdb", "synth_bb2.pdb"), "altr_ir": ("synth_bb1.pdb", "synth_bb2.pdb")}
 PAIR = ("hemoglobin.pdb,*.A", "myoglobin.pdb")
 
 
@@ -55,7 +61,7 @@ def run(exe, args, workdir, cfg=None):
     mols = MOLS.get(cfg, PAIR)
     for f in mols:
         subprocess.check_call(["cp", os.path.join(HERE, f.split(",")[0]), workdir])
-    if cfg in ("bb", "alt_bb", "alt_rall"):   # the reference reads the atom names from atoms_used.txt in its cwd
+    if cfg in ("bb", "alt_bb", "alt_rall", "altr_bb"):   # the reference reads the atom names from atoms_used.txt in its cwd
         subprocess.check_call(["cp", os.path.join(HERE, "atoms_used_backbone.txt"), os.path.join(workdir, "atoms_used.txt")])
     subprocess.check_call([exe] + args + list(mols), cwd=workdir,
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)

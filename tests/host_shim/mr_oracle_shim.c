@@ -147,3 +147,47 @@ int mr_superimpose_batch(mr_ctx *c, int32_t batch, int32_t np, const float *fixe
     rmsd[b] = orc_superimpose(np, fixed + (size_t)3 * np * b, moveable + (size_t)3 * np * b, T + 12 * b);
   return 0;
 }
+
+/* SearchOrDyn3d::MultiPass (search_or_dyn3d.cc:1975-2250) through the oracle's per-orientation
+ * body: same early exits, a size is recorded only if its alignment shares at most
+ * max_pairs_common pairs with every lower table's alignment of that size. */
+int mr_search_dissimilar(mr_ctx *c, const float *orient12, int64_t count, int64_t first_id,
+                         mr_best *best, int32_t n_lower, const mr_best *lower,
+                         int32_t max_pairs_common)
+{
+  const int N = c->N, R = c->R;
+  orc_eval e;
+  int64_t o;
+  int r, q, k, k2;
+  e.cost = (float *)malloc(sizeof(float) * N);
+  e.valid = (uint8_t *)malloc(N);
+  e.ssd = (float *)malloc(sizeof(float) * N);
+  e.T = (float *)malloc(sizeof(float) * 12 * N);
+  e.pairs = (int16_t *)malloc(sizeof(int16_t) * 2 * N * N);
+  for (o = 0; o < count; o++) {
+    orc_eval_orientation(c->ws, c->A, c->B, orient12 + 12 * o, 1, &e);
+    if (e.n_last <= 0) continue;
+    for (r = 0; r < R; r++) {
+      const int n = c->p.n_min + r;
+      const int16_t *mine = e.pairs + (size_t)(n - 1) * 2 * N;
+      int ok = 1;
+      if (n > N || !e.valid[n - 1] || !(e.ssd[n - 1] < best->ssd[r])) continue;
+      for (q = 0; q < n_lower && ok; q++) {
+        const int16_t *theirs = lower[q].pairs + (size_t)r * 2 * N;
+        int common = 0;
+        if (!(lower[q].ssd[r] < ORC_UPPER_BOUND)) continue;
+        for (k = 0; k < n; k++)
+          for (k2 = 0; k2 < n; k2++)
+            if (mine[2 * k] == theirs[2 * k2] && mine[2 * k + 1] == theirs[2 * k2 + 1]) common++;
+        if (common > max_pairs_common) ok = 0;
+      }
+      if (!ok) continue;
+      best->ssd[r] = e.ssd[n - 1];
+      memcpy(best->T + 12 * r, e.T + 12 * (n - 1), 12 * sizeof(float));
+      memcpy(best->pairs + (size_t)r * 2 * N, mine, sizeof(int16_t) * 2 * n);
+      if (best->o_id) best->o_id[r] = first_id + o;
+    }
+  }
+  free(e.cost); free(e.valid); free(e.ssd); free(e.T); free(e.pairs);
+  return 0;
+}

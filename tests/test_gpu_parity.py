@@ -767,3 +767,80 @@ def test_search_scores_match_oracle(variant, golden_c1, golden_c2, golden_ir_off
     got2 = s.SearchScores(orient[100:400], first_id=100)
     assert np.array_equal(bits(got2), bits(want[100:400]))
     s.close()
+
+
+def _oracle_dissimilar(ws, orient, n_min, R, N, lower, max_common):
+    """SearchOrDyn3d::MultiPass (search_or_dyn3d.cc:1975-2250) from the oracle's FirstPass body:
+    strictly lower score wins in id order, only among the alignments that share at most
+    max_common pairs with every lower table's alignment of the same size"""
+    ssd = np.full(R, np.float32(1e26), np.float32)
+    T = np.zeros((R, 12), np.float32)
+    pairs = np.full((R, N, 2), -1, np.int16)
+    o_id = np.full(R, -1, np.int64)
+    n_excluded = 0
+    for o, M in enumerate(orient):
+        e = ws.eval(M)
+        if e["n_last"] <= 0:
+            continue
+        for r in range(R):
+            n = n_min + r
+            if not e["valid"][n - 1] or not e["ssd"][n - 1] < ssd[r]:
+                continue
+            mine = set(map(tuple, e["pairs"][n - 1][:n].tolist()))
+            ok = True
+            for t in lower:
+                if t["ssd"][r] < np.float32(1e26):
+                    ok = ok and len(mine & set(map(tuple, t["pairs"][r][:n].tolist()))) <= max_common
+            if not ok:
+                n_excluded += 1
+                continue
+            ssd[r], T[r], o_id[r] = e["ssd"][n - 1], e["T"][n - 1], o
+            pairs[r][:n] = e["pairs"][n - 1][:n]
+    return dict(ssd=ssd, T=T, pairs=pairs, o_id=o_id), n_excluded
+
+
+@pytest.mark.parametrize("variant", ["c1_filter", "c2_chunks", "ir_off", "synth_nb4_general"])
+def test_search_dissimilar_matches_oracle(variant, golden_c1, golden_c2, golden_ir_off):
+    """mr_search_dissimilar (-alt-r): ranks 2 and 3 after a FirstPass, each against the oracle's
+    per-orientation results with the common-pairs rule applied on the host; through the tiled
+    traceback with and without the -of filter, several chunks, -IR (no costs-only pass here)
+    and the general kernel's column layout with four atoms per residue."""
+    from minrms_b200 import OrientationGenerator
+    if variant == "synth_nb4_general":
+        rng = np.random.default_rng(977)
+        A = random_chain(rng, 40, 4)
+        B = related_chain(rng, A, 46, 4, noise=0.9)
+        p = oc.make_params(nb=4, n_min=10, n_max=36, max_rmsd=3.0)
+        s = make_search(A, B, settings_from_params(p, 4), kernel=1)
+        k, max_common = 600, 6
+    else:
+        g = {"c1_filter": golden_c1, "c2_chunks": golden_c2, "ir_off": golden_ir_off}[variant]
+        A, B, p = g["A"], g["B"], params_from_golden(g)
+        s = make_search(A, B, settings_from_golden(g))
+        k, max_common = {"c1_filter": (2500, 40), "c2_chunks": (300, 60), "ir_off": (1500, 12)}[variant]
+        if variant == "c2_chunks":
+            s.set_option("chunk", 128)
+    orient = np.ascontiguousarray(OrientationGenerator(s).orientations[:k])
+    ws = oc.Workspace(A, B, p)
+    R, N = p.n_max - p.n_min + 1, min(A.shape[0], B.shape[0]) // p.nb
+    lower = []
+    s.Search(orient)
+    total_excluded = 0
+    for rank in range(3):
+        t = s.best_table()
+        if rank == 0:
+            want = ws.search(orient)
+        else:
+            want, n_excl = _oracle_dissimilar(ws, orient, p.n_min, R, N, lower, max_common)
+            total_excluded += n_excl
+        assert_table_equal(t["ssd"], t["T"], t["pairs"], want["ssd"], want["T"], want["pairs"], p.n_min,
+                           "%s rank %d" % (variant, rank))
+        have = want["ssd"] < np.float32(1e26)
+        assert np.array_equal(t["o_id"][have], want["o_id"][have])
+        lower.append(t)
+        if rank < 2:
+            s.load_table(dict(ssd=np.full(R, np.float32(1e26), np.float32), T=np.zeros((R, 12), np.float32),
+                              pairs=np.full((R, N, 2), -1, np.int16), o_id=np.full(R, -1, np.int64)))
+            s.SearchDissimilar(orient, lower, max_common)
+    assert total_excluded > 0          # the rule did reject better-scoring alignments
+    s.close()

@@ -4,6 +4,7 @@ oracle/build_ref.sh) with the C ABI answered by the CPU oracle (tests/host_shim/
 in the place of libminrms_b200.so.  What is checked is the logic that lives above the C ABI --
 table merging, the alternate-solutions bookkeeping of -alt-o / -alt-o-orig
 (bin/minrms/search_or_dyn3d.cc:477-542, 626-952, 1253-1447 restated without temp files), the
+orientation subset and the per-rank searches of -alt-r (:367-416, 960-1035), -r-all, the
 per-rank writers -- against the digests of the files the UNMODIFIED reference binary writes
 (tests/golden/msf_digests.json).  The GPU suite runs the same configurations through the CUDA
 library (tests/test_gpu_cli.py).  Needs the reference's headers, i.e. /root/reference."""
@@ -46,7 +47,7 @@ def hostcheck(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("cfg", ["bb", "alt_bb", "alt_bbnr", "alt", "alt_rall", "alt_rall_orig"])
+@pytest.mark.parametrize("cfg", ["bb", "alt_bb", "alt_bbnr", "alt", "alt_rall", "alt_rall_orig", "altr_bb", "altr_ir"])
 def test_host_logic_writes_the_reference_files(cfg, hostcheck, tmp_path):
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "msf_digests.json")))[cfg]
     got = run(hostcheck, CONFIGS[cfg], str(tmp_path), cfg)
@@ -67,9 +68,12 @@ def test_two_slices_give_the_same_alternates(hostcheck, tmp_path):
     assert got == want
 
 
-def test_alt_r_is_refused(hostcheck, tmp_path):
-    for f in ("synth_bb1.pdb", "synth_bb2.pdb"):
-        subprocess.check_call(["cp", os.path.join(ROOT, "tests", "golden", f), str(tmp_path)])
-    r = subprocess.run([hostcheck, "-fm", "4", "-HS", "-alt-r", "2,10", "synth_bb1.pdb", "synth_bb2.pdb"],
-                       cwd=str(tmp_path), capture_output=True, text=True)
-    assert r.returncode != 0 and "-alt-r" in (r.stderr + r.stdout)
+def test_two_slices_give_the_same_pairs_alternates(hostcheck, tmp_path):
+    """-alt-r with MINRMS_CUDA_GPUS=2: every rank's search is cut in two and merged"""
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "msf_digests.json")))["altr_ir"]
+    os.environ["MINRMS_CUDA_GPUS"] = "2"
+    try:
+        got = run(hostcheck, CONFIGS["altr_ir"], str(tmp_path), "altr_ir")
+    finally:
+        del os.environ["MINRMS_CUDA_GPUS"]
+    assert got == want
