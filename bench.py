@@ -26,7 +26,8 @@ Prints ONE JSON line (rank 0).  `value` = orientations/s with the orientation li
 resident in HBM; `e2e` = the same through the host-buffer C-ABI call (mr_search: H2D of the
 list from pinned memory + D2H of the best table inside the timed region).  On the default
 line also: `full_run` (orientation generation + FirstPass + Refine through the public API)
-and `nw_filter` (the NW orientation filter of config 1 with its own roofline).
+and `nw_filter` (the NW orientation filter of config 1 with its own roofline), and `alternates`
+(the FirstPass variants behind -alt-o / -alt-r on the same workload).
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/fast, built by
 oracle/build_ref.sh) on the host cores instead.
 """
@@ -456,7 +457,7 @@ def main():
     d2h = (st_after["d2h_bytes"] - st_before["d2h_bytes"]) // e_steps
 
     # ---------------- extras on one GPU: the whole run, and the NW filter ---------------
-    full_run = nw_filter = None
+    full_run = nw_filter = alternates = None
     if world == 1 and not args.no_extras:
         reps = 3 if cells_per * total < 5e11 else 1
         evals = 0
@@ -474,6 +475,8 @@ def main():
                     "what": "context + orientation generation (GPU) + FirstPass + Refine + tables on the host, "
                             "through SearchOrCuda (the calls bin/minrms/main.cc:123-173 makes), warm process (work space of a previous context re-used)"}
         nw_filter = measure_nw_filter(local, clocks)
+        if cells_per * total < 5e11:
+            alternates = measure_alternates(SearchOrCuda, OrientationGenerator, A, B, st, local, count)
 
     if rank != 0:
         if world > 1:
@@ -548,6 +551,8 @@ def main():
         line["full_run"] = full_run
     if nw_filter:
         line["nw_filter"] = nw_filter
+    if alternates:
+        line["alternates"] = alternates
 
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
@@ -570,6 +575,45 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_alternates(SearchOrCuda, OrientationGenerator, A, B, st, local, count):
+    """The FirstPass variants behind -alt-o / -alt-r on the bench workload, host buffers, wall clock
+    around the C ABI call (best of 5): mr_search, mr_search_scores (every compared score returned),
+    mr_search_dissimilar with one lower rank (common-pairs test in the traceback kernel).  Extra
+    information only: a failure here is reported in the block, never in the headline numbers."""
+    try:
+        s = SearchOrCuda(A, B, st, device=local)
+        orient = np.ascontiguousarray(OrientationGenerator(s).orientations[:count])
+        R, N = max(s.R, 1), s.N
+
+        def fresh():
+            s.load_table(dict(ssd=np.full(s.R, np.float32(1e26), np.float32), T=np.zeros((s.R, 12), np.float32),
+                              pairs=np.full((R, N, 2), -1, np.int16)[:s.R], o_id=np.full(s.R, -1, np.int64)))
+
+        def timed(f):
+            best = None
+            for _ in range(5):
+                fresh()
+                t0 = time.perf_counter()
+                f()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            return 1e3 * best
+
+        ms_search = timed(lambda: s.Search(orient))
+        rank0 = s.best_table()
+        ms_scores = timed(lambda: s.SearchScores(orient))
+        same = bool(np.array_equal(s.best_table()["ssd"].view(np.uint32), rank0["ssd"].view(np.uint32)))
+        ms_dis = timed(lambda: s.SearchDissimilar(orient, [rank0], max(1, N // 3)))
+        found = int((s.best_table()["ssd"] < 1e26).sum())
+        s.close()
+        return {"search_ms": ms_search, "search_scores_ms": ms_scores, "search_dissimilar_1_lower_ms": ms_dis,
+                "scores_bytes": int(4 * orient.shape[0] * s.R), "scores_table_equals_search": same,
+                "max_pairs_common": max(1, N // 3), "second_rank_sizes_with_solution": found,
+                "what": "mr_search / mr_search_scores / mr_search_dissimilar over the whole list, host buffers, best of 5"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 def measure_nw_filter(local, clocks):
