@@ -29,6 +29,8 @@ CONFIGS = {
     "alt_orig": ["-fm", "4", "-of", "8.0,0.33", "-HS", "-minN", "0.33", "-max-rmsd", "3.5", "-r",
                  "-alt-o-orig", "3,1.5,1.6"],
     "alt_bbnr": ["-fm", "4", "-HS", "-ir", "-alt-o", "3,0.5,1.3", "-max-dist", "6.0"],
+    # config 2 (no cut-offs: every size of all 20 424 orientations is a candidate record)
+    "alt_c2": ["-fm", "4", "-HS", "-ir", "-r", "-alt-o", "3,3.0,1.3"],
     # -r-all: the alternates are refined too (bin/minrms/search_or_dyn3d.cc:2344-2640 with r > 0)
     "alt_rall": ["-fm", "4", "-HS", "-ir", "-r-all", "-alt-o", "3,1.0,1.6"],
     "alt_rall_orig": ["-fm", "4", "-HS", "-r-all", "-alt-o-orig", "3,1.0,1.6", "-max-dist", "7.0"],

@@ -21,7 +21,7 @@ REF = os.path.join(ROOT, "oracle", "_ref", "strict", "minrms")
 
 
 @pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("cfg", ["c1", "c2", "long", "bb", "alt", "alt_bb", "alt_orig", "alt_bbnr", "alt_rall", "alt_rall_orig",
+@pytest.mark.parametrize("cfg", ["c1", "c2", "long", "bb", "alt", "alt_c2", "alt_bb", "alt_orig", "alt_bbnr", "alt_rall", "alt_rall_orig",
                                  "altr", "altr_bb", "altr_ir"])
 def test_cli_output_matches_reference_digests(cfg, tmp_path):
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "msf_digests.json")))[cfg]
