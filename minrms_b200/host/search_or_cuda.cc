@@ -156,6 +156,8 @@ void SearchOrCuda::Search(OrientationGenerator const& og, long start, long stop)
              scores.empty() ? NULL : &scores[0], 0, NULL, oid);
   int n;
   for (n = n_min; n <= n_max && aaSumSqdDists[0][n - n_min] == DistanceMetric::UPPER_BOUND; ++n) {}
+  found_solutions = n <= n_max;
+  if (n > n_max && !fatal_without_solutions) return;   // batch runs: the caller skips this pair
   if (n > n_max)  // search_or_dyn3d.cc:1929-1941
     ERR("Error: No solutions were found satisfying your criteria.\n"
         "       The restrictions you placed on accepting solutions were\n"

@@ -49,8 +49,14 @@ class SearchOrCuda : public SearchOrDyn3d {
   // SearchOr::WriteChimeraInfo (search_or.h:125-129): align_chimera.info as the reference
   // writes it and align_chimera.plot with its per-size statistics computed on the GPU
   void WriteChimeraInfo() const;
+  // The reference ends the process when a search finds nothing (search_or_dyn3d.cc:1929-1941);
+  // a batch driver turns that off and asks afterwards.
+  void SetFatalWithoutSolutions(bool fatal) { fatal_without_solutions = fatal; }
+  bool FoundSolutions() const { return found_solutions; }
 
  private:
+  bool fatal_without_solutions = true;
+  bool found_solutions = false;
   SearchOrCuda(SearchOrCuda const&);
   SearchOrCuda& operator=(SearchOrCuda const&);
   void TableToHost(mr_best& t, int rank = 0);   // reference tables of a rank -> flat C-ABI table

@@ -72,6 +72,10 @@ build_flavour() {
     g++ -std=c++11 $FLAGS -w $INC -I$HERE/../include $HOST/main_cuda.cc $HOST/search_or_cuda.cc \
         $O/libminrms_bin.a $O/libminrms_ref.a -L$LIBDIR -lminrms_b200 -lpthread \
         -Wl,-rpath,'$ORIGIN/../../../minrms_b200' -o $O/minrms_cuda
+    # all-vs-all driver over the same objects (one process per pair, see batch_cuda.cc)
+    g++ -std=c++11 $FLAGS -w $INC -I$HERE/../include $HOST/batch_cuda.cc $HOST/search_or_cuda.cc \
+        $O/libminrms_bin.a $O/libminrms_ref.a -L$LIBDIR -lminrms_b200 -lpthread \
+        -Wl,-rpath,'$ORIGIN/../../../minrms_b200' -o $O/minrms_batch_cuda
   fi
   echo "built $O"
 }

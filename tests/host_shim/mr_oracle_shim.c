@@ -191,3 +191,8 @@ int mr_search_dissimilar(mr_ctx *c, const float *orient12, int64_t count, int64_
   free(e.cost); free(e.valid); free(e.ssd); free(e.T); free(e.pairs);
   return 0;
 }
+
+int64_t mr_dp_cells_per_orientation(int32_t m, int32_t nB, int32_t n_min, int32_t n_max)
+{
+  return orc_dp_cells(m, nB, n_min, n_max);
+}

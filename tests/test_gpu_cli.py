@@ -58,3 +58,15 @@ def test_cli_two_gpu_slices_give_identical_files(tmp_path):
                        capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr[-500:]
     assert digest_dir(str(tmp_path)) == want
+
+
+BATCH = os.path.join(ROOT, "oracle", "_ref", "strict", "minrms_batch_cuda")
+
+
+@pytest.mark.skipif(not (os.path.exists(BATCH) and os.path.exists(REF)), reason="oracle/_ref not built")
+def test_batch_cli_matches_pairwise_reference_runs(tmp_path):
+    """the C++ all-vs-all driver (minrms_b200/host/batch_cuda.cc) on four small structures, two
+    slots on the GPU: every pair directory holds the files of `minrms [flags] A B`"""
+    from test_host_alternates_cpu import check_batch_against_pairwise_reference
+    n = check_batch_against_pairwise_reference(BATCH, REF, str(tmp_path), ["-batch-workers-per-gpu", "2"])
+    assert n > 100

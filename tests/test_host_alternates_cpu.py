@@ -44,6 +44,12 @@ def hostcheck(tmp_path_factory):
                            os.path.join(d, "shim.o"), os.path.join(d, "oracle.o"),
                            os.path.join(STRICT, "libminrms_bin.a"), os.path.join(STRICT, "libminrms_ref.a"),
                            "-lpthread", "-lm", "-o", exe])
+    # the all-vs-all driver over the same host sources
+    subprocess.check_call(["g++", "-std=c++11", "-DNDEBUG", "-w"] + strict + inc +
+                          [os.path.join(host, "batch_cuda.cc"), os.path.join(host, "search_or_cuda.cc"),
+                           os.path.join(d, "shim.o"), os.path.join(d, "oracle.o"),
+                           os.path.join(STRICT, "libminrms_bin.a"), os.path.join(STRICT, "libminrms_ref.a"),
+                           "-lpthread", "-lm", "-o", os.path.join(d, "minrms_batch_hostcheck")])
     return exe
 
 
@@ -77,3 +83,42 @@ def test_two_slices_give_the_same_pairs_alternates(hostcheck, tmp_path):
     finally:
         del os.environ["MINRMS_CUDA_GPUS"]
     assert got == want
+
+
+BATCH_STRUCTURES = ["synth_e.pdb", "synth_f.pdb", "synth_bb1.pdb", "synth_bb2.pdb"]
+BATCH_FLAGS = ["-fm", "4", "-HS", "-ir", "-r", "-minN", "0.4"]
+
+
+def check_batch_against_pairwise_reference(batch_exe, ref_exe, workdir, extra=()):
+    """every pair directory of the batch driver holds the files `minrms [flags] A B` writes"""
+    from make_msf_digests import digest_dir
+    for f in BATCH_STRUCTURES:
+        subprocess.check_call(["cp", os.path.join(ROOT, "tests", "golden", f), workdir])
+    with open(os.path.join(workdir, "list.txt"), "w") as f:
+        f.write("# structures\n" + "\n".join(BATCH_STRUCTURES) + "\n")
+    r = subprocess.run([batch_exe] + BATCH_FLAGS + ["-batch", "list.txt", "-batch-out", "out"] + list(extra),
+                       cwd=workdir, capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[-300:], r.stderr[-300:])
+    assert "6 pairs in" in r.stdout
+    n_files = 0
+    for i, a in enumerate(BATCH_STRUCTURES):
+        for b in BATCH_STRUCTURES[i + 1:]:
+            got = digest_dir(os.path.join(workdir, "out", a[:-4] + "__" + b[:-4]))
+            refdir = os.path.join(workdir, "ref_" + a[:-4] + "_" + b[:-4])
+            os.mkdir(refdir)
+            subprocess.check_call(["cp", os.path.join(workdir, a), os.path.join(workdir, b), refdir])
+            subprocess.check_call([ref_exe] + BATCH_FLAGS + [a, b], cwd=refdir,
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            want = digest_dir(refdir)
+            assert got == want and len(want) > 10, (a, b)
+            n_files += len(want)
+    return n_files
+
+
+def test_batch_driver_writes_what_pairwise_runs_write(hostcheck, tmp_path):
+    """minrms_b200/host/batch_cuda.cc (all-vs-all, one process per pair, list scheduling over
+    slots) against one run of the unmodified reference binary per pair"""
+    batch = os.path.join(os.path.dirname(hostcheck), "minrms_batch_hostcheck")
+    n = check_batch_against_pairwise_reference(batch, os.path.join(STRICT, "minrms"), str(tmp_path),
+                                               ["-batch-workers-per-gpu", "3"])
+    assert n > 100
