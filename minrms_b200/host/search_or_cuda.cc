@@ -50,6 +50,11 @@ SearchOrCuda::SearchOrCuda(SearchOrDyn3d::Settings const& s) : SearchOrDyn3d(s)
     if (mr_create(&c, &aRotateUsingTheseCoords1[0][0], numRes1, &aRotateUsingTheseCoords2[0][0],
                   numRes2, &p, g) != 0)
       ERR("Error: cannot start the CUDA search: " << mr_last_error(NULL));
+    // work space of the context (default: sized by the library, up to 32 GB, allocated at the first
+    // search): runs that start many short processes on one GPU (batch_cuda.cc) set a smaller one
+    if (const char* e = getenv("MINRMS_CUDA_BUDGET_MB"))
+      if (atol(e) > 0 && mr_set_option(c, "budget_mb", atol(e)) != 0)
+        ERR("Error: cannot set the CUDA work space: " << mr_last_error(c));
     ctx.push_back(c);
   }
   ssd.resize(R);

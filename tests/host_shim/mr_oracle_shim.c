@@ -196,3 +196,9 @@ int64_t mr_dp_cells_per_orientation(int32_t m, int32_t nB, int32_t n_min, int32_
 {
   return orc_dp_cells(m, nB, n_min, n_max);
 }
+
+int mr_set_option(mr_ctx *c, const char *name, int64_t value)
+{
+  (void)c; (void)name; (void)value;   /* device work-space and kernel switches: nothing to do on the CPU */
+  return 0;
+}
