@@ -2,13 +2,18 @@
 // BASELINE config 5).  The reference has no batch mode; every unordered pair of a set of
 // structures is an independent `minrms [flags] A B` run (bin/minrms/main.cc:60-176: parse,
 // OrientationGenerator, Search(og, 0, og.size()), Refine(), WriteMSF(), WriteChimeraInfo()), so
-// the pairs shard over GPUs with no exchange.  The reference's parser keeps process-wide state
-// that does not survive a second parse (Biopolymer::Residue::StoreBackboneAtomName's static
-// atom table, lib/biopolymer/biopolymer.cc:163-200; DistanceMetric::max_allowed_dist_metric), so
-// every pair runs main.cc's sequence with SearchOrCuda in a PROCESS of its own, forked by a
-// parent that never touches CUDA; G x K slots (K per GPU) are kept busy by list scheduling, the
-// pairs taken largest first (cost = fragment pairs x Dyn3d cells, as in minrms_b200/batch.py).
-// K > 1 overlaps one pair's start-up (CUDA context, PDB parsing) with another pair's search.
+// the pairs shard over GPUs with no exchange: G x K worker processes (K per GPU, forked before any
+// CUDA call; K > 1 overlaps one pair's parsing, host-side fragment matching and Refine with
+// another pair's search), each taking a cost-balanced share of the pair list (largest first, to
+// the least loaded worker: the rule of minrms_b200/batch.py; cost = fragment pairs x Dyn3d cells)
+// and running main.cc's sequence with SearchOrCuda pair after pair -- the CUDA context and the
+// library's parked work space are reused from one pair to the next.
+// The reference's parser was written for one run per process: Biopolymer::Residue keeps the
+// names of the atoms used in a static table (lib/biopolymer/biopolymer.cc:166-200) to which a
+// second parse appends, shifting the atom ids; the table is emptied before every parse (see
+// BackboneTable below) once the previous pair's objects are gone.  ERR() ends a process
+// (ERR.h:20-21), so a pair the reference refuses takes its worker down: the parent notices,
+// reports the pair as failed and starts a new worker on the rest of that share.
 // The files of pair (A, B) are what `minrms [flags] A B` writes, in <out>/<A>__<B>/.
 //
 //   minrms_batch_cuda [minrms flags ...] -batch LIST [-batch-out DIR] [-batch-gpus G]
@@ -44,6 +49,19 @@ extern const char g_date_string[] = "<cuda batch>";
 using namespace minrms;
 
 namespace {
+
+// Access to the private static Biopolymer::Residue::backboneAtomLookup without touching the
+// reference's headers: an explicit template instantiation may name a private member
+// ([temp.spec]/6), and the friend function it defines hands the address out.
+struct BackboneTable {
+  typedef map<string, int>* type;
+  friend type get(BackboneTable);
+};
+template <typename Tag, typename Tag::type Member>
+struct Expose {
+  friend typename Tag::type get(Tag) { return Member; }
+};
+template struct Expose<BackboneTable, &Biopolymer::Residue::backboneAtomLookup>;
 
 struct Pair { int i, j; double cost; };
 
@@ -98,6 +116,7 @@ void RunPair(vector<string> const& flags, string const& a, string const& b, stri
   vArgs.push_back(a);
   vArgs.push_back(b);
   if (chdir(cwd.c_str()) != 0) ERR("Error: cannot change to \"" << cwd << "\"");  // atoms_used.txt etc. are read from here
+  get(BackboneTable())->clear();   // the parser registers the atoms used again, from id 0
   MinrmsParser settings(vArgs);
   if (vArgs.size() != 1) ERR("Error: Unrecognized command line option: \"" << vArgs[1] << "\"\n");
   OrientationGenerator og(settings);
@@ -169,56 +188,72 @@ int main(int argc, char** argv)
     }
   stable_sort(pairs.begin(), pairs.end(), [](Pair const& x, Pair const& y) { return x.cost > y.cost; });
   const int W = gpus * per_gpu;
+  vector<double> load(W, 0.0);
+  vector<vector<Pair> > share(W);
+  for (size_t k = 0; k < pairs.size(); ++k) {
+    int w = 0;
+    for (int c = 1; c < W; ++c) if (load[c] < load[w]) w = c;
+    share[w].push_back(pairs[k]);
+    load[w] += pairs[k].cost;
+  }
   cout << "minrms batch v" << g_version_string << ": " << structures.size() << " structures, " << pairs.size()
-       << " pairs, " << W << " slot(s) on " << gpus << " GPU(s)\n" << flush;
+       << " pairs, " << W << " worker(s) on " << gpus << " GPU(s)\n" << flush;
 
-  // List scheduling, largest pair first: whenever one of the W slots (slot w runs on GPU
-  // w % gpus) is free, the next pair of the list starts there in a process of its own.
   const double t0 = Now();
-  vector<pid_t> slot_pid(W, (pid_t)0);
-  vector<size_t> slot_pair(W, 0);
-  size_t next = 0, running = 0;
+  vector<pid_t> worker_pid(W, (pid_t)0);
+  vector<size_t> worker_from(W, 0);   // first pair of its share the current process of worker w was given
   int failed = 0;
-  while (next < pairs.size() || running > 0) {
-    for (int w = 0; w < W && next < pairs.size(); ++w) {
-      if (slot_pid[w] != 0) continue;
-      Pair const& p = pairs[next];
-      const string dir = out_abs + "/" + BaseName(structures[p.i]) + "__" + BaseName(structures[p.j]);
-      fflush(stdout);
-      const pid_t pid = fork();
-      if (pid < 0) ERR("Error: fork failed");
-      if (pid == 0) {
-        // the child's GPU: set before the first CUDA call of this process
-        char dev[16];
-        snprintf(dev, sizeof(dev), "%d", w % gpus);
-        if (gpus > 1 || !getenv("CUDA_VISIBLE_DEVICES")) setenv("CUDA_VISIBLE_DEVICES", dev, 1);
-        unsetenv("MINRMS_CUDA_GPUS");
+  size_t running = 0;
+  // worker w = GPU w % gpus; runs share[w][from...] in order, leaving <dir>/minrms.done behind each pair
+  auto pair_dir = [&](Pair const& p) { return out_abs + "/" + BaseName(structures[p.i]) + "__" + BaseName(structures[p.j]); };
+  auto spawn = [&](int w, size_t from) {
+    fflush(stdout);
+    const pid_t pid = fork();
+    if (pid < 0) ERR("Error: fork failed");
+    if (pid == 0) {
+      char dev[16];
+      snprintf(dev, sizeof(dev), "%d", w % gpus);   // set before the first CUDA call of this process
+      if (gpus > 1 || !getenv("CUDA_VISIBLE_DEVICES")) setenv("CUDA_VISIBLE_DEVICES", dev, 1);
+      unsetenv("MINRMS_CUDA_GPUS");
+      for (size_t k = from; k < share[w].size(); ++k) {
+        Pair const& p = share[w][k];
+        const string dir = pair_dir(p);
         mkdir(dir.c_str(), 0777);
         FILE* log = freopen((dir + "/minrms.log").c_str(), "w", stdout);   // the reference's progress output
         (void)log;
-        dup2(fileno(stdout), 2);   // and its warnings
+        dup2(fileno(stdout), 2);                                            // and its warnings
         RunPair(flags, structures[p.i], structures[p.j], dir, cwd);
         fflush(stdout);
-        _exit(0);
+        ofstream((dir + "/minrms.done").c_str()) << "done\n";
       }
-      slot_pid[w] = pid;
-      slot_pair[w] = next++;
-      ++running;
+      _exit(0);
     }
+    worker_pid[w] = pid;
+    worker_from[w] = from;
+    ++running;
+  };
+  for (int w = 0; w < W; ++w)
+    if (!share[w].empty()) spawn(w, 0);
+  while (running > 0) {
     int status = 0;
     const pid_t done = waitpid(-1, &status, 0);
     if (done <= 0) break;
     for (int w = 0; w < W; ++w) {
-      if (slot_pid[w] != done) continue;
-      Pair const& p = pairs[slot_pair[w]];
-      if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) {
+      if (worker_pid[w] != done) continue;
+      worker_pid[w] = 0;
+      --running;
+      if (WIFEXITED(status) && WEXITSTATUS(status) == 0) continue;
+      // the first pair without its marker is the one that ended the process
+      size_t k = worker_from[w];
+      while (k < share[w].size() && ifstream((pair_dir(share[w][k]) + "/minrms.done").c_str())) ++k;
+      if (k < share[w].size()) {
+        Pair const& p = share[w][k];
         ++failed;
         cerr << "pair " << BaseName(structures[p.i]) << " " << BaseName(structures[p.j]) << " FAILED ("
              << (WIFSIGNALED(status) ? "signal " : "exit status ")
              << (WIFSIGNALED(status) ? WTERMSIG(status) : WEXITSTATUS(status)) << "), see its minrms.log\n";
+        if (k + 1 < share[w].size()) spawn(w, k + 1);
       }
-      slot_pid[w] = 0;
-      --running;
     }
   }
   const double dt = Now() - t0;

@@ -115,10 +115,36 @@ def check_batch_against_pairwise_reference(batch_exe, ref_exe, workdir, extra=()
     return n_files
 
 
-def test_batch_driver_writes_what_pairwise_runs_write(hostcheck, tmp_path):
-    """minrms_b200/host/batch_cuda.cc (all-vs-all, one process per pair, list scheduling over
-    slots) against one run of the unmodified reference binary per pair"""
+@pytest.mark.parametrize("workers", [1, 3])
+def test_batch_driver_writes_what_pairwise_runs_write(workers, hostcheck, tmp_path):
+    """minrms_b200/host/batch_cuda.cc (all-vs-all: worker processes that run pair after pair, the
+    parser's static atom table emptied in between) against one run of the unmodified reference
+    binary per pair; with one worker all six pairs go through one process"""
     batch = os.path.join(os.path.dirname(hostcheck), "minrms_batch_hostcheck")
     n = check_batch_against_pairwise_reference(batch, os.path.join(STRICT, "minrms"), str(tmp_path),
-                                               ["-batch-workers-per-gpu", "3"])
+                                               ["-batch-workers-per-gpu", str(workers)])
     assert n > 100
+
+
+def test_batch_driver_survives_a_pair_the_reference_refuses(hostcheck, tmp_path):
+    """a structure too short for the fragment size makes the reference end the process (ERR):
+    the pairs with it are reported as failed, every other pair of the worker's share still runs"""
+    from make_msf_digests import digest_dir
+    work = str(tmp_path)
+    for f in BATCH_STRUCTURES[:3]:
+        subprocess.check_call(["cp", os.path.join(ROOT, "tests", "golden", f), work])
+    with open(os.path.join(work, "tiny.pdb"), "w") as f:      # two residues: no fragment of four
+        for k in range(2):
+            f.write("ATOM  %5d  %-3s %3s %1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n" % (k + 1, "CA", "GLY", "A", k + 1, 3.8 * k, 0.0, 0.0, 1.0, 0.0))
+        f.write("END\n")
+    with open(os.path.join(work, "list.txt"), "w") as f:
+        f.write("\n".join(BATCH_STRUCTURES[:2] + ["tiny.pdb", BATCH_STRUCTURES[2]]) + "\n")
+    batch = os.path.join(os.path.dirname(hostcheck), "minrms_batch_hostcheck")
+    r = subprocess.run([batch] + BATCH_FLAGS + ["-batch", "list.txt", "-batch-out", "out"], cwd=work,
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "3 pair(s) FAILED" in r.stdout, (r.stdout[-300:], r.stderr[-300:])
+    good = [d for d in os.listdir(os.path.join(work, "out")) if "tiny" not in d]
+    assert len(good) == 3
+    for d in good:
+        assert os.path.exists(os.path.join(work, "out", d, "minrms.done"))
+        assert len(digest_dir(os.path.join(work, "out", d))) > 10
