@@ -25,6 +25,21 @@ static void Check(mr_ctx* c, int rc)
   if (rc != 0) ERR("CUDA search failed: " << mr_last_error(c));  // ERR.h:20-21 -> exit(-1)
 }
 
+// Score columns of sizes row0 .. row0 + cols.size() - 1 out of the [count][R] array of
+// mr_search_scores: one sequential pass over the array per block of 16 sizes (a cache line of a
+// row) instead of a strided walk per size -- the array is 0.86 GB at config-3 size.
+static const int kScoreBlock = 16;
+static void GatherScoreColumns(vector<float> const& scores, long count, int R, int row0,
+                               vector<vector<float> >& cols)
+{
+  const int nrows = (int)cols.size();
+  for (int c = 0; c < nrows; ++c) cols[c].resize(count);
+  for (long o = 0; o < count; ++o) {
+    const float* src = &scores[(size_t)o * R + row0];
+    for (int c = 0; c < nrows; ++c) cols[c][o] = src[c];
+  }
+}
+
 SearchOrCuda::SearchOrCuda(SearchOrDyn3d::Settings const& s) : SearchOrDyn3d(s)
 {
   const int nb = Biopolymer::Residue::NumBackboneAtoms();
@@ -185,14 +200,20 @@ void SearchOrCuda::CalcAlternatesByPairs(OrientationGenerator const& og, long st
   const int nb = Biopolymer::Residue::NumBackboneAtoms();
   set<long> use_these_orientations;
   if (settings.alt_rmsd_tolerance != Settings::ALTERNATES_NOT_LIMITED_BY_RMSD) {
+    vector<vector<float> > cols;
     for (int n = n_min; n <= n_max; ++n) {
       const int row = n - n_min;
+      if (row % kScoreBlock == 0) {
+        cols.resize(min(kScoreBlock, R - row));
+        GatherScoreColumns(scores, stop - start, R, row, cols);
+      }
+      vector<float> const& column = cols[row % kScoreBlock];
       if (aaSumSqdDists[0][row] == DistanceMetric::UPPER_BOUND) continue;
       const Real best_rmsd = sqrt(aaSumSqdDists[0][row] / (n * nb));
       const Real tolerable_rmsd = settings.alt_rmsd_tolerance * best_rmsd;
       Real lowest_sum_sqd_dist_so_far = lowest_before[row];
       for (long o = start; o < stop; ++o) {
-        const Real sum_sqd_dist = scores[(size_t)(o - start) * R + row];
+        const Real sum_sqd_dist = column[o - start];
         if (!(sum_sqd_dist < DistanceMetric::UPPER_BOUND)) continue;
         if (sum_sqd_dist < lowest_sum_sqd_dist_so_far) lowest_sum_sqd_dist_so_far = sum_sqd_dist;
         if (!(sum_sqd_dist <= lowest_sum_sqd_dist_so_far * SQR(settings.alt_rmsd_tolerance))) continue;  // :493-497
@@ -264,15 +285,21 @@ void SearchOrCuda::CalcAlternates(OrientationGenerator const& og, long start, lo
   multimap<long, OrientationOwner> orientation_owners;
   vector<long> alt_ids(settings.num_solutions);
   vector<float> alt_mats((size_t)12 * settings.num_solutions);
+  vector<vector<float> > cols;
   for (int n = n_min; n <= n_max; ++n) {
     const int row = n - n_min;
+    if (row % kScoreBlock == 0) {
+      cols.resize(min(kScoreBlock, R - row));
+      GatherScoreColumns(scores, stop - start, R, row, cols);
+    }
+    vector<float> const& column = cols[row % kScoreBlock];
     if (aaSumSqdDists[0][row] == DistanceMetric::UPPER_BOUND) continue;  // :641
     vector<OrientationUsageInstance> vInstances;
     OrientationUsageInstance best_orientation;
     bool best_orientation_found = false;
     Real lowest_sum_sqd_dist_so_far = lowest_before[row];
     for (long o = start; o < stop; ++o) {
-      const Real sum_sqd_dist = scores[(size_t)(o - start) * R + row];
+      const Real sum_sqd_dist = column[o - start];
       if (!(sum_sqd_dist < DistanceMetric::UPPER_BOUND)) continue;  // never compared at this size
       if (sum_sqd_dist < lowest_sum_sqd_dist_so_far) lowest_sum_sqd_dist_so_far = sum_sqd_dist;  // :1825-1835
       if (!((sum_sqd_dist <= lowest_sum_sqd_dist_so_far * SQR(settings.alt_rmsd_tolerance)) || unlimited))
