@@ -53,6 +53,13 @@ def main():
     write_pdb(os.path.join(HERE, "synth_c.pdb"), A)
     write_pdb(os.path.join(HERE, "synth_d.pdb"), B)
     print("wrote synth_c.pdb (280 CA), synth_d.pdb (300 CA)")
+    # two short chains for the all-vs-all command line (with synth_bb1 / synth_bb2: six pairs)
+    rng = np.random.default_rng(50505)
+    A = random_chain(rng, 52, 1)
+    write_pdb(os.path.join(HERE, "synth_e.pdb"), np.round(A, 3))
+    B = related_chain(rng, A, 47, 1, noise=1.0)
+    write_pdb(os.path.join(HERE, "synth_f.pdb"), np.round(B, 3))
+    print("wrote synth_e.pdb (52 CA), synth_f.pdb (47 CA)")
 
 
 if __name__ == "__main__":
