@@ -42,6 +42,25 @@ def test_sass_is_sm100a():
     assert "sm_100a" in out
 
 
+def test_traceback_kernel_instances_and_registers():
+    """The FirstPass traceback / superposition kernel exists per layout (tiles, columns) in three
+    instances -- plain, emitting (payload, Refine) and with the common-pairs test of
+    mr_search_dissimilar -- and the two throughput instances stay at the 40 registers their
+    launch bounds (12 blocks of 128 threads per SM) allow: the -alt-r variant is a separate
+    instantiation, the FirstPass kernel is not touched by it."""
+    from minrms_b200 import _lib, build
+    build.build()
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    regs = {}
+    for fn, r in re.findall(r"Function (\S*k_traceback_kabsch\S*):\s*\n\s*REG:(\d+)", out):
+        layout = "tiles" if "TbTiled" in fn else "columns"
+        emit, excl = re.search(r"Lb([01])ELb([01])E", fn).groups()
+        regs[(layout, int(emit), int(excl))] = int(r)
+    for layout in ("tiles", "columns"):
+        assert regs[(layout, 0, 0)] <= 40 and regs[(layout, 0, 1)] <= 40, regs
+        assert (layout, 1, 0) in regs and (layout, 1, 1) not in regs, regs
+
+
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only check")
 def test_create_fails_loudly_without_gpu():
     from minrms_b200 import SearchOrCuda, Settings, MinrmsError
